@@ -1,0 +1,331 @@
+"""Host-side mirror of the reference's bilateral-grid interface over the sm_100a kernels.
+
+Same names, constructor arguments, state-dict keys and error behaviour as the reference
+(paths relative to /root/reference/project) so that released checkpoints load with
+``strict=True`` and the YAML dotted path ``model.Affine.type`` can point here:
+
+* ``BilateralGrid``, ``slice``, ``total_variation_loss``, ``color_affine_transform``
+  - ``bilateral/lib_bilagrid.py:135-230, 256-368``
+* ``BilateralAffineTransform`` - ``models/modules.py:275-351``
+* ``MultiScaleBilateralAffineTransform`` - ``models/modules.py:422-593``
+
+plus ``multiscale_bilateral(rgb, slots, sizes, factors)``: the fused slice + sequential apply
+(``models/trainers/scene_graph.py:112-117``) that never materialises the 12-channel full-resolution
+affine fields.  All arithmetic runs in ``libbds_b200.so``; there is no torch fallback.
+"""
+import ctypes as C
+from typing import List, Optional, Sequence
+
+import torch
+from torch import nn
+
+from . import _lib
+from ._lib import BilateralDesc, check, lib, ptr, ptr_array, require_cuda, stream_ptr
+
+
+def _workspace(desc, H, W, device):
+    nbytes = lib.bds_bilateral_workspace_bytes(C.byref(desc), H, W)
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+
+
+class _MSBilateralFn(torch.autograd.Function):
+    """rgb [H,W,3] + per-level grid slots [12,L,GY,GX] -> rgb_out [H,W,3] (+ affine fields)."""
+
+    @staticmethod
+    def forward(ctx, rgb, sizes, factors, want_affine, *slots):
+        require_cuda(rgb, *slots)
+        if rgb.dim() != 3 or rgb.shape[-1] != 3:
+            raise ValueError(f"rgb must be [H,W,3], got {tuple(rgb.shape)}")
+        H, W, _ = rgb.shape
+        desc = BilateralDesc.make(sizes, factors)
+        rgb_c = rgb.contiguous().float()
+        slots_c = [s.contiguous().float() for s in slots]
+        for s, (gx, gy, gl) in zip(slots_c, sizes):
+            if tuple(s.shape) != (12, gl, gy, gx):
+                raise ValueError(f"grid slot shape {tuple(s.shape)} != (12,{gl},{gy},{gx})")
+        out = torch.empty_like(rgb_c)
+        affines = [torch.empty(H, W, 12, device=rgb.device, dtype=torch.float32) for _ in slots] if want_affine else []
+        ws = _workspace(desc, H, W, rgb.device)
+        check(lib.bds_bilateral_fwd(C.byref(desc), H, W, ptr(rgb_c), ptr_array(slots_c), ptr(out),
+                                    ptr_array(affines) if want_affine else C.c_void_p(0), ptr(ws), stream_ptr()),
+              "bds_bilateral_fwd")
+        ctx.desc = desc
+        ctx.n_levels = len(slots)
+        ctx.want_affine = want_affine
+        ctx.save_for_backward(rgb_c, *slots_c)
+        if want_affine:
+            return (out, *[a.view(1, H, W, 3, 4) for a in affines])
+        return out
+
+    @staticmethod
+    def backward(ctx, v_out, *v_affines):
+        rgb_c, *slots_c = ctx.saved_tensors
+        H, W, _ = rgb_c.shape
+        v_out = v_out.contiguous().float() if v_out is not None else torch.zeros_like(rgb_c)
+        v_aff = None
+        if ctx.want_affine and any(v is not None for v in v_affines):
+            v_aff = [None if v is None else v.contiguous().float() for v in v_affines]
+        v_rgb = torch.empty_like(rgb_c)
+        v_slots = [torch.zeros_like(s) for s in slots_c]
+        ws = _workspace(ctx.desc, H, W, rgb_c.device)
+        check(lib.bds_bilateral_bwd(C.byref(ctx.desc), H, W, ptr(rgb_c), ptr_array(slots_c), ptr(v_out),
+                                    ptr_array(v_aff) if v_aff is not None else C.c_void_p(0), ptr(v_rgb),
+                                    ptr_array(v_slots), ptr(ws), stream_ptr()),
+              "bds_bilateral_bwd")
+        return (v_rgb, None, None, None, *v_slots)
+
+
+def multiscale_bilateral(rgb, slots: Sequence[torch.Tensor], sizes, factors=(4, 4, 2), return_affine=False):
+    """Fused multi-scale slice + sequential apply.  ``slots[l]`` is the image's grid ``[12,L,GY,GX]``
+    (``grids[idx]``, or the neighbour average at test time); ``sizes[l] = (grid_X, grid_Y, grid_W)``;
+    ``factors`` = the reference's ``guidance_factor`` (None = full-resolution guidance)."""
+    sizes = tuple(tuple(int(v) for v in s) for s in sizes)
+    factors = None if factors is None else tuple(int(f) for f in factors)
+    res = _MSBilateralFn.apply(rgb, sizes, factors, bool(return_affine), *slots)
+    if return_affine:
+        return res[0], list(res[1:])
+    return res
+
+
+class _SliceFn(torch.autograd.Function):
+    """Generic per-sample slice: xy [n,2], rgb [n,3], grid [12,L,GY,GX] -> affine [n,12]."""
+
+    @staticmethod
+    def forward(ctx, grid, xy, rgb):
+        require_cuda(grid, xy, rgb)
+        grid_c, xy_c, rgb_c = grid.contiguous().float(), xy.contiguous().float(), rgb.contiguous().float()
+        _, L, GY, GX = grid_c.shape
+        n = xy_c.shape[0]
+        out = torch.empty(n, 12, device=grid.device, dtype=torch.float32)
+        check(lib.bds_bilagrid_slice_fwd(ptr(grid_c), L, GY, GX, n, ptr(xy_c), ptr(rgb_c), ptr(out), stream_ptr()),
+              "bds_bilagrid_slice_fwd")
+        ctx.save_for_backward(grid_c, xy_c, rgb_c)
+        return out
+
+    @staticmethod
+    def backward(ctx, v_aff):
+        grid_c, xy_c, rgb_c = ctx.saved_tensors
+        _, L, GY, GX = grid_c.shape
+        n = xy_c.shape[0]
+        v_grid = torch.zeros_like(grid_c)
+        v_rgb = torch.zeros_like(rgb_c)
+        check(lib.bds_bilagrid_slice_bwd(ptr(grid_c), L, GY, GX, n, ptr(xy_c), ptr(rgb_c),
+                                         ptr(v_aff.contiguous().float()), ptr(v_grid), ptr(v_rgb), stream_ptr()),
+              "bds_bilagrid_slice_bwd")
+        return v_grid, None, v_rgb  # xy carries no gradient in the reference's use (lattice constants)
+
+
+class _TVFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, grids, weight):
+        require_cuda(grids)
+        g = grids.contiguous().float()
+        N, _, L, GY, GX = g.shape
+        loss = torch.zeros((), device=g.device, dtype=torch.float32)
+        check(lib.bds_tv_fwd_bwd(ptr(g), N, L, GY, GX, C.c_float(weight), C.c_float(0.0), ptr(loss), C.c_void_p(0),
+                                 stream_ptr()), "bds_tv_fwd_bwd")
+        ctx.save_for_backward(g)
+        ctx.weight = weight
+        return loss
+
+    @staticmethod
+    def backward(ctx, v_loss):
+        (g,) = ctx.saved_tensors
+        N, _, L, GY, GX = g.shape
+        v_g = torch.zeros_like(g)
+        scratch = torch.zeros((), device=g.device, dtype=torch.float32)
+        check(lib.bds_tv_fwd_bwd(ptr(g), N, L, GY, GX, C.c_float(ctx.weight), C.c_float(float(v_loss)),
+                                 ptr(scratch), ptr(v_g), stream_ptr()), "bds_tv_fwd_bwd")
+        return v_g, None
+
+
+def total_variation_loss(x, weight: float = 1.0):
+    """lib_bilagrid.py:152-168 for x of shape (B, 12, L, GY, GX)."""
+    if x.dim() != 5 or x.shape[1] != 12:
+        raise ValueError("total_variation_loss expects a (B,12,L,H,W) bilateral grid tensor")
+    return _TVFn.apply(x, float(weight))
+
+
+def color_affine_transform(affine_mats, rgb):
+    """lib_bilagrid.py:135-145 (plain torch glue; not on the fused path)."""
+    return torch.matmul(affine_mats[..., :3], rgb.unsqueeze(-1)).squeeze(-1) + affine_mats[..., 3]
+
+
+class BilateralGrid(nn.Module):
+    """lib_bilagrid.py:256-368.  Parameter ``grids`` (N,12,L,H,W), buffer ``rgb2gray_weight`` [1,3]."""
+
+    def __init__(self, num, grid_X=16, grid_Y=16, grid_W=8, mode="bilinear"):
+        super().__init__()
+        if mode != "bilinear":
+            raise NotImplementedError("only the reference's default mode='bilinear' is built")
+        self.grid_width, self.grid_height, self.grid_guidance, self.mode = grid_X, grid_Y, grid_W, mode
+        eye = torch.tensor([1.0, 0, 0, 0, 0, 1.0, 0, 0, 0, 0, 1.0, 0])
+        grid = eye.view(1, 12, 1, 1, 1).expand(num, 12, grid_W, grid_Y, grid_X).contiguous()
+        self.grids = nn.Parameter(grid)
+        self.register_buffer("rgb2gray_weight", torch.Tensor([[0.299, 0.587, 0.114]]))
+
+    @property
+    def size_xyl(self):
+        return (self.grid_width, self.grid_height, self.grid_guidance)
+
+    def tv_loss(self):
+        return total_variation_loss(self.grids)
+
+    def forward(self, grid_xy, rgb, idx=None):
+        """Slices with arbitrary xy in [0,1]; 2-D..5-D inputs as in the reference."""
+        nd = grid_xy.dim()
+        if rgb.dim() != nd:
+            raise AssertionError("grid_xy and rgb must have the same number of dims")
+        if 1 < nd < 5:
+            for _ in range(5 - nd):
+                grid_xy, rgb = grid_xy.unsqueeze(1), rgb.unsqueeze(1)
+            assert idx is not None
+        elif nd != 5:
+            raise ValueError("Bilateral grid slicing only takes either 2D, 3D, 4D and 5D inputs")
+        grids = self.grids if idx is None else self.grids[idx]
+        if grids.dim() == 4:
+            grids = grids[None]
+        assert grids.shape[0] == grid_xy.shape[0]
+        outs = []
+        for b in range(grids.shape[0]):
+            a = _SliceFn.apply(grids[b], grid_xy[b].reshape(-1, 2), rgb[b].reshape(-1, 3))
+            outs.append(a.reshape(*grid_xy.shape[1:-1], 3, 4))
+        affine = torch.stack(outs, 0)
+        for _ in range(5 - nd):
+            affine = affine.squeeze(1)
+        return affine
+
+
+def slice(bil_grids, xy, rgb, grid_idx):  # noqa: A001 - name mirrors the reference
+    """lib_bilagrid.py:171-230."""
+    sh_ = rgb.shape
+    grid_idx_unique = torch.unique(grid_idx)
+    if len(grid_idx_unique) == 1:
+        grid_idx = grid_idx_unique
+        xy, rgb = xy.unsqueeze(0), rgb.unsqueeze(0)
+    else:
+        if grid_idx.dim() == 4:
+            grid_idx = grid_idx[:, 0, 0, 0]
+        elif grid_idx.dim() == 3:
+            grid_idx = grid_idx[:, 0, 0]
+        elif grid_idx.dim() == 2:
+            grid_idx = grid_idx[:, 0]
+        else:
+            raise ValueError("The input to bilateral grid slicing is not supported yet.")
+    affine_mats = bil_grids(xy, rgb, grid_idx)
+    rgb = color_affine_transform(affine_mats, rgb)
+    return {
+        "rgb": rgb.reshape(*sh_),
+        "rgb_affine_mats": affine_mats.reshape(*sh_[:-1], affine_mats.shape[-2], affine_mats.shape[-1]),
+    }
+
+
+def _cam_index(image_infos) -> int:
+    assert "img_idx" in image_infos
+    if "img_idx_host" in image_infos:  # optional: avoids the device->host sync of modules.py:507
+        return int(image_infos["img_idx_host"])
+    return int(image_infos["img_idx"][0][0])
+
+
+class BilateralAffineTransform(nn.Module):
+    """models/modules.py:275-351 (single grid, full-resolution guidance)."""
+
+    def __init__(self, class_name, n, grid_X, grid_Y, grid_W, device="cuda"):
+        super().__init__()
+        self.bil_grids = BilateralGrid(num=n, grid_X=grid_X, grid_Y=grid_Y, grid_W=grid_W)
+        self.register_buffer("rgb2gray_weight", torch.Tensor([0.299, 0.587, 0.114]))
+        self.class_prefix = class_name + "#"
+        self.device = device
+        self.in_test_set = False
+
+    def tv_loss(self):
+        return total_variation_loss(self.bil_grids.grids)
+
+    def _slots(self, cam_idx):
+        if not self.in_test_set:
+            return [self.bil_grids.grids[cam_idx]]
+        near = self.training_indices_for_test[cam_idx]
+        return [torch.stack([self.bil_grids.grids[i] for i in near]).mean(0)]
+
+    def forward(self, rgb, image_infos):
+        cam_idx = _cam_index(image_infos)
+        _, aff = multiscale_bilateral(rgb, self._slots(cam_idx), [self.bil_grids.size_xyl], None, True)
+        return aff[0]
+
+    def transform(self, rgb, image_infos):
+        """Fused forward + apply of scene_graph.py:95-98."""
+        return multiscale_bilateral(rgb, self._slots(_cam_index(image_infos)), [self.bil_grids.size_xyl], None)
+
+    def get_param_groups(self):
+        return {self.class_prefix + "all": self.bil_grids.parameters()}
+
+
+def affine_to_homogeneous_batch(affine_matrices):
+    """models/modules.py:352-358."""
+    b, h, w, _, _ = affine_matrices.shape
+    hom = torch.zeros((b, h, w, 4, 4), device=affine_matrices.device)
+    hom[:, :, :, :3, :] = affine_matrices
+    hom[:, :, :, 3, 3] = 1
+    return hom
+
+
+class MultiScaleBilateralAffineTransform(nn.Module):
+    """models/modules.py:422-593.  ``forward`` keeps the reference's return value (a list of
+    [1,H,W,3,4] affine fields, also stored in ``save_matrix``); ``transform`` is the fused
+    slice + apply the drop-in trainer uses instead (no 100 MB-per-level fields)."""
+
+    def __init__(self, class_name, n, grid, device="cuda"):
+        super().__init__()
+        self.grid_size = grid
+        self.tv_weight = []
+        for i in range(len(self.grid_size)):
+            setattr(self, f"bil_grids{i}", BilateralGrid(num=n, grid_X=grid[i][0], grid_Y=grid[i][1], grid_W=grid[i][2]))
+            self.tv_weight.append(0.5 * (grid[i][0] * grid[i][1] * grid[i][2]) ** 0.5)
+        self.register_buffer("rgb2gray_weight", torch.Tensor([0.299, 0.587, 0.114]))
+        self.class_prefix = class_name + "#"
+        self.device = device
+        self.in_test_set = False
+        self.save_matrix = None
+
+    def _levels(self):
+        return [getattr(self, f"bil_grids{i}") for i in range(len(self.grid_size))]
+
+    def tv_loss(self):
+        loss = 0
+        for i, bg in enumerate(self._levels()):
+            loss = loss + total_variation_loss(bg.grids, self.tv_weight[i])
+        return loss
+
+    def _slots(self, image_infos):
+        cam_idx = _cam_index(image_infos)
+        if "img_idx" in image_infos and not self.in_test_set:
+            return [bg.grids[cam_idx] for bg in self._levels()]
+        near = self.training_indices_for_test[cam_idx]
+        # the mean over neighbour slices equals the slice of the mean grid (slicing is linear in the
+        # grid values at fixed coordinates): modules.py:523-538
+        return [torch.stack([bg.grids[i] for i in near]).mean(0) for bg in self._levels()]
+
+    def forward(self, rgb, image_infos, guidance_factor=[4, 4, 2]):  # noqa: B006 - reference signature
+        sizes = [bg.size_xyl for bg in self._levels()]
+        _, out_list = multiscale_bilateral(rgb, self._slots(image_infos), sizes, guidance_factor, True)
+        self.save_matrix = out_list
+        return out_list
+
+    def transform(self, rgb, image_infos, guidance_factor=[4, 4, 2]):  # noqa: B006
+        sizes = [bg.size_xyl for bg in self._levels()]
+        return multiscale_bilateral(rgb, self._slots(image_infos), sizes, guidance_factor)
+
+    def inverse_loss(self, gt, render):
+        """modules.py:474-492 (cycle loss on the saved affine fields)."""
+        shape = self.save_matrix[0].shape
+        B, H, W, _, _ = shape
+        mat = torch.eye(4, device=gt.device).view(1, 1, 1, 4, 4).repeat(1, H, W, 1, 1)
+        for arr in self.save_matrix:
+            mat = affine_to_homogeneous_batch(arr) @ mat
+        inverses = torch.inverse(mat.view(-1, 4, 4)).view(B, H, W, 4, 4)
+        inverse_affine = inverses[:, :, :, :3, :].reshape(gt.shape[0], gt.shape[1], 3, 4)
+        gt_t = (inverse_affine[..., :3, :3] @ gt[..., None] + inverse_affine[..., :3, 3:])[..., 0]
+        return torch.abs(gt_t - render).mean()
+
+    def get_param_groups(self):
+        return {f"{self.class_prefix}grid{i}": bg.parameters() for i, bg in enumerate(self._levels())}

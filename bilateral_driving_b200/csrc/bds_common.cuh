@@ -1,0 +1,74 @@
+// Shared helpers for the sm_100a kernels of libbds_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/bds.h"
+
+#define BDS_HD __host__ __device__ __forceinline__
+#define BDS_D __device__ __forceinline__
+
+namespace bds {
+
+void set_error(const char* fmt, ...);
+
+#define BDS_CHECK_CUDA(expr)                                                              \
+  do {                                                                                    \
+    cudaError_t err__ = (expr);                                                           \
+    if (err__ != cudaSuccess) {                                                           \
+      bds::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(err__)); \
+      return -2;                                                                          \
+    }                                                                                     \
+  } while (0)
+
+#define BDS_REQUIRE(cond, ...)        \
+  do {                                \
+    if (!(cond)) {                    \
+      bds::set_error(__VA_ARGS__);    \
+      return -1;                      \
+    }                                 \
+  } while (0)
+
+#define BDS_CHECK_LAUNCH() BDS_CHECK_CUDA(cudaGetLastError())
+
+static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+constexpr int kTile = BDS_TILE;
+constexpr float kAlphaMin = 1.0f / 255.0f;
+constexpr float kAlphaMax = 0.999f;
+constexpr float kTStop = 1e-4f;
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+
+// warp helpers ---------------------------------------------------------------------------------
+BDS_D float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+BDS_D unsigned lane_id() {
+  unsigned l;
+  asm volatile("mov.u32 %0, %%laneid;" : "=r"(l));
+  return l;
+}
+
+// streaming (read-once) 128-bit load / store that do not allocate in L1
+BDS_D float4 ld_stream_f4(const float4* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p));
+  return r;
+}
+BDS_D void st_stream_f4(float4* p, float4 v) {
+  asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y),
+               "f"(v.z), "f"(v.w));
+}
+
+// fire-and-forget fp32 reduction into global memory (RED.ADD.F32)
+BDS_D void red_add(float* p, float v) { atomicAdd(p, v); }
+
+}  // namespace bds

@@ -1,0 +1,474 @@
+// Stand-alone multi-scale bilateral-grid slice + sequential 3x4 apply, forward and backward.
+// This is the drop-in for the reference's MultiScaleBilateralAffineTransform.forward
+// (models/modules.py:505-584) + scene_graph.py:112-117 when it is NOT fused into the composite
+// kernel: default low-resolution guidance ([4,4,2]) and the guidance_factor=None branch.
+//
+// Kernels (all HBM/L2-bound gather / pointwise work; no tensor cores):
+//   repack_grid_kernel       [12,L,GY,GX] -> [L,GY,GX,12]                       (tiny)
+//   lowres_slice_fwd_kernel  per low-res pixel: bilinear-down guidance -> luma -> trilerp -> A_low
+//   apply_fwd_kernel         per pixel: A_l = up(A_low) or direct trilerp; x <- A_l x
+//   apply_bwd_kernel         per pixel: recompute chain; g_l; vA_l -> v_A_low (transposed up-sample)
+//                            or direct trilerp scatter (+ guidance gradient)
+//   lowres_slice_bwd_kernel  per low-res pixel: v_A_low -> v_grid, guidance gradient -> transposed
+//                            down-sample into v_rgb_in
+//   unpack_add_grid_kernel   v_grid_cl [L,GY,GX,12] += into the parameter-layout gradient slot
+#include "bilateral_math.cuh"
+
+namespace bds {
+
+__global__ void repack_grid_kernel(const float* __restrict__ cf, float* __restrict__ cl, int nodes) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;  // over nodes*12, channel fastest
+  if (i >= nodes * 12) return;
+  int node = i / 12, ch = i - node * 12;
+  cl[i] = cf[(size_t)ch * nodes + node];
+}
+
+__global__ void unpack_add_grid_kernel(const float* __restrict__ cl, float* __restrict__ cf, int nodes) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;  // over 12*nodes, node fastest (coalesced writes)
+  if (i >= nodes * 12) return;
+  int ch = i / nodes, node = i - ch * nodes;
+  cf[i] += cl[(size_t)node * 12 + ch];
+}
+
+// bilinear gather of the guidance RGB at low-res pixel (h, w)
+BDS_D void downsample_rgb(const float* __restrict__ rgb, int H, int W, const LinTap& ty, const LinTap& tx,
+                          float& r, float& g, float& b) {
+  const float* p00 = rgb + ((size_t)ty.i0 * W + tx.i0) * 3;
+  const float* p01 = rgb + ((size_t)ty.i0 * W + tx.i1) * 3;
+  const float* p10 = rgb + ((size_t)ty.i1 * W + tx.i0) * 3;
+  const float* p11 = rgb + ((size_t)ty.i1 * W + tx.i1) * 3;
+  float w0 = 1.f - tx.t, w1 = tx.t, h0 = 1.f - ty.t, h1 = ty.t;
+  r = h0 * (w0 * __ldg(p00) + w1 * __ldg(p01)) + h1 * (w0 * __ldg(p10) + w1 * __ldg(p11));
+  g = h0 * (w0 * __ldg(p00 + 1) + w1 * __ldg(p01 + 1)) + h1 * (w0 * __ldg(p10 + 1) + w1 * __ldg(p11 + 1));
+  b = h0 * (w0 * __ldg(p00 + 2) + w1 * __ldg(p01 + 2)) + h1 * (w0 * __ldg(p10 + 2) + w1 * __ldg(p11 + 2));
+}
+
+__global__ void __launch_bounds__(256) lowres_slice_fwd_kernel(const float* __restrict__ rgb, int H, int W,
+                                                               BilLevel lv, float* __restrict__ a_low) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= lv.Hd * lv.Wd) return;
+  int h = idx / lv.Wd, w = idx - h * lv.Wd;
+  LinTap ty = lin_src(h, H, lv.Hd), tx = lin_src(w, W, lv.Wd);
+  float r, g, b;
+  downsample_rgb(rgb, H, W, ty, tx, r, g, b);
+  float fx = lattice_coord(w, lv.Wd, lv.GX), fy = lattice_coord(h, lv.Hd, lv.GY);
+  float fz = luma_coord(luma_of(r, g, b), lv.L);
+  Tri t = tri_setup(fx, fy, fz, lv.L, lv.GY, lv.GX);
+  float A[12];
+  tri_fetch<false>(lv.grid_cl, t, A, nullptr);
+  float4* o = reinterpret_cast<float4*>(a_low + (size_t)idx * 12);
+  o[0] = make_float4(A[0], A[1], A[2], A[3]);
+  o[1] = make_float4(A[4], A[5], A[6], A[7]);
+  o[2] = make_float4(A[8], A[9], A[10], A[11]);
+}
+
+// full-res affine of one level at pixel (i, j)
+BDS_D void level_affine_fwd(const BilLevel& lv, int H, int W, int i, int j, float lum, float A[12]) {
+  if (lv.factor > 1) {
+    LinTap ty = lin_src(i, lv.Hd, H), tx = lin_src(j, lv.Wd, W);
+    float v00[12], v01[12], v10[12], v11[12];
+    load12(lv.a_low + ((size_t)ty.i0 * lv.Wd + tx.i0) * 12, v00);
+    load12(lv.a_low + ((size_t)ty.i0 * lv.Wd + tx.i1) * 12, v01);
+    load12(lv.a_low + ((size_t)ty.i1 * lv.Wd + tx.i0) * 12, v10);
+    load12(lv.a_low + ((size_t)ty.i1 * lv.Wd + tx.i1) * 12, v11);
+    float w0 = 1.f - tx.t, w1 = tx.t, h0 = 1.f - ty.t, h1 = ty.t;
+#pragma unroll
+    for (int k = 0; k < 12; ++k) A[k] = h0 * (w0 * v00[k] + w1 * v01[k]) + h1 * (w0 * v10[k] + w1 * v11[k]);
+  } else {
+    Tri t = tri_setup(lattice_coord(j, W, lv.GX), lattice_coord(i, H, lv.GY), luma_coord(lum, lv.L), lv.L,
+                      lv.GY, lv.GX);
+    tri_fetch<false>(lv.grid_cl, t, A, nullptr);
+  }
+}
+
+__global__ void __launch_bounds__(256) apply_fwd_kernel(const float* __restrict__ rgb_in, float* __restrict__ rgb_out,
+                                                        BilChain ch) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= ch.H * ch.W) return;
+  int i = idx / ch.W, j = idx - i * ch.W;
+  float r = rgb_in[(size_t)idx * 3], g = rgb_in[(size_t)idx * 3 + 1], b = rgb_in[(size_t)idx * 3 + 2];
+  float lum = luma_of(r, g, b);
+  for (int l = 0; l < ch.n_levels; ++l) {
+    float A[12];
+    level_affine_fwd(ch.lv[l], ch.H, ch.W, i, j, lum, A);
+    if (ch.lv[l].affine_out) {
+      float4* o = reinterpret_cast<float4*>(ch.lv[l].affine_out + (size_t)idx * 12);
+      o[0] = make_float4(A[0], A[1], A[2], A[3]);
+      o[1] = make_float4(A[4], A[5], A[6], A[7]);
+      o[2] = make_float4(A[8], A[9], A[10], A[11]);
+    }
+    affine_apply(A, r, g, b);
+  }
+  rgb_out[(size_t)idx * 3] = r;
+  rgb_out[(size_t)idx * 3 + 1] = g;
+  rgb_out[(size_t)idx * 3 + 2] = b;
+}
+
+__global__ void __launch_bounds__(256) apply_bwd_kernel(const float* __restrict__ rgb_in,
+                                                        const float* __restrict__ v_rgb_out,
+                                                        float* __restrict__ v_rgb_in, BilChain ch) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= ch.H * ch.W) return;
+  int i = idx / ch.W, j = idx - i * ch.W;
+  float r0 = rgb_in[(size_t)idx * 3], g0 = rgb_in[(size_t)idx * 3 + 1], b0 = rgb_in[(size_t)idx * 3 + 2];
+  float lum = luma_of(r0, g0, b0);
+  float A[BDS_MAX_LEVELS][12];
+  float xs[BDS_MAX_LEVELS][3];
+  float r = r0, g = g0, b = b0;
+#pragma unroll
+  for (int l = 0; l < BDS_MAX_LEVELS; ++l) {
+    if (l < ch.n_levels) {
+      xs[l][0] = r; xs[l][1] = g; xs[l][2] = b;
+      level_affine_fwd(ch.lv[l], ch.H, ch.W, i, j, lum, A[l]);
+      affine_apply(A[l], r, g, b);
+    }
+  }
+  float gr = v_rgb_out[(size_t)idx * 3], gg = v_rgb_out[(size_t)idx * 3 + 1], gb = v_rgb_out[(size_t)idx * 3 + 2];
+  float v_lum = 0.f;
+#pragma unroll
+  for (int l = BDS_MAX_LEVELS - 1; l >= 0; --l) {
+    if (l < ch.n_levels) {
+      const BilLevel& lv = ch.lv[l];
+      float vA[12];
+      if (lv.v_affine) {
+        load12(lv.v_affine + (size_t)idx * 12, vA);
+      } else {
+#pragma unroll
+        for (int k = 0; k < 12; ++k) vA[k] = 0.f;
+      }
+      float nr, ng, nb;
+      affine_apply_bwd(A[l], xs[l][0], xs[l][1], xs[l][2], gr, gg, gb, vA, nr, ng, nb);
+      gr = nr; gg = ng; gb = nb;
+      if (lv.factor > 1) {
+        // transposed bilinear up-sample: 4 taps x 12 channels
+        LinTap ty = lin_src(i, lv.Hd, ch.H), tx = lin_src(j, lv.Wd, ch.W);
+        float w0 = 1.f - tx.t, w1 = tx.t, h0 = 1.f - ty.t, h1 = ty.t;
+        float* p00 = lv.v_a_low + ((size_t)ty.i0 * lv.Wd + tx.i0) * 12;
+        float* p01 = lv.v_a_low + ((size_t)ty.i0 * lv.Wd + tx.i1) * 12;
+        float* p10 = lv.v_a_low + ((size_t)ty.i1 * lv.Wd + tx.i0) * 12;
+        float* p11 = lv.v_a_low + ((size_t)ty.i1 * lv.Wd + tx.i1) * 12;
+#pragma unroll
+        for (int k = 0; k < 12; ++k) {
+          red_add(p00 + k, h0 * w0 * vA[k]);
+          red_add(p01 + k, h0 * w1 * vA[k]);
+          red_add(p10 + k, h1 * w0 * vA[k]);
+          red_add(p11 + k, h1 * w1 * vA[k]);
+        }
+      } else {
+        Tri t = tri_setup(lattice_coord(j, ch.W, lv.GX), lattice_coord(i, ch.H, lv.GY), luma_coord(lum, lv.L),
+                          lv.L, lv.GY, lv.GX);
+        tri_scatter(lv.v_grid_cl, t, vA);
+        if (t.z_inside) {
+          float Ad[12], dAdz[12];
+          tri_fetch<true>(lv.grid_cl, t, Ad, dAdz);
+          float s = 0.f;
+#pragma unroll
+          for (int k = 0; k < 12; ++k) s = fmaf(vA[k], dAdz[k], s);
+          v_lum += s * (float)(lv.L - 1);
+        }
+      }
+    }
+  }
+  v_rgb_in[(size_t)idx * 3] = gr + v_lum * kLumaR;
+  v_rgb_in[(size_t)idx * 3 + 1] = gg + v_lum * kLumaG;
+  v_rgb_in[(size_t)idx * 3 + 2] = gb + v_lum * kLumaB;
+}
+
+__global__ void __launch_bounds__(256) lowres_slice_bwd_kernel(const float* __restrict__ rgb, int H, int W,
+                                                               BilLevel lv, float* __restrict__ v_rgb_in) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= lv.Hd * lv.Wd) return;
+  int h = idx / lv.Wd, w = idx - h * lv.Wd;
+  LinTap ty = lin_src(h, H, lv.Hd), tx = lin_src(w, W, lv.Wd);
+  float r, g, b;
+  downsample_rgb(rgb, H, W, ty, tx, r, g, b);
+  Tri t = tri_setup(lattice_coord(w, lv.Wd, lv.GX), lattice_coord(h, lv.Hd, lv.GY),
+                    luma_coord(luma_of(r, g, b), lv.L), lv.L, lv.GY, lv.GX);
+  float vA[12];
+  load12(lv.v_a_low + (size_t)idx * 12, vA);
+  tri_scatter(lv.v_grid_cl, t, vA);
+  if (t.z_inside) {
+    float Ad[12], dAdz[12];
+    tri_fetch<true>(lv.grid_cl, t, Ad, dAdz);
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 12; ++k) s = fmaf(vA[k], dAdz[k], s);
+    float v_lum = s * (float)(lv.L - 1);
+    float w0 = 1.f - tx.t, w1 = tx.t, h0 = 1.f - ty.t, h1 = ty.t;
+    const float lw[3] = {kLumaR, kLumaG, kLumaB};
+    float* p00 = v_rgb_in + ((size_t)ty.i0 * W + tx.i0) * 3;
+    float* p01 = v_rgb_in + ((size_t)ty.i0 * W + tx.i1) * 3;
+    float* p10 = v_rgb_in + ((size_t)ty.i1 * W + tx.i0) * 3;
+    float* p11 = v_rgb_in + ((size_t)ty.i1 * W + tx.i1) * 3;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float v = v_lum * lw[c];
+      red_add(p00 + c, h0 * w0 * v);
+      red_add(p01 + c, h0 * w1 * v);
+      red_add(p10 + c, h1 * w0 * v);
+      red_add(p11 + c, h1 * w1 * v);
+    }
+  }
+}
+
+// generic per-sample slice on the channel-first parameter layout (BilateralGrid.forward) ----------
+__global__ void slice_generic_fwd_kernel(const float* __restrict__ grid, int L, int GY, int GX, int n,
+                                         const float* __restrict__ xy, const float* __restrict__ rgb,
+                                         float* __restrict__ affine) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n) return;
+  float fx = unit_coord(xy[2 * (size_t)idx], GX), fy = unit_coord(xy[2 * (size_t)idx + 1], GY);
+  float fz = luma_coord(luma_of(rgb[3 * (size_t)idx], rgb[3 * (size_t)idx + 1], rgb[3 * (size_t)idx + 2]), L);
+  Tri t = tri_setup(fx, fy, fz, L, GY, GX);
+  int nodes = L * GY * GX;
+  float wx0 = 1.f - t.wx1, wy0 = 1.f - t.wy1, wz0 = 1.f - t.wz1;
+  for (int k = 0; k < 12; ++k) {
+    const float* g = grid + (size_t)k * nodes;
+    float c0 = wy0 * (wx0 * __ldg(g + t.n00) + t.wx1 * __ldg(g + t.n01)) +
+               t.wy1 * (wx0 * __ldg(g + t.n10) + t.wx1 * __ldg(g + t.n11));
+    float c1 = wy0 * (wx0 * __ldg(g + t.n00 + t.dz) + t.wx1 * __ldg(g + t.n01 + t.dz)) +
+               t.wy1 * (wx0 * __ldg(g + t.n10 + t.dz) + t.wx1 * __ldg(g + t.n11 + t.dz));
+    affine[(size_t)idx * 12 + k] = wz0 * c0 + t.wz1 * c1;
+  }
+}
+
+__global__ void slice_generic_bwd_kernel(const float* __restrict__ grid, int L, int GY, int GX, int n,
+                                         const float* __restrict__ xy, const float* __restrict__ rgb,
+                                         const float* __restrict__ v_affine, float* __restrict__ v_grid,
+                                         float* __restrict__ v_rgb) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n) return;
+  float fx = unit_coord(xy[2 * (size_t)idx], GX), fy = unit_coord(xy[2 * (size_t)idx + 1], GY);
+  float fz = luma_coord(luma_of(rgb[3 * (size_t)idx], rgb[3 * (size_t)idx + 1], rgb[3 * (size_t)idx + 2]), L);
+  Tri t = tri_setup(fx, fy, fz, L, GY, GX);
+  int nodes = L * GY * GX;
+  float wx0 = 1.f - t.wx1, wy0 = 1.f - t.wy1, wz0 = 1.f - t.wz1;
+  float s = 0.f;
+  for (int k = 0; k < 12; ++k) {
+    float va = v_affine[(size_t)idx * 12 + k];
+    const float* g = grid + (size_t)k * nodes;
+    float* vg = v_grid + (size_t)k * nodes;
+    float c0 = wy0 * (wx0 * __ldg(g + t.n00) + t.wx1 * __ldg(g + t.n01)) +
+               t.wy1 * (wx0 * __ldg(g + t.n10) + t.wx1 * __ldg(g + t.n11));
+    float c1 = wy0 * (wx0 * __ldg(g + t.n00 + t.dz) + t.wx1 * __ldg(g + t.n01 + t.dz)) +
+               t.wy1 * (wx0 * __ldg(g + t.n10 + t.dz) + t.wx1 * __ldg(g + t.n11 + t.dz));
+    s = fmaf(va, c1 - c0, s);
+    red_add(vg + t.n00, va * wz0 * wy0 * wx0);
+    red_add(vg + t.n01, va * wz0 * wy0 * t.wx1);
+    red_add(vg + t.n10, va * wz0 * t.wy1 * wx0);
+    red_add(vg + t.n11, va * wz0 * t.wy1 * t.wx1);
+    red_add(vg + t.n00 + t.dz, va * t.wz1 * wy0 * wx0);
+    red_add(vg + t.n01 + t.dz, va * t.wz1 * wy0 * t.wx1);
+    red_add(vg + t.n10 + t.dz, va * t.wz1 * t.wy1 * wx0);
+    red_add(vg + t.n11 + t.dz, va * t.wz1 * t.wy1 * t.wx1);
+  }
+  float v_lum = t.z_inside ? s * (float)(L - 1) : 0.f;
+  v_rgb[(size_t)idx * 3] = v_lum * kLumaR;
+  v_rgb[(size_t)idx * 3 + 1] = v_lum * kLumaG;
+  v_rgb[(size_t)idx * 3 + 2] = v_lum * kLumaB;
+}
+
+// TV loss (lib_bilagrid.py:152-168): sum over the 3 spatial axes of mean squared forward
+// differences, divided by the batch size N.  One thread per element; block reduction; one atomic.
+__global__ void __launch_bounds__(256) tv_kernel(const float* __restrict__ g, int N, int L, int GY, int GX,
+                                                 float weight, float v_loss, float* __restrict__ loss,
+                                                 float* __restrict__ v_g) {
+  size_t total = (size_t)N * 12 * L * GY * GX;
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  float acc = 0.f;
+  if (idx < total) {
+    int x = idx % GX;
+    size_t r = idx / GX;
+    int y = r % GY;
+    r /= GY;
+    int z = r % L;
+    float v = g[idx];
+    // counts = elements of one batch item of the differenced tensor (x1.size()[1:])
+    float cz = fmaxf(12.f * (L - 1) * GY * GX, 1.f), cy = fmaxf(12.f * L * (GY - 1) * GX, 1.f),
+          cx = fmaxf(12.f * L * GY * (GX - 1), 1.f);
+    float sN = weight / (float)N;
+    float grad = 0.f;
+    if (x + 1 < GX) { float d = g[idx + 1] - v; acc += d * d / cx; grad -= 2.f * d / cx; }
+    if (x > 0) { float d = v - g[idx - 1]; grad += 2.f * d / cx; }
+    if (y + 1 < GY) { float d = g[idx + GX] - v; acc += d * d / cy; grad -= 2.f * d / cy; }
+    if (y > 0) { float d = v - g[idx - GX]; grad += 2.f * d / cy; }
+    size_t sz = (size_t)GY * GX;
+    if (z + 1 < L) { float d = g[idx + sz] - v; acc += d * d / cz; grad -= 2.f * d / cz; }
+    if (z > 0) { float d = v - g[idx - sz]; grad += 2.f * d / cz; }
+    acc *= sN;
+    if (v_g) v_g[idx] += v_loss * sN * grad;
+  }
+  __shared__ float red[8];
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    float v = red[threadIdx.x];
+    for (int o = 4; o > 0; o >>= 1) v += __shfl_xor_sync(0xffu, v, o);
+    if (threadIdx.x == 0 && v != 0.f) red_add(loss, v);
+  }
+}
+
+// workspace carving ---------------------------------------------------------------------------------
+struct BilWorkspace {
+  size_t grid_cl[BDS_MAX_LEVELS], v_grid_cl[BDS_MAX_LEVELS], a_low[BDS_MAX_LEVELS], v_a_low[BDS_MAX_LEVELS];
+  size_t total;
+};
+static BilWorkspace carve(const bds_bilateral_desc* d, int H, int W) {
+  BilWorkspace w;
+  size_t off = 0;
+  for (int l = 0; l < d->n_levels; ++l) {
+    size_t gbytes = align_up((size_t)d->L[l] * d->GY[l] * d->GX[l] * 12 * sizeof(float), 256);
+    w.grid_cl[l] = off; off += gbytes;
+    w.v_grid_cl[l] = off; off += gbytes;
+    size_t abytes = 0;
+    if (d->factor[l] > 1) abytes = align_up((size_t)(H / d->factor[l]) * (W / d->factor[l]) * 12 * sizeof(float), 256);
+    w.a_low[l] = off; off += abytes;
+    w.v_a_low[l] = off; off += abytes;
+  }
+  w.total = off;
+  return w;
+}
+
+static int check_desc(const bds_bilateral_desc* d, int H, int W) {
+  BDS_REQUIRE(d && d->n_levels >= 1 && d->n_levels <= BDS_MAX_LEVELS, "bilateral: n_levels out of range");
+  BDS_REQUIRE(H > 0 && W > 0, "bilateral: empty image");
+  for (int l = 0; l < d->n_levels; ++l) {
+    BDS_REQUIRE(d->L[l] >= 1 && d->GY[l] >= 1 && d->GX[l] >= 1, "bilateral: bad grid size at level %d", l);
+    BDS_REQUIRE(d->factor[l] >= 0, "bilateral: negative guidance factor");
+    if (d->factor[l] > 1)
+      BDS_REQUIRE(H / d->factor[l] >= 1 && W / d->factor[l] >= 1, "bilateral: image smaller than guidance factor");
+  }
+  return 0;
+}
+
+static void fill_chain(BilChain& ch, const bds_bilateral_desc* d, int H, int W, char* ws, const BilWorkspace& w) {
+  ch.n_levels = d->n_levels;
+  ch.H = H;
+  ch.W = W;
+  for (int l = 0; l < d->n_levels; ++l) {
+    BilLevel& lv = ch.lv[l];
+    lv.grid_cl = reinterpret_cast<const float*>(ws + w.grid_cl[l]);
+    lv.v_grid_cl = reinterpret_cast<float*>(ws + w.v_grid_cl[l]);
+    lv.a_low = reinterpret_cast<const float*>(ws + w.a_low[l]);
+    lv.v_a_low = reinterpret_cast<float*>(ws + w.v_a_low[l]);
+    lv.affine_out = nullptr;
+    lv.v_affine = nullptr;
+    lv.L = d->L[l]; lv.GY = d->GY[l]; lv.GX = d->GX[l];
+    lv.factor = d->factor[l] > 1 ? d->factor[l] : 1;
+    lv.Hd = H / lv.factor; lv.Wd = W / lv.factor;
+  }
+}
+
+}  // namespace bds
+
+using namespace bds;
+
+extern "C" size_t bds_bilateral_workspace_bytes(const bds_bilateral_desc* d, int H, int W) {
+  if (!d || d->n_levels < 1 || d->n_levels > BDS_MAX_LEVELS) return 0;
+  return carve(d, H, W).total + 256;
+}
+
+extern "C" int bds_bilateral_fwd(const bds_bilateral_desc* d, int H, int W, const float* rgb_in,
+                                 const float* const* host_grids, float* rgb_out,
+                                 float* const* host_affine_out, void* workspace, bds_stream_t stream_) {
+  if (int rc = check_desc(d, H, W)) return rc;
+  BDS_REQUIRE(rgb_in && rgb_out && host_grids && workspace, "bilateral_fwd: null pointer");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  BilWorkspace w = carve(d, H, W);
+  BilChain ch;
+  fill_chain(ch, d, H, W, static_cast<char*>(workspace), w);
+  for (int l = 0; l < d->n_levels; ++l) {
+    BDS_REQUIRE(host_grids[l], "bilateral_fwd: null grid at level %d", l);
+    int nodes = d->L[l] * d->GY[l] * d->GX[l];
+    repack_grid_kernel<<<ceil_div(nodes * 12, 256), 256, 0, stream>>>(host_grids[l], const_cast<float*>(ch.lv[l].grid_cl), nodes);
+    BDS_CHECK_LAUNCH();
+    if (host_affine_out) ch.lv[l].affine_out = host_affine_out[l];
+  }
+  for (int l = 0; l < d->n_levels; ++l) {
+    if (ch.lv[l].factor > 1) {
+      lowres_slice_fwd_kernel<<<ceil_div((int64_t)ch.lv[l].Hd * ch.lv[l].Wd, 256), 256, 0, stream>>>(
+          rgb_in, H, W, ch.lv[l], const_cast<float*>(ch.lv[l].a_low));
+      BDS_CHECK_LAUNCH();
+    }
+  }
+  apply_fwd_kernel<<<ceil_div((int64_t)H * W, 256), 256, 0, stream>>>(rgb_in, rgb_out, ch);
+  BDS_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int bds_bilateral_bwd(const bds_bilateral_desc* d, int H, int W, const float* rgb_in,
+                                 const float* const* host_grids, const float* v_rgb_out,
+                                 const float* const* host_v_affine, float* v_rgb_in,
+                                 float* const* host_v_grids, void* workspace, bds_stream_t stream_) {
+  if (int rc = check_desc(d, H, W)) return rc;
+  BDS_REQUIRE(rgb_in && v_rgb_out && v_rgb_in && host_grids && host_v_grids && workspace,
+              "bilateral_bwd: null pointer");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  BilWorkspace w = carve(d, H, W);
+  BilChain ch;
+  fill_chain(ch, d, H, W, static_cast<char*>(workspace), w);
+  // the forward left grid_cl and a_low in the workspace; rebuild them anyway so that backward is
+  // self-contained (the workspace may have been reused) - both are tiny next to the image passes
+  for (int l = 0; l < d->n_levels; ++l) {
+    BDS_REQUIRE(host_grids[l] && host_v_grids[l], "bilateral_bwd: null grid at level %d", l);
+    int nodes = d->L[l] * d->GY[l] * d->GX[l];
+    repack_grid_kernel<<<ceil_div(nodes * 12, 256), 256, 0, stream>>>(host_grids[l], const_cast<float*>(ch.lv[l].grid_cl), nodes);
+    BDS_CHECK_LAUNCH();
+    BDS_CHECK_CUDA(cudaMemsetAsync(ch.lv[l].v_grid_cl, 0, (size_t)nodes * 12 * sizeof(float), stream));
+    if (ch.lv[l].factor > 1) {
+      size_t n_low = (size_t)ch.lv[l].Hd * ch.lv[l].Wd;
+      lowres_slice_fwd_kernel<<<ceil_div((int64_t)n_low, 256), 256, 0, stream>>>(rgb_in, H, W, ch.lv[l],
+                                                                                const_cast<float*>(ch.lv[l].a_low));
+      BDS_CHECK_LAUNCH();
+      BDS_CHECK_CUDA(cudaMemsetAsync(ch.lv[l].v_a_low, 0, n_low * 12 * sizeof(float), stream));
+    }
+    if (host_v_affine) ch.lv[l].v_affine = host_v_affine[l];
+  }
+  apply_bwd_kernel<<<ceil_div((int64_t)H * W, 256), 256, 0, stream>>>(rgb_in, v_rgb_out, v_rgb_in, ch);
+  BDS_CHECK_LAUNCH();
+  for (int l = 0; l < d->n_levels; ++l) {
+    if (ch.lv[l].factor > 1) {
+      lowres_slice_bwd_kernel<<<ceil_div((int64_t)ch.lv[l].Hd * ch.lv[l].Wd, 256), 256, 0, stream>>>(
+          rgb_in, H, W, ch.lv[l], v_rgb_in);
+      BDS_CHECK_LAUNCH();
+    }
+    int nodes = d->L[l] * d->GY[l] * d->GX[l];
+    unpack_add_grid_kernel<<<ceil_div(nodes * 12, 256), 256, 0, stream>>>(ch.lv[l].v_grid_cl, host_v_grids[l], nodes);
+    BDS_CHECK_LAUNCH();
+  }
+  return 0;
+}
+
+extern "C" int bds_bilagrid_slice_fwd(const float* grid, int L, int GY, int GX, int n, const float* xy,
+                                      const float* rgb, float* affine, bds_stream_t stream) {
+  BDS_REQUIRE(L >= 1 && GY >= 1 && GX >= 1 && n >= 0, "slice_fwd: bad sizes");
+  if (n == 0) return 0;
+  BDS_REQUIRE(grid && xy && rgb && affine, "slice_fwd: null pointer");
+  slice_generic_fwd_kernel<<<ceil_div(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(grid, L, GY, GX, n, xy, rgb, affine);
+  BDS_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int bds_bilagrid_slice_bwd(const float* grid, int L, int GY, int GX, int n, const float* xy,
+                                      const float* rgb, const float* v_affine, float* v_grid, float* v_rgb,
+                                      bds_stream_t stream) {
+  BDS_REQUIRE(L >= 1 && GY >= 1 && GX >= 1 && n >= 0, "slice_bwd: bad sizes");
+  if (n == 0) return 0;
+  BDS_REQUIRE(grid && xy && rgb && v_affine && v_grid && v_rgb, "slice_bwd: null pointer");
+  slice_generic_bwd_kernel<<<ceil_div(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(grid, L, GY, GX, n, xy, rgb,
+                                                                                          v_affine, v_grid, v_rgb);
+  BDS_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int bds_tv_fwd_bwd(const float* grids, int N, int L, int GY, int GX, float weight, float v_loss,
+                              float* loss, float* v_grids, bds_stream_t stream) {
+  BDS_REQUIRE(N >= 1 && L >= 1 && GY >= 1 && GX >= 1, "tv: bad sizes");
+  BDS_REQUIRE(grids && loss, "tv: null pointer");
+  size_t total = (size_t)N * 12 * L * GY * GX;
+  tv_kernel<<<ceil_div((int64_t)total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(grids, N, L, GY, GX, weight, v_loss,
+                                                                                        loss, v_grids);
+  BDS_CHECK_LAUNCH();
+  return 0;
+}

@@ -1,0 +1,192 @@
+// Per-pixel arithmetic of the multi-scale bilateral-grid chain, shared by the stand-alone
+// bilateral kernels (bilateral.cu) and the fused composite epilogue (composite.cu).
+//
+// Semantics follow the reference (paths relative to /root/reference/project):
+//   bilateral/lib_bilagrid.py:317-368   xy in [0,1] -> [-1,1], z = luma*2-1, F.grid_sample 5-D
+//                                       trilinear, align_corners=True, padding_mode="border",
+//                                       channel c = 4*row + col of the 3x4 affine
+//   models/modules.py:494-504, 409-420  bilinear resize, align_corners=False (low-res guidance)
+//   models/trainers/scene_graph.py:112-117   x <- A[:, :3] x + A[:, 3], level after level
+//
+// Grids are read in a channel-LAST repack [L][GY][GX][12] (three float4 per lattice node) that the
+// host entry points build from the reference's channel-first [12][L][GY][GX] parameter slot.
+#pragma once
+#include "bds_common.cuh"
+
+namespace bds {
+
+constexpr float kLumaR = 0.299f, kLumaG = 0.587f, kLumaB = 0.114f;
+
+// torch bilinear (align_corners=False) source taps: models/modules.py:497, :414-419
+struct LinTap {
+  int i0, i1;
+  float t;
+};
+BDS_HD LinTap lin_src(int d, int in_size, int out_size) {
+  LinTap r;
+  float scale = (float)in_size / (float)out_size;
+  float s = scale * ((float)d + 0.5f) - 0.5f;
+  if (s < 0.f) s = 0.f;
+  int i0 = (int)s;
+  if (i0 > in_size - 1) i0 = in_size - 1;
+  r.i0 = i0;
+  r.i1 = i0 + (i0 < in_size - 1 ? 1 : 0);
+  r.t = s - (float)i0;
+  return r;
+}
+
+// torch.linspace(0, 1, n)[j] in fp32 (symmetric evaluation, as ATen does)
+BDS_HD float lin01(int j, int n) {
+  if (n <= 1) return 0.f;
+  float step = 1.0f / (float)(n - 1);
+  return (j < n / 2) ? step * (float)j : 1.0f - step * (float)(n - 1 - j);
+}
+
+// lattice coordinate -> voxel units, as BilateralGrid.forward + grid_sampler_unnormalize do
+BDS_HD float lattice_coord(int j, int n, int gsize) {
+  float x = lin01(j, n);
+  float xn = (x - 0.5f) * 2.0f;
+  return ((xn + 1.0f) * 0.5f) * (float)(gsize - 1);
+}
+BDS_HD float unit_coord(float x01, int gsize) {
+  float xn = (x01 - 0.5f) * 2.0f;
+  return ((xn + 1.0f) * 0.5f) * (float)(gsize - 1);
+}
+BDS_HD float luma_of(float r, float g, float b) { return r * kLumaR + g * kLumaG + b * kLumaB; }
+BDS_HD float luma_coord(float luma, int L) {
+  float z = luma * 2.0f - 1.0f;
+  return ((z + 1.0f) * 0.5f) * (float)(L - 1);
+}
+
+// Trilinear set-up with border clamping.  Offsets are in lattice NODES of the [L][GY][GX] repack.
+struct Tri {
+  int n00, n01, n10, n11;  // (y0,x0) (y0,x1) (y1,x0) (y1,x1) node offsets inside slab z0
+  int dz;                  // node offset from slab z0 to slab z1 (0 when clamped)
+  float wx1, wy1, wz1;     // upper weights; lower = 1 - upper
+  bool z_inside;           // 0 < fz < L-1 (strict): guidance gradient flows
+};
+BDS_HD Tri tri_setup(float fx, float fy, float fz, int L, int GY, int GX) {
+  Tri t;
+  t.z_inside = (fz > 0.f) && (fz < (float)(L - 1));
+  fx = fminf(fmaxf(fx, 0.f), (float)(GX - 1));
+  fy = fminf(fmaxf(fy, 0.f), (float)(GY - 1));
+  fz = fminf(fmaxf(fz, 0.f), (float)(L - 1));
+  int x0 = (int)floorf(fx), y0 = (int)floorf(fy), z0 = (int)floorf(fz);
+  t.wx1 = fx - (float)x0;
+  t.wy1 = fy - (float)y0;
+  t.wz1 = fz - (float)z0;
+  int x1 = x0 + 1 < GX ? x0 + 1 : x0;  // weight of the clamped corner is exactly 0
+  int y1 = y0 + 1 < GY ? y0 + 1 : y0;
+  int z1 = z0 + 1 < L ? z0 + 1 : z0;
+  int base = (z0 * GY) * GX;
+  t.n00 = base + y0 * GX + x0;
+  t.n01 = base + y0 * GX + x1;
+  t.n10 = base + y1 * GX + x0;
+  t.n11 = base + y1 * GX + x1;
+  t.dz = (z1 - z0) * GY * GX;
+  return t;
+}
+
+#ifdef __CUDACC__
+BDS_D void load12(const float* p, float v[12]) {
+  const float4* q = reinterpret_cast<const float4*>(p);
+  float4 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+  v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  v[8] = c.x; v[9] = c.y; v[10] = c.z; v[11] = c.w;
+}
+
+// A = trilerp(grid)(t); optionally dA/dfz (slab difference, xy-interpolated)
+template <bool WITH_DZ>
+BDS_D void tri_fetch(const float* __restrict__ g, const Tri& t, float A[12], float dAdz[12]) {
+  float w00 = (1.f - t.wx1) * (1.f - t.wy1), w01 = t.wx1 * (1.f - t.wy1);
+  float w10 = (1.f - t.wx1) * t.wy1, w11 = t.wx1 * t.wy1;
+  float c0[12], c1[12], v[12];
+  load12(g + 12 * t.n00, v);
+#pragma unroll
+  for (int k = 0; k < 12; ++k) c0[k] = w00 * v[k];
+  load12(g + 12 * t.n01, v);
+#pragma unroll
+  for (int k = 0; k < 12; ++k) c0[k] = fmaf(w01, v[k], c0[k]);
+  load12(g + 12 * t.n10, v);
+#pragma unroll
+  for (int k = 0; k < 12; ++k) c0[k] = fmaf(w10, v[k], c0[k]);
+  load12(g + 12 * t.n11, v);
+#pragma unroll
+  for (int k = 0; k < 12; ++k) c0[k] = fmaf(w11, v[k], c0[k]);
+  load12(g + 12 * (t.n00 + t.dz), v);
+#pragma unroll
+  for (int k = 0; k < 12; ++k) c1[k] = w00 * v[k];
+  load12(g + 12 * (t.n01 + t.dz), v);
+#pragma unroll
+  for (int k = 0; k < 12; ++k) c1[k] = fmaf(w01, v[k], c1[k]);
+  load12(g + 12 * (t.n10 + t.dz), v);
+#pragma unroll
+  for (int k = 0; k < 12; ++k) c1[k] = fmaf(w10, v[k], c1[k]);
+  load12(g + 12 * (t.n11 + t.dz), v);
+#pragma unroll
+  for (int k = 0; k < 12; ++k) c1[k] = fmaf(w11, v[k], c1[k]);
+#pragma unroll
+  for (int k = 0; k < 12; ++k) {
+    A[k] = fmaf(t.wz1, c1[k] - c0[k], c0[k]);
+    if (WITH_DZ) dAdz[k] = c1[k] - c0[k];
+  }
+}
+
+// scatter w * vA into the 8 nodes (global fp32 reductions)
+BDS_D void tri_scatter(float* __restrict__ vg, const Tri& t, const float vA[12]) {
+  float wx0 = 1.f - t.wx1, wy0 = 1.f - t.wy1, wz0 = 1.f - t.wz1;
+  const int nodes[4] = {t.n00, t.n01, t.n10, t.n11};
+  const float wxy[4] = {wx0 * wy0, t.wx1 * wy0, wx0 * t.wy1, t.wx1 * t.wy1};
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    float w0 = wxy[c] * wz0, w1 = wxy[c] * t.wz1;
+    float* p0 = vg + 12 * nodes[c];
+    float* p1 = vg + 12 * (nodes[c] + t.dz);
+    if (w0 != 0.f) {
+#pragma unroll
+      for (int k = 0; k < 12; ++k) red_add(p0 + k, w0 * vA[k]);
+    }
+    if (w1 != 0.f) {
+#pragma unroll
+      for (int k = 0; k < 12; ++k) red_add(p1 + k, w1 * vA[k]);
+    }
+  }
+}
+#endif  // __CUDACC__
+
+// x <- A[:, :3] x + A[:, 3]
+BDS_HD void affine_apply(const float A[12], float& r, float& g, float& b) {
+  float nr = A[0] * r + A[1] * g + A[2] * b + A[3];
+  float ng = A[4] * r + A[5] * g + A[6] * b + A[7];
+  float nb = A[8] * r + A[9] * g + A[10] * b + A[11];
+  r = nr; g = ng; b = nb;
+}
+// cotangents: vA += gout (x) [x;1];  gin = A[:, :3]^T gout
+BDS_HD void affine_apply_bwd(const float A[12], float xr, float xg, float xb, float gr, float gg,
+                             float gb, float vA[12], float& or_, float& og, float& ob) {
+  vA[0] += gr * xr; vA[1] += gr * xg; vA[2] += gr * xb; vA[3] += gr;
+  vA[4] += gg * xr; vA[5] += gg * xg; vA[6] += gg * xb; vA[7] += gg;
+  vA[8] += gb * xr; vA[9] += gb * xg; vA[10] += gb * xb; vA[11] += gb;
+  or_ = A[0] * gr + A[4] * gg + A[8] * gb;
+  og = A[1] * gr + A[5] * gg + A[9] * gb;
+  ob = A[2] * gr + A[6] * gg + A[10] * gb;
+}
+
+// Device-side description of one level / the whole chain ------------------------------------------
+struct BilLevel {
+  const float* grid_cl;  // [L][GY][GX][12] repack
+  float* v_grid_cl;      // same shape, accumulated
+  const float* a_low;    // [Hd][Wd][12] low-res affine field (factor > 1)
+  float* v_a_low;        // same shape, accumulated
+  float* affine_out;     // optional full-res [H][W][12]
+  const float* v_affine; // optional cotangent on affine_out
+  int L, GY, GX, factor, Hd, Wd;
+};
+struct BilChain {
+  int n_levels;
+  int H, W;
+  BilLevel lv[BDS_MAX_LEVELS];
+};
+
+}  // namespace bds

@@ -1,0 +1,28 @@
+"""CPU: the C-ABI library loads and exports every symbol include/bds.h declares."""
+import os
+import re
+
+
+def test_library_loads_and_exports_all_symbols():
+    from bilateral_driving_b200 import _lib
+
+    assert _lib.lib.bds_abi_version() == 1
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    header = open(os.path.join(root, "include", "bds.h")).read()
+    declared = set(re.findall(r"\b(bds_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(_lib.ABI_SYMBOLS), declared ^ set(_lib.ABI_SYMBOLS)
+    for name in declared:
+        assert hasattr(_lib.lib, name), f"{name} not exported by libbds_b200.so"
+
+
+def test_ops_fail_loudly_without_cuda():
+    import pytest
+    import torch
+
+    from bilateral_driving_b200._lib import BdsError
+    from bilateral_driving_b200.bilateral import multiscale_bilateral
+
+    if torch.cuda.is_available():
+        pytest.skip("CPU-only check")
+    with pytest.raises(BdsError):
+        multiscale_bilateral(torch.rand(8, 8, 3), [torch.zeros(12, 1, 2, 2)], [(2, 2, 1)], None)
