@@ -79,12 +79,12 @@ def test_against_oracle(H, W, gf):
     big = H * W > 500_000
     # oracle (fp32 on CPU; fp64 for the small cases)
     dt = torch.float32 if big else torch.float64
-    o_rgb = rgb.to(dt).requires_grad_(True)
-    o_grids = [g.to(dt).requires_grad_(True) for g in grids]
+    o_rgb = rgb.detach().clone().to(dt).requires_grad_(True)
+    o_grids = [g.detach().clone().to(dt).requires_grad_(True) for g in grids]
     o_y = B.multiscale_forward(o_grids, o_rgb, gf)
     (o_y * G.to(dt)).sum().backward()
-    c_rgb = rgb.cuda().requires_grad_(True)
-    c_grids = [g.cuda().requires_grad_(True) for g in grids]
+    c_rgb = rgb.detach().clone().cuda().requires_grad_(True)
+    c_grids = [g.detach().clone().cuda().requires_grad_(True) for g in grids]
     c_y = multiscale_bilateral(c_rgb, c_grids, sizes, gf)
     (c_y * G.cuda()).sum().backward()
     assert (c_y.detach().cpu() - o_y.detach().float()).abs().max() < 1e-5
