@@ -1,6 +1,7 @@
 // Shared helpers for the sm_100a kernels of libbds_b200.so.
 #pragma once
 #include <cuda_runtime.h>
+#include <math.h>
 #include <stdint.h>
 #include <stdio.h>
 
@@ -42,6 +43,7 @@ constexpr float kTStop = 1e-4f;
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 
+#ifdef __CUDACC__
 // warp helpers ---------------------------------------------------------------------------------
 BDS_D float warp_sum(float v) {
 #pragma unroll
@@ -70,5 +72,6 @@ BDS_D void st_stream_f4(float4* p, float4 v) {
 
 // fire-and-forget fp32 reduction into global memory (RED.ADD.F32)
 BDS_D void red_add(float* p, float v) { atomicAdd(p, v); }
+#endif  // __CUDACC__
 
 }  // namespace bds

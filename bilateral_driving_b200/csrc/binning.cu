@@ -1,0 +1,411 @@
+// Tile binning: exclusive scan of per-(camera, Gaussian) tile counts, emission of
+// (band tile | fp32 depth bits) keys in Gaussian-id order, a stable LSD radix sort written for this
+// library (no CUB / thrust), per-tile start offsets and the gather of the packed 48-byte splat
+// records into sorted order so that the composite kernels read contiguous chunks (TMA bulk copies).
+//
+// Replaces gsplat's isect_tiles + torch.cumsum + cub::DeviceRadixSort + isect_offset_encode for the
+// reference call at models/trainers/base.py:393-408.  Ordering contract = gsplat's: ascending
+// (camera, tile, depth bits), ties in Gaussian-id order (stable sort over id-ordered emission).
+//
+// All kernels are HBM-bound integer / copy work: coalesced loads, grid sized to the data.
+#include "projection_math.cuh"
+
+namespace bds {
+
+// band helpers shared with projection.cu (same arithmetic, kept local to avoid a link dependency)
+BDS_HD void band_rows2(const bds_render_desc& d, int tile_h, int c, int& ty0, int& ty1) {
+  int g0 = c * tile_h, g1 = g0 + tile_h;
+  int lo = d.row_begin > g0 ? d.row_begin : g0;
+  int hi = d.row_end < g1 ? d.row_end : g1;
+  if (hi <= lo) { ty0 = ty1 = 0; return; }
+  ty0 = lo - g0;
+  ty1 = hi - g0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// exclusive scan (reduce-then-scan, 3 kernels, no spin-waits): TIn -> int64 prefix
+// ---------------------------------------------------------------------------------------------
+constexpr int kScanThreads = 256;
+constexpr int kScanItems = 16;
+constexpr int kScanTile = kScanThreads * kScanItems;  // 4096 elements per block
+
+template <typename T>
+BDS_D T block_exclusive_scan(T v, T* smem /*[kScanThreads/32]*/, T& block_total) {
+  // warp inclusive scan
+  int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  T inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    T t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) smem[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    T w = lane < kScanThreads / 32 ? smem[lane] : T(0);
+    T winc = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      T t = __shfl_up_sync(0xffffffffu, winc, o);
+      if (lane >= o) winc += t;
+    }
+    if (lane < kScanThreads / 32) smem[lane] = winc - w;  // exclusive warp offsets
+    if (lane == kScanThreads / 32 - 1) smem[kScanThreads / 32] = winc;
+  }
+  __syncthreads();
+  T res = smem[warp] + inc - v;
+  block_total = smem[kScanThreads / 32];
+  __syncthreads();
+  return res;
+}
+
+template <typename TIn>
+__global__ void __launch_bounds__(kScanThreads) scan_reduce_kernel(const TIn* __restrict__ in, int64_t n,
+                                                                   int64_t* __restrict__ block_sums) {
+  __shared__ int64_t sm[kScanThreads / 32 + 1];
+  int64_t base = (int64_t)blockIdx.x * kScanTile;
+  int64_t acc = 0;
+#pragma unroll
+  for (int k = 0; k < kScanItems; ++k) {
+    int64_t i = base + (int64_t)k * kScanThreads + threadIdx.x;
+    if (i < n) acc += (int64_t)in[i];
+  }
+  int64_t tot;
+  block_exclusive_scan<int64_t>(acc, sm, tot);
+  if (threadIdx.x == 0) block_sums[blockIdx.x] = tot;
+}
+
+// single block: exclusive scan of block_sums in place; total written to *total
+__global__ void __launch_bounds__(kScanThreads) scan_spine_kernel(int64_t* __restrict__ block_sums, int nblocks,
+                                                                  int64_t* __restrict__ total) {
+  __shared__ int64_t sm[kScanThreads / 32 + 1];
+  int64_t carry = 0;
+  for (int base = 0; base < nblocks; base += kScanThreads) {
+    int i = base + threadIdx.x;
+    int64_t v = i < nblocks ? block_sums[i] : 0;
+    int64_t tot;
+    int64_t ex = block_exclusive_scan<int64_t>(v, sm, tot);
+    if (i < nblocks) block_sums[i] = carry + ex;
+    carry += tot;
+  }
+  if (threadIdx.x == 0 && total) *total = carry;
+}
+
+template <typename TIn, typename TOut>
+__global__ void __launch_bounds__(kScanThreads) scan_apply_kernel(const TIn* __restrict__ in, int64_t n,
+                                                                  const int64_t* __restrict__ block_sums,
+                                                                  TOut* __restrict__ out) {
+  __shared__ int64_t sm[kScanThreads / 32 + 1];
+  // blocked arrangement: thread t owns items [t*kScanItems, (t+1)*kScanItems)
+  int64_t base = (int64_t)blockIdx.x * kScanTile + (int64_t)threadIdx.x * kScanItems;
+  int64_t vals[kScanItems];
+  int64_t acc = 0;
+#pragma unroll
+  for (int k = 0; k < kScanItems; ++k) {
+    int64_t i = base + k;
+    vals[k] = i < n ? (int64_t)in[i] : 0;
+    acc += vals[k];
+  }
+  int64_t tot;
+  int64_t ex = block_exclusive_scan<int64_t>(acc, sm, tot) + block_sums[blockIdx.x];
+#pragma unroll
+  for (int k = 0; k < kScanItems; ++k) {
+    int64_t i = base + k;
+    if (i < n) out[i] = (TOut)ex;
+    ex += vals[k];
+  }
+}
+
+static size_t scan_workspace_bytes(int64_t n) { return align_up((size_t)(ceil_div(n, kScanTile) + 1) * sizeof(int64_t), 256); }
+
+template <typename TIn, typename TOut>
+static int exclusive_scan(const TIn* in, TOut* out, int64_t n, int64_t* total_dev, void* ws, cudaStream_t stream) {
+  int nblocks = ceil_div(n, kScanTile);
+  int64_t* sums = static_cast<int64_t*>(ws);
+  if (n == 0) {
+    if (total_dev) BDS_CHECK_CUDA(cudaMemsetAsync(total_dev, 0, sizeof(int64_t), stream));
+    return 0;
+  }
+  scan_reduce_kernel<TIn><<<nblocks, kScanThreads, 0, stream>>>(in, n, sums);
+  BDS_CHECK_LAUNCH();
+  scan_spine_kernel<<<1, kScanThreads, 0, stream>>>(sums, nblocks, total_dev);
+  BDS_CHECK_LAUNCH();
+  scan_apply_kernel<TIn, TOut><<<nblocks, kScanThreads, 0, stream>>>(in, n, sums, out);
+  BDS_CHECK_LAUNCH();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// key emission: one thread per (camera, Gaussian) with tiles_touched > 0
+// ---------------------------------------------------------------------------------------------
+struct EmitParams {
+  bds_render_desc d;
+  int tile_w, tile_h;
+  const int32_t* radii;
+  const int32_t* slot_of;
+  const int32_t* tiles_touched;
+  int n_tiles;
+  const int64_t* offsets;
+  const float* splats;
+  uint64_t* keys;
+  uint32_t* vals;
+};
+
+__global__ void __launch_bounds__(256) emit_keys_kernel(EmitParams p) {
+  const int N = p.d.n_gauss;
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)N * p.d.n_cams) return;
+  int slot = p.slot_of[idx];
+  if (slot < 0) return;
+  int c = (int)(idx / N);
+  int ty0, ty1;
+  band_rows2(p.d, p.tile_h, c, ty0, ty1);
+  const float4* rp = reinterpret_cast<const float4*>(p.splats + (size_t)slot * 12);
+  float4 r0 = __ldg(rp), r1 = __ldg(rp + 1), r2 = __ldg(rp + 2);
+  float radius = (float)p.radii[idx];
+  // same rectangle + same hit test as the counting pass in project_fwd_kernel
+  float tr = radius / (float)kTile, txf = r0.x / (float)kTile, tyf = r0.y / (float)kTile;
+  int x0 = (int)fminf(fmaxf(floorf(txf - tr), 0.f), (float)p.tile_w);
+  int x1 = (int)fminf(fmaxf(ceilf(txf + tr), 0.f), (float)p.tile_w);
+  int y0 = (int)fminf(fmaxf(floorf(tyf - tr), 0.f), (float)p.tile_h);
+  int y1 = (int)fminf(fmaxf(ceilf(tyf + tr), 0.f), (float)p.tile_h);
+  if (y0 < ty0) y0 = ty0;
+  if (y1 > ty1) y1 = ty1;
+  uint64_t depth_bits = (uint64_t)(uint32_t)__float_as_int(r2.y);
+  int64_t o = p.offsets[idx];
+  const int64_t o_end = o + p.tiles_touched[idx];
+  // tile_hit is the same non-inlined body the counting pass ran, so the counts agree; the o_end
+  // guard and the sentinel padding (a key that sorts behind every real tile) only make a
+  // disagreement memory-safe should a toolchain ever break that.
+  for (int ty = y0; ty < y1; ++ty) {
+    for (int tx = x0; tx < x1; ++tx) {
+      if (tile_hit(r0.x, r0.y, r0.z, r0.w, r1.x, r2.w, tx, ty, p.d.width, p.d.height) && o < o_end) {
+        uint64_t band_tile = (uint64_t)((c * p.tile_h + ty - p.d.row_begin) * p.tile_w + tx);
+        p.keys[o] = (band_tile << 32) | depth_bits;
+        p.vals[o] = (uint32_t)slot;
+        ++o;
+      }
+    }
+  }
+  for (; o < o_end; ++o) {
+    p.keys[o] = ((uint64_t)p.n_tiles << 32) | depth_bits;
+    p.vals[o] = (uint32_t)slot;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// LSD radix sort, 8-bit digits, (uint64 key, uint32 value), stable.  Per pass:
+//   rs_hist_kernel     per-block digit histogram -> hist[digit][block]
+//   exclusive_scan     over the digit-major array -> global base of every (digit, block)
+//   rs_scatter_kernel  stable in-block ranking (warp match_any + per-warp counters) and scatter
+// ---------------------------------------------------------------------------------------------
+constexpr int kRsThreads = 256;
+constexpr int kRsItems = 16;
+constexpr int kRsTile = kRsThreads * kRsItems;  // 4096 keys per block
+constexpr int kRsWarps = kRsThreads / 32;
+
+__global__ void __launch_bounds__(kRsThreads) rs_hist_kernel(const uint64_t* __restrict__ keys, int64_t n, int shift,
+                                                             int nblocks, uint32_t* __restrict__ hist) {
+  __shared__ uint32_t sh[256];
+  sh[threadIdx.x] = 0;
+  __syncthreads();
+  int64_t base = (int64_t)blockIdx.x * kRsTile;
+#pragma unroll
+  for (int k = 0; k < kRsItems; ++k) {
+    int64_t i = base + (int64_t)k * kRsThreads + threadIdx.x;
+    if (i < n) atomicAdd(&sh[(uint32_t)(keys[i] >> shift) & 255u], 1u);
+  }
+  __syncthreads();
+  hist[(size_t)threadIdx.x * nblocks + blockIdx.x] = sh[threadIdx.x];
+}
+
+__global__ void __launch_bounds__(kRsThreads) rs_scatter_kernel(const uint64_t* __restrict__ keys_in,
+                                                                const uint32_t* __restrict__ vals_in, int64_t n,
+                                                                int shift, int nblocks,
+                                                                const uint32_t* __restrict__ base,
+                                                                uint64_t* __restrict__ keys_out,
+                                                                uint32_t* __restrict__ vals_out) {
+  __shared__ uint32_t warp_hist[kRsWarps][256];
+  __shared__ uint32_t gbase[256];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < kRsWarps * 256; i += kRsThreads) (&warp_hist[0][0])[i] = 0;
+  gbase[threadIdx.x] = base[(size_t)threadIdx.x * nblocks + blockIdx.x];
+  __syncthreads();
+  // warp w owns the contiguous segment [w*512, (w+1)*512) of the block tile, in rounds of 32
+  int64_t seg = (int64_t)blockIdx.x * kRsTile + (int64_t)warp * (32 * kRsItems);
+  uint64_t key[kRsItems];
+  uint32_t rank[kRsItems];
+#pragma unroll
+  for (int r = 0; r < kRsItems; ++r) {
+    int64_t i = seg + r * 32 + lane;
+    bool valid = i < n;
+    key[r] = valid ? keys_in[i] : ~0ull;
+    uint32_t digit = valid ? ((uint32_t)(key[r] >> shift) & 255u) : 256u;  // 256 = "no element"
+    unsigned peers = __match_any_sync(0xffffffffu, digit);
+    uint32_t before = __popc(peers & ((1u << lane) - 1u));
+    int leader = __ffs(peers) - 1;
+    uint32_t old = 0;
+    if (valid && lane == leader) {
+      old = warp_hist[warp][digit];
+      warp_hist[warp][digit] = old + __popc(peers);
+    }
+    old = __shfl_sync(0xffffffffu, old, leader);
+    rank[r] = old + before;
+    __syncwarp();
+  }
+  __syncthreads();
+  {  // exclusive scan over warps, per digit
+    uint32_t run = 0;
+#pragma unroll
+    for (int w = 0; w < kRsWarps; ++w) {
+      uint32_t cnt = warp_hist[w][threadIdx.x];
+      warp_hist[w][threadIdx.x] = run;
+      run += cnt;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < kRsItems; ++r) {
+    int64_t i = seg + r * 32 + lane;
+    if (i < n) {
+      uint32_t digit = (uint32_t)(key[r] >> shift) & 255u;
+      uint32_t pos = gbase[digit] + warp_hist[warp][digit] + rank[r];
+      keys_out[pos] = key[r];
+      vals_out[pos] = vals_in[i];
+    }
+  }
+}
+
+// per-tile start offsets from the sorted keys (the role of isect_offset_encode)
+__global__ void __launch_bounds__(256) tile_offsets_kernel(const uint64_t* __restrict__ keys, int64_t n, int n_tiles,
+                                                           int32_t* __restrict__ offsets) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n == 0) {
+    if (i <= n_tiles) offsets[i] = 0;
+    return;
+  }
+  if (i >= n) return;
+  int cur = (int)(keys[i] >> 32);
+  if (i == 0) {
+    for (int t = 0; t <= cur; ++t) offsets[t] = 0;
+  } else {
+    int prev = (int)(keys[i - 1] >> 32);
+    for (int t = prev + 1; t <= cur; ++t) offsets[t] = (int32_t)i;
+  }
+  if (i == n - 1) {
+    for (int t = cur + 1; t <= n_tiles; ++t) offsets[t] = (int32_t)n;
+  }
+}
+
+// sorted_splats[i] = splats[vals[i]] with the id field replaced by the slot; one thread per float4
+__global__ void __launch_bounds__(256) gather_records_kernel(const uint32_t* __restrict__ vals, int64_t n,
+                                                             const float4* __restrict__ splats,
+                                                             float4* __restrict__ sorted) {
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n * 3) return;
+  int64_t i = t / 3;
+  int part = (int)(t - i * 3);
+  uint32_t slot = vals[i];
+  float4 v = __ldg(splats + (size_t)slot * 3 + part);
+  if (part == 2) v.z = __int_as_float((int)slot);
+  sorted[t] = v;
+}
+
+struct SortWorkspace {
+  size_t keys_a, keys_b, vals_a, vals_b, hist, scan, total;
+};
+static SortWorkspace carve_sort(int64_t n_isect) {
+  SortWorkspace w;
+  size_t off = 0;
+  size_t nk = (size_t)(n_isect > 0 ? n_isect : 1);
+  int nblocks = ceil_div((int64_t)nk, kRsTile);
+  w.keys_a = off; off += align_up(nk * 8, 256);
+  w.keys_b = off; off += align_up(nk * 8, 256);
+  w.vals_a = off; off += align_up(nk * 4, 256);
+  w.vals_b = off; off += align_up(nk * 4, 256);
+  w.hist = off; off += align_up((size_t)256 * nblocks * 4, 256);
+  w.scan = off; off += scan_workspace_bytes((int64_t)256 * nblocks);
+  w.total = off;
+  return w;
+}
+
+static int tile_bits_for(int n_tiles) {
+  int bits = 1;
+  while ((1 << bits) < n_tiles) ++bits;
+  return bits;
+}
+
+int check_render_desc(const bds_render_desc* d);  // projection.cu
+
+}  // namespace bds
+
+using namespace bds;
+
+extern "C" size_t bds_bin_count_workspace_bytes(int64_t n_elems) { return scan_workspace_bytes(n_elems) + 256; }
+
+extern "C" int bds_bin_count(const bds_render_desc* d, const int32_t* tiles_touched, int64_t* isect_offsets,
+                             int64_t* n_isect_dev, void* workspace, bds_stream_t stream) {
+  if (int rc = check_render_desc(d)) return rc;
+  BDS_REQUIRE(tiles_touched && isect_offsets && n_isect_dev && workspace, "bin_count: null pointer");
+  int64_t n = (int64_t)d->n_gauss * d->n_cams;
+  return exclusive_scan<int32_t, int64_t>(tiles_touched, isect_offsets, n, n_isect_dev, workspace,
+                                          static_cast<cudaStream_t>(stream));
+}
+
+extern "C" size_t bds_bin_sort_workspace_bytes(const bds_render_desc* d, int64_t n_isect) {
+  (void)d;
+  return carve_sort(n_isect).total + 256;
+}
+
+extern "C" int bds_bin_sort(const bds_render_desc* d, int64_t n_isect, const int32_t* radii,
+                            const int32_t* tiles_touched, const int32_t* slot_of, const int64_t* isect_offsets,
+                            const float* splats, float* sorted_splats, int32_t* sorted_slots, int32_t* tile_offsets,
+                            void* workspace, bds_stream_t stream_) {
+  if (int rc = check_render_desc(d)) return rc;
+  BDS_REQUIRE(n_isect >= 0 && n_isect < ((int64_t)1 << 31), "bin_sort: n_isect must fit int32 (got %lld)", (long long)n_isect);
+  BDS_REQUIRE(radii && tiles_touched && slot_of && isect_offsets && splats && tile_offsets && workspace, "bin_sort: null pointer");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const int tile_w = (d->width + kTile - 1) / kTile, tile_h = (d->height + kTile - 1) / kTile;
+  const int n_tiles = (d->row_end - d->row_begin) * tile_w;
+  if (n_isect == 0) {
+    tile_offsets_kernel<<<ceil_div(n_tiles + 1, 256), 256, 0, stream>>>(nullptr, 0, n_tiles, tile_offsets);
+    BDS_CHECK_LAUNCH();
+    return 0;
+  }
+  BDS_REQUIRE(sorted_splats, "bin_sort: null sorted_splats");
+  char* ws = static_cast<char*>(workspace);
+  SortWorkspace w = carve_sort(n_isect);
+  uint64_t* keys[2] = {reinterpret_cast<uint64_t*>(ws + w.keys_a), reinterpret_cast<uint64_t*>(ws + w.keys_b)};
+  uint32_t* vals[2] = {reinterpret_cast<uint32_t*>(ws + w.vals_a), reinterpret_cast<uint32_t*>(ws + w.vals_b)};
+  uint32_t* hist = reinterpret_cast<uint32_t*>(ws + w.hist);
+  void* scan_ws = ws + w.scan;
+
+  EmitParams ep;
+  ep.d = *d; ep.tile_w = tile_w; ep.tile_h = tile_h; ep.radii = radii; ep.slot_of = slot_of; ep.tiles_touched = tiles_touched; ep.n_tiles = n_tiles; ep.offsets = isect_offsets;
+  ep.splats = splats; ep.keys = keys[0]; ep.vals = vals[0];
+  int64_t total = (int64_t)d->n_gauss * d->n_cams;
+  emit_keys_kernel<<<ceil_div(total, 256), 256, 0, stream>>>(ep);
+  BDS_CHECK_LAUNCH();
+
+  const int nblocks = ceil_div(n_isect, kRsTile);
+  const int end_bit = 32 + tile_bits_for(n_tiles + 1);  // +1: the sentinel tile
+  int cur = 0;
+  for (int shift = 0; shift < end_bit; shift += 8) {
+    rs_hist_kernel<<<nblocks, kRsThreads, 0, stream>>>(keys[cur], n_isect, shift, nblocks, hist);
+    BDS_CHECK_LAUNCH();
+    if (int rc = exclusive_scan<uint32_t, uint32_t>(hist, hist, (int64_t)256 * nblocks, nullptr, scan_ws, stream)) return rc;
+    rs_scatter_kernel<<<nblocks, kRsThreads, 0, stream>>>(keys[cur], vals[cur], n_isect, shift, nblocks, hist,
+                                                          keys[cur ^ 1], vals[cur ^ 1]);
+    BDS_CHECK_LAUNCH();
+    cur ^= 1;
+  }
+  tile_offsets_kernel<<<ceil_div(n_isect, 256), 256, 0, stream>>>(keys[cur], n_isect, n_tiles, tile_offsets);
+  BDS_CHECK_LAUNCH();
+  gather_records_kernel<<<ceil_div(n_isect * 3, 256), 256, 0, stream>>>(vals[cur], n_isect,
+                                                                       reinterpret_cast<const float4*>(splats),
+                                                                       reinterpret_cast<float4*>(sorted_splats));
+  BDS_CHECK_LAUNCH();
+  if (sorted_slots)
+    BDS_CHECK_CUDA(cudaMemcpyAsync(sorted_slots, vals[cur], (size_t)n_isect * 4, cudaMemcpyDeviceToDevice, stream));
+  return 0;
+}

@@ -1,0 +1,663 @@
+// Fused front-to-back alpha compositing + reference glue + multi-scale bilateral chain, forward and
+// backward.  One CTA (256 threads = 8 warps x 8x4 pixels) per 16x16 tile of the band.
+//
+// Replaces, in one launch each way (paths relative to /root/reference/project):
+//   gsplat rasterize_to_pixels_fwd/bwd          called via models/trainers/base.py:393-408
+//   clamp(rgb, max=1), RGB+ED depth normalise   base.py:414-417 (+ gsplat rendering ED branch)
+//   rgb_gaussians + rgb_sky * (1 - opacity)     models/trainers/scene_graph.py:287-294
+//   MultiScaleBilateralAffineTransform (guidance_factor=None branch, modules.py:548-559) and the
+//   sequential 3x4 apply                         scene_graph.py:112-117
+//
+// B200 mapping:
+//   * the tile's depth-sorted 48-byte splat records are contiguous in HBM (binning.cu) and are staged
+//     into shared memory with 1-D TMA bulk copies (cp.async.bulk ... mbarrier::complete_tx), 3 stages
+//     of 128 records, issued by one elected thread;
+//   * each warp tests 32 records at a time (one per lane) against its own 8x4 pixel rectangle with an
+//     exact ellipse-vs-rectangle bound, ballots, and only walks the survivors - the blend itself reads
+//     records from shared memory as 128-bit broadcasts; transmittance lives in a register per pixel and
+//     a warp vote retires the warp when all its pixels are saturated;
+//   * the backward re-walks the same records back to front; per-record gradients are reduced across
+//     the warp with a 16-value transposing shuffle reduction (16 shuffles instead of 12x5) and leave as
+//     ONE 12-lane red.global.add.f32 per (warp, record) into a 48-byte-per-splat gradient record;
+//   * no tensor cores: the work is gather / pointwise / scatter.
+#include "bilateral_math.cuh"
+#include "projection_math.cuh"
+
+namespace bds {
+
+constexpr int kChunk = 128;                 // records per stage
+constexpr int kStages = 3;
+constexpr int kRecBytes = 48;
+constexpr unsigned kFull = 0xffffffffu;
+
+// ---- mbarrier / TMA bulk copy (PTX) -----------------------------------------------------------
+BDS_D uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+BDS_D void mbar_init(uint64_t* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+BDS_D void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+BDS_D void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+BDS_D void bulk_g2s(void* dst, const void* src, unsigned bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+BDS_D bool mbar_try_wait(uint64_t* bar, unsigned parity) {
+  unsigned ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+BDS_D void mbar_wait(uint64_t* bar, unsigned parity) {
+  // bounded spin: a byte-count mismatch would otherwise hang the GPU; trap instead
+  for (unsigned it = 0; it < (1u << 24); ++it)
+    if (mbar_try_wait(bar, parity)) return;
+  __trap();
+}
+
+// ---- parameters ----------------------------------------------------------------------------------
+struct FusedBil {       // per-camera bilateral chain, full-resolution guidance
+  int n_levels;
+  const float* grid_cl[BDS_MAX_LEVELS];  // base of [C][L][GY][GX][12]
+  float* v_grid_cl[BDS_MAX_LEVELS];
+  int L[BDS_MAX_LEVELS], GY[BDS_MAX_LEVELS], GX[BDS_MAX_LEVELS];
+};
+
+struct CompParams {
+  const float4* recs;
+  const int32_t* tile_offsets;
+  int W, H, tile_w, tile_h, row_begin;
+  int64_t pix_row0;     // first stacked pixel row (c*H + y) of the band
+  int channels, expected_depth;
+  const float* backgrounds;  // [C, channels] or null
+  const float* sky;          // band pixels x 3 or null
+  float *out_rgb, *out_rgbg, *out_depth, *out_alpha;
+  int32_t* last_ids;
+  FusedBil bil;
+  // backward only
+  const float *v_rgb, *v_rgbg, *v_depth, *v_alpha;
+  float *v_splats, *v_sky, *v_backgrounds;
+};
+
+struct TileGeom {
+  int cam, px, py;      // pixel of this thread
+  bool inside;
+  int64_t pix;          // index into band-pixel arrays
+  float wx0, wy0;       // warp rectangle origin (pixel index)
+  int start, end;       // record range of the tile
+};
+
+BDS_D TileGeom tile_geom(const CompParams& p) {
+  TileGeom g;
+  int t = blockIdx.x;
+  int grow = p.row_begin + t / p.tile_w;
+  int tx = t - (t / p.tile_w) * p.tile_w;
+  g.cam = grow / p.tile_h;
+  int ty = grow - g.cam * p.tile_h;
+  int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int sx = (warp & 1) * 8, sy = (warp >> 1) * 4;
+  g.px = tx * kTile + sx + (lane & 7);
+  g.py = ty * kTile + sy + (lane >> 3);
+  g.wx0 = (float)(tx * kTile + sx);
+  g.wy0 = (float)(ty * kTile + sy);
+  g.inside = g.px < p.W && g.py < p.H;
+  g.pix = ((int64_t)g.cam * p.H + g.py - p.pix_row0) * p.W + g.px;
+  g.start = p.tile_offsets[t];
+  g.end = p.tile_offsets[t + 1];
+  return g;
+}
+
+// full-resolution-guidance chain on one pixel; fills A (all levels) and the level inputs xs
+BDS_D void fused_chain_fwd(const FusedBil& b, int cam, int H, int W, int i, int j, float& r, float& g, float& bl,
+                           float lum) {
+  for (int l = 0; l < b.n_levels; ++l) {
+    const float* grid = b.grid_cl[l] + (size_t)cam * b.L[l] * b.GY[l] * b.GX[l] * 12;
+    Tri t = tri_setup(lattice_coord(j, W, b.GX[l]), lattice_coord(i, H, b.GY[l]), luma_coord(lum, b.L[l]), b.L[l],
+                      b.GY[l], b.GX[l]);
+    float A[12];
+    tri_fetch<false>(grid, t, A, nullptr);
+    affine_apply(A, r, g, bl);
+  }
+}
+
+// =================================================================================================
+// forward
+// =================================================================================================
+template <int MODE>
+__global__ void __launch_bounds__(256) composite_fwd_kernel(CompParams p) {
+  __shared__ __align__(128) float4 srec[kStages][kChunk * 3];
+  __shared__ __align__(8) uint64_t bars[kStages];
+
+  const TileGeom g = tile_geom(p);
+  const int lane = threadIdx.x & 31;
+  const int n = g.end - g.start;
+  const int nchunks = (n + kChunk - 1) / kChunk;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) mbar_init(&bars[s], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  int issued = 0;
+  if (threadIdx.x == 0) {
+    for (; issued < nchunks && issued < kStages; ++issued) {
+      int cnt = min(kChunk, n - issued * kChunk);
+      mbar_expect_tx(&bars[issued], cnt * kRecBytes);
+      bulk_g2s(&srec[issued][0], p.recs + (size_t)(g.start + issued * kChunk) * 3, cnt * kRecBytes, &bars[issued]);
+    }
+  }
+
+  const float pxf = (float)g.px + 0.5f, pyf = (float)g.py + 0.5f;
+  const float rxmin = g.wx0 + 0.5f, rxmax = g.wx0 + 7.5f, rymin = g.wy0 + 0.5f, rymax = g.wy0 + 3.5f;
+  float T = 1.f, cr = 0.f, cg = 0.f, cb = 0.f, cd = 0.f;
+  int last = -1;
+  bool done = !g.inside;
+  bool warp_done = __all_sync(kFull, done);
+
+  int waited = 0;
+  for (int k = 0; k < nchunks; ++k) {
+    const int st = k % kStages;
+    mbar_wait(&bars[st], (k / kStages) & 1);
+    waited = k + 1;
+    if (!warp_done) {
+      const int cnt = min(kChunk, n - k * kChunk);
+      const float4* sr = &srec[st][0];
+      for (int base = 0; base < cnt && !warp_done; base += 32) {
+        // lane j tests record base+j against the warp's 8x4 pixel rectangle
+        int j = base + lane;
+        bool hit = false;
+        if (j < cnt) {
+          float4 r0 = sr[j * 3], r1 = sr[j * 3 + 1], r2 = sr[j * 3 + 2];
+          float s = min_sigma_rect(r0.x, r0.y, r0.z, r0.w, r1.x, rxmin, rxmax, rymin, rymax);
+          hit = !(s > r2.w + kCullMargin);
+        }
+        unsigned m = __ballot_sync(kFull, hit);
+        while (m) {
+          int jj = base + __ffs(m) - 1;
+          m &= m - 1;
+          float4 r0 = sr[jj * 3], r1 = sr[jj * 3 + 1], r2 = sr[jj * 3 + 2];
+          float dx = r0.x - pxf, dy = r0.y - pyf;
+          float s = r0.z * dx * dx + r0.w * dx * dy + r1.x * dy * dy;  // sigma * log2(e)
+          float alpha = fminf(kAlphaMax, r1.y * exp2f(-s));
+          if (!done && s >= 0.f && alpha >= kAlphaMin) {
+            float nT = T * (1.f - alpha);
+            if (nT <= kTStop) {
+              done = true;
+            } else {
+              float vis = alpha * T;
+              cr = fmaf(vis, r1.z, cr);
+              cg = fmaf(vis, r1.w, cg);
+              cb = fmaf(vis, r2.x, cb);
+              cd = fmaf(vis, r2.y, cd);
+              T = nT;
+              last = g.start + k * kChunk + jj;
+            }
+          }
+        }
+        warp_done = __all_sync(kFull, done);
+      }
+    }
+    // every warp is past stage st: it may be refilled; also the block-wide early exit
+    int all_done = __syncthreads_and(warp_done ? 1 : 0);
+    if (all_done) break;
+    if (threadIdx.x == 0 && issued < nchunks) {
+      int cnt = min(kChunk, n - issued * kChunk);
+      mbar_expect_tx(&bars[st], cnt * kRecBytes);
+      bulk_g2s(&srec[st][0], p.recs + (size_t)(g.start + issued * kChunk) * 3, cnt * kRecBytes, &bars[st]);
+      ++issued;
+    }
+  }
+  // never leave with a bulk copy still in flight into this CTA's shared memory
+  if (threadIdx.x == 0) {
+    for (int k = waited; k < issued; ++k) mbar_wait(&bars[k % kStages], (k / kStages) & 1);
+  }
+
+  if (!g.inside) return;
+  const float A = 1.f - T;
+  p.last_ids[g.pix] = last;
+  p.out_alpha[g.pix] = A;
+  if (MODE == 0) {
+    float bgv[4] = {0.f, 0.f, 0.f, 0.f};
+    if (p.backgrounds)
+      for (int c = 0; c < p.channels; ++c) bgv[c] = p.backgrounds[g.cam * p.channels + c];
+    float o[4] = {cr + T * bgv[0], cg + T * bgv[1], cb + T * bgv[2], cd + T * bgv[3]};
+    if (p.channels == 4 && p.expected_depth) o[3] = o[3] / fmaxf(A, 1e-10f);
+    for (int c = 0; c < p.channels; ++c) p.out_rgb[g.pix * p.channels + c] = o[c];
+  } else {
+    float rg = fminf(cr, 1.f), gg = fminf(cg, 1.f), bg = fminf(cb, 1.f);  // base.py:417
+    p.out_rgbg[g.pix * 3] = rg; p.out_rgbg[g.pix * 3 + 1] = gg; p.out_rgbg[g.pix * 3 + 2] = bg;
+    p.out_depth[g.pix] = cd / fmaxf(A, 1e-10f);                           // RGB+ED
+    float r = rg, gr = gg, b = bg;
+    if (p.sky) {                                                          // scene_graph.py:293
+      r = fmaf(p.sky[g.pix * 3], T, r);
+      gr = fmaf(p.sky[g.pix * 3 + 1], T, gr);
+      b = fmaf(p.sky[g.pix * 3 + 2], T, b);
+    }
+    if (MODE == 2) fused_chain_fwd(p.bil, g.cam, p.H, p.W, g.py, g.px, r, gr, b, luma_of(r, gr, b));
+    p.out_rgb[g.pix * 3] = r; p.out_rgb[g.pix * 3 + 1] = gr; p.out_rgb[g.pix * 3 + 2] = b;
+  }
+}
+
+// =================================================================================================
+// backward
+// =================================================================================================
+// Sum 16 per-lane values across the warp; afterwards lane L holds the total of value (L >> 1).
+BDS_D float warp_transpose_reduce16(float v[16]) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int step = 0; step < 4; ++step) {
+    const int off = 16 >> step;        // 16, 8, 4, 2
+    const int half = 8 >> step;        // values kept after this step: 8, 4, 2, 1
+    const bool upper = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < half; ++i) {
+      float keep = upper ? v[i + half] : v[i];
+      float send = upper ? v[i] : v[i + half];
+      v[i] = keep + __shfl_xor_sync(kFull, send, off);
+    }
+  }
+  return v[0] + __shfl_xor_sync(kFull, v[0], 1);
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(256) composite_bwd_kernel(CompParams p) {
+  __shared__ __align__(128) float4 srec[kStages][kChunk * 3];
+  __shared__ __align__(8) uint64_t bars[kStages];
+  __shared__ int s_last[8];
+
+  const TileGeom g = tile_geom(p);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+  // ---- per-pixel epilogue backward: cotangents of the raw accumulators C (3), D and of A = 1 - T
+  float vC[4] = {0.f, 0.f, 0.f, 0.f};
+  float vA = 0.f, Tfin = 1.f;
+  int last = -1;
+  float bgv[4] = {0.f, 0.f, 0.f, 0.f};
+  if (g.inside) {
+    last = p.last_ids[g.pix];
+    const float A = p.out_alpha[g.pix];
+    Tfin = 1.f - A;
+    if (p.v_alpha) vA = p.v_alpha[g.pix];
+    if (MODE == 0) {
+      float vo[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int c = 0; c < p.channels; ++c) vo[c] = p.v_rgb[g.pix * p.channels + c];
+      if (p.backgrounds)  // T_final * <bg, v> enters through the walk (bg_dot below)
+        for (int c = 0; c < p.channels; ++c) bgv[c] = p.backgrounds[g.cam * p.channels + c];
+      vC[0] = vo[0]; vC[1] = vo[1]; vC[2] = vo[2];
+      if (p.channels == 4) {
+        if (p.expected_depth) {
+          float Ac = fmaxf(A, 1e-10f);
+          vC[3] = vo[3] / Ac;
+          if (A >= 1e-10f) vA -= vo[3] * p.out_depth[g.pix] / Ac;  // out_depth holds the normalised depth
+        } else {
+          vC[3] = vo[3];
+        }
+      }
+    } else {
+      float rg = p.out_rgbg[g.pix * 3], gg = p.out_rgbg[g.pix * 3 + 1], bg = p.out_rgbg[g.pix * 3 + 2];
+      float sk[3] = {0.f, 0.f, 0.f};
+      if (p.sky) { sk[0] = p.sky[g.pix * 3]; sk[1] = p.sky[g.pix * 3 + 1]; sk[2] = p.sky[g.pix * 3 + 2]; }
+      float gr = p.v_rgb[g.pix * 3], gg2 = p.v_rgb[g.pix * 3 + 1], gb = p.v_rgb[g.pix * 3 + 2];
+      if (MODE == 2) {
+        // recompute the chain, then walk it backwards (appendix A.3 of SURVEY.md)
+        float x0r = fmaf(sk[0], Tfin, rg), x0g = fmaf(sk[1], Tfin, gg), x0b = fmaf(sk[2], Tfin, bg);
+        float lum = luma_of(x0r, x0g, x0b);
+        float Aall[BDS_MAX_LEVELS][12], xs[BDS_MAX_LEVELS][3];
+        Tri tri[BDS_MAX_LEVELS];
+        float r = x0r, gq = x0g, b = x0b;
+#pragma unroll
+        for (int l = 0; l < BDS_MAX_LEVELS; ++l) {
+          if (l < p.bil.n_levels) {
+            const float* grid = p.bil.grid_cl[l] + (size_t)g.cam * p.bil.L[l] * p.bil.GY[l] * p.bil.GX[l] * 12;
+            tri[l] = tri_setup(lattice_coord(g.px, p.W, p.bil.GX[l]), lattice_coord(g.py, p.H, p.bil.GY[l]),
+                               luma_coord(lum, p.bil.L[l]), p.bil.L[l], p.bil.GY[l], p.bil.GX[l]);
+            xs[l][0] = r; xs[l][1] = gq; xs[l][2] = b;
+            tri_fetch<false>(grid, tri[l], Aall[l], nullptr);
+            affine_apply(Aall[l], r, gq, b);
+          }
+        }
+        float v_lum = 0.f;
+#pragma unroll
+        for (int l = BDS_MAX_LEVELS - 1; l >= 0; --l) {
+          if (l < p.bil.n_levels) {
+            size_t goff = (size_t)g.cam * p.bil.L[l] * p.bil.GY[l] * p.bil.GX[l] * 12;
+            float vAff[12];
+#pragma unroll
+            for (int k = 0; k < 12; ++k) vAff[k] = 0.f;
+            float nr, ng, nb;
+            affine_apply_bwd(Aall[l], xs[l][0], xs[l][1], xs[l][2], gr, gg2, gb, vAff, nr, ng, nb);
+            gr = nr; gg2 = ng; gb = nb;
+            tri_scatter(p.bil.v_grid_cl[l] + goff, tri[l], vAff);
+            if (tri[l].z_inside) {
+              float Ad[12], dAdz[12];
+              tri_fetch<true>(p.bil.grid_cl[l] + goff, tri[l], Ad, dAdz);
+              float s = 0.f;
+#pragma unroll
+              for (int k = 0; k < 12; ++k) s = fmaf(vAff[k], dAdz[k], s);
+              v_lum += s * (float)(p.bil.L[l] - 1);
+            }
+          }
+        }
+        gr += v_lum * kLumaR; gg2 += v_lum * kLumaG; gb += v_lum * kLumaB;
+      }
+      // (gr, gg2, gb) = cotangent of rgb_in = rgb_gauss + sky * (1 - A)
+      if (p.v_sky) { p.v_sky[g.pix * 3] = gr * Tfin; p.v_sky[g.pix * 3 + 1] = gg2 * Tfin; p.v_sky[g.pix * 3 + 2] = gb * Tfin; }
+      vA -= sk[0] * gr + sk[1] * gg2 + sk[2] * gb;
+      float vr = gr, vg = gg2, vb = gb;
+      if (p.v_rgbg) { vr += p.v_rgbg[g.pix * 3]; vg += p.v_rgbg[g.pix * 3 + 1]; vb += p.v_rgbg[g.pix * 3 + 2]; }
+      vC[0] = rg < 1.f ? vr : 0.f;   // clamp(max=1) passes gradient below the bound
+      vC[1] = gg < 1.f ? vg : 0.f;
+      vC[2] = bg < 1.f ? vb : 0.f;
+      if (p.v_depth) {
+        float Ac = fmaxf(A, 1e-10f);
+        float vd = p.v_depth[g.pix];
+        vC[3] = vd / Ac;
+        if (A >= 1e-10f) vA -= vd * p.out_depth[g.pix] / Ac;
+      }
+    }
+  }
+
+  // ---- block-wide last contributing record
+  int wl = last;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) wl = max(wl, __shfl_xor_sync(kFull, wl, o));
+  if (lane == 0) s_last[warp] = wl;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) mbar_init(&bars[s], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  int block_last = -1;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) block_last = max(block_last, s_last[w]);
+  const int warp_last = wl;
+
+  const int n = block_last < 0 ? 0 : block_last - g.start + 1;
+  const int nchunks = (n + kChunk - 1) / kChunk;
+  // chunks are walked from the back: walk index q = 0.. corresponds to chunk k = nchunks-1-q
+  int issued = 0;
+  if (threadIdx.x == 0) {
+    for (; issued < nchunks && issued < kStages; ++issued) {
+      int k = nchunks - 1 - issued;
+      int cnt = min(kChunk, n - k * kChunk);
+      mbar_expect_tx(&bars[issued], cnt * kRecBytes);
+      bulk_g2s(&srec[issued][0], p.recs + (size_t)(g.start + k * kChunk) * 3, cnt * kRecBytes, &bars[issued]);
+    }
+  }
+
+  const float pxf = (float)g.px + 0.5f, pyf = (float)g.py + 0.5f;
+  const float rxmin = g.wx0 + 0.5f, rxmax = g.wx0 + 7.5f, rymin = g.wy0 + 0.5f, rymax = g.wy0 + 3.5f;
+  float T = Tfin;
+  float buf[4] = {0.f, 0.f, 0.f, 0.f};
+  // background: render = C + T_final * bg  ->  d/dalpha_i carries -T_final/(1-alpha_i) <bg, v>
+  float bg_dot = 0.f;
+  if (MODE == 0 && p.backgrounds) {
+    bg_dot = bgv[0] * vC[0] + bgv[1] * vC[1] + bgv[2] * vC[2];
+    if (p.channels == 4) bg_dot += bgv[3] * vC[3];
+  }
+  const float vA_eff = vA - bg_dot;  // both multiply T_final / (1 - alpha_i)
+
+  for (int q = 0; q < nchunks; ++q) {
+    const int st = q % kStages;
+    const int k = nchunks - 1 - q;
+    mbar_wait(&bars[st], (q / kStages) & 1);
+    const int cnt = min(kChunk, n - k * kChunk);
+    const int chunk0 = g.start + k * kChunk;
+    if (warp_last >= chunk0) {
+      const float4* sr = &srec[st][0];
+      for (int base = ((cnt - 1) / 32) * 32; base >= 0; base -= 32) {
+        if (chunk0 + base > warp_last) continue;
+        int j = base + lane;
+        bool hit = false;
+        if (j < cnt) {
+          float4 r0 = sr[j * 3], r1 = sr[j * 3 + 1], r2 = sr[j * 3 + 2];
+          float s = min_sigma_rect(r0.x, r0.y, r0.z, r0.w, r1.x, rxmin, rxmax, rymin, rymax);
+          hit = !(s > r2.w + kCullMargin);
+        }
+        unsigned m = __ballot_sync(kFull, hit);
+        while (m) {
+          int bit = 31 - __clz(m);
+          m &= ~(1u << bit);
+          int jj = base + bit;
+          int gidx = chunk0 + jj;
+          float4 r0 = sr[jj * 3], r1 = sr[jj * 3 + 1], r2 = sr[jj * 3 + 2];
+          float dx = r0.x - pxf, dy = r0.y - pyf;
+          float s = r0.z * dx * dx + r0.w * dx * dy + r1.x * dy * dy;
+          float vis = exp2f(-s);
+          float araw = r1.y * vis;
+          float alpha = fminf(kAlphaMax, araw);
+          bool valid = g.inside && gidx <= last && s >= 0.f && alpha >= kAlphaMin;
+          if (!__any_sync(kFull, valid)) continue;
+          float v[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = 0.f;
+          if (valid) {
+            float ra = 1.f / (1.f - alpha);
+            T *= ra;
+            float fac = alpha * T;
+            float col[4] = {r1.z, r1.w, r2.x, r2.y};
+            float v_alpha = 0.f;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              v[6 + c] = fac * vC[c];
+              v_alpha = fmaf(col[c] * T - buf[c] * ra, vC[c], v_alpha);
+              buf[c] = fmaf(col[c], fac, buf[c]);
+            }
+            v_alpha = fmaf(Tfin * ra, vA_eff, v_alpha);
+            if (araw <= kAlphaMax) {
+              float v_s = -kLn2 * araw * v_alpha;         // d alpha / d sigma' = -ln2 * alpha
+              v[2] = v_s * dx * dx;
+              v[3] = v_s * dx * dy;
+              v[4] = v_s * dy * dy;
+              float vx = v_s * (2.f * r0.z * dx + r0.w * dy);
+              float vy = v_s * (r0.w * dx + 2.f * r1.x * dy);
+              v[0] = vx; v[1] = vy;
+              v[10] = fabsf(vx); v[11] = fabsf(vy);
+              v[5] = vis * v_alpha;
+            }
+          }
+          float tot = warp_transpose_reduce16(v);
+          int comp = lane >> 1;
+          if ((lane & 1) == 0 && comp < 12 && tot != 0.f) {
+            int slot = __float_as_int(r2.z);
+            red_add(p.v_splats + (size_t)slot * 12 + comp, tot);
+          }
+        }
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && issued < nchunks) {
+      int kk = nchunks - 1 - issued;
+      int c2 = min(kChunk, n - kk * kChunk);
+      mbar_expect_tx(&bars[st], c2 * kRecBytes);
+      bulk_g2s(&srec[st][0], p.recs + (size_t)(g.start + kk * kChunk) * 3, c2 * kRecBytes, &bars[st]);
+      ++issued;
+    }
+  }
+  // v_backgrounds: sum over pixels of T_final * v (MODE 0)
+  if (MODE == 0 && p.v_backgrounds) {
+    for (int c = 0; c < p.channels; ++c) {
+      float contrib = g.inside ? Tfin * vC[c] : 0.f;
+      float sum = warp_sum(contrib);
+      if (lane == 0 && sum != 0.f) red_add(p.v_backgrounds + g.cam * p.channels + c, sum);
+    }
+  }
+}
+
+__global__ void repack_grids_kernel(const float* __restrict__ cf, float* __restrict__ cl, int nodes) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nodes * 12) return;
+  int node = i / 12, ch = i - node * 12;
+  cl[i] = cf[(size_t)ch * nodes + node];
+}
+__global__ void unpack_add_grids_kernel(const float* __restrict__ cl, float* __restrict__ cf, int nodes) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nodes * 12) return;
+  int ch = i / nodes, node = i - ch * nodes;
+  cf[i] += cl[(size_t)node * 12 + ch];
+}
+
+struct CompWorkspace {
+  size_t grid_cl[BDS_MAX_LEVELS], v_grid_cl[BDS_MAX_LEVELS];
+  size_t total;
+};
+static CompWorkspace carve_comp(const bds_render_desc* d, const bds_epilogue_desc* e) {
+  CompWorkspace w;
+  size_t off = 0;
+  for (int l = 0; l < BDS_MAX_LEVELS; ++l) w.grid_cl[l] = w.v_grid_cl[l] = 0;
+  if (e->mode == 2) {
+    for (int l = 0; l < e->bil.n_levels; ++l) {
+      size_t b = align_up((size_t)d->n_cams * e->bil.L[l] * e->bil.GY[l] * e->bil.GX[l] * 12 * sizeof(float), 256);
+      w.grid_cl[l] = off; off += b;
+      w.v_grid_cl[l] = off; off += b;
+    }
+  }
+  w.total = off;
+  return w;
+}
+
+int check_render_desc(const bds_render_desc* d);
+
+static int fill_common(CompParams& p, const bds_render_desc* d, const bds_epilogue_desc* e) {
+  BDS_REQUIRE(e && e->mode >= 0 && e->mode <= 2, "composite: epilogue mode must be 0, 1 or 2");
+  if (e->mode == 0) BDS_REQUIRE(e->channels == 3 || e->channels == 4, "composite: channels must be 3 or 4");
+  if (e->mode == 2) {
+    BDS_REQUIRE(e->bil.n_levels >= 1 && e->bil.n_levels <= BDS_MAX_LEVELS, "composite: bad n_levels");
+    for (int l = 0; l < e->bil.n_levels; ++l)
+      BDS_REQUIRE(e->bil.factor[l] <= 1, "composite: the fused epilogue implements full-resolution guidance "
+                                          "(guidance_factor=None); run mode 1 + bds_bilateral_* for low-res guidance");
+  }
+  p.W = d->width; p.H = d->height;
+  p.tile_w = (d->width + kTile - 1) / kTile;
+  p.tile_h = (d->height + kTile - 1) / kTile;
+  p.row_begin = d->row_begin;
+  // first stacked pixel row of the band
+  int cam0 = d->row_begin / p.tile_h, ty0 = d->row_begin - cam0 * p.tile_h;
+  p.pix_row0 = (int64_t)cam0 * d->height + (int64_t)ty0 * kTile;
+  p.channels = e->mode == 0 ? e->channels : 4;
+  p.expected_depth = e->expected_depth;
+  return 0;
+}
+
+}  // namespace bds
+
+using namespace bds;
+
+extern "C" size_t bds_composite_workspace_bytes(const bds_render_desc* d, const bds_epilogue_desc* e) {
+  if (!d || !e) return 0;
+  return carve_comp(d, e).total + 256;
+}
+
+extern "C" int bds_composite_fwd(const bds_render_desc* d, const bds_epilogue_desc* e, const float* sorted_splats,
+                                 const int32_t* tile_offsets, const float* backgrounds, const float* sky,
+                                 const float* const* host_grids, float* out_rgb, float* out_rgb_gauss,
+                                 float* out_depth, float* out_alpha, int32_t* last_ids, void* workspace,
+                                 bds_stream_t stream_) {
+  if (int rc = check_render_desc(d)) return rc;
+  CompParams p{};
+  if (int rc = fill_common(p, d, e)) return rc;
+  const int n_tiles = (d->row_end - d->row_begin) * p.tile_w;
+  if (n_tiles == 0) return 0;
+  BDS_REQUIRE(tile_offsets && out_rgb && out_alpha && last_ids, "composite_fwd: null pointer");
+  if (e->mode != 0) BDS_REQUIRE(out_rgb_gauss && out_depth, "composite_fwd: modes 1/2 need rgb_gauss and depth outputs");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  p.recs = reinterpret_cast<const float4*>(sorted_splats);
+  p.tile_offsets = tile_offsets;
+  p.backgrounds = backgrounds; p.sky = sky;
+  p.out_rgb = out_rgb; p.out_rgbg = out_rgb_gauss; p.out_depth = out_depth; p.out_alpha = out_alpha; p.last_ids = last_ids;
+  if (e->mode == 2) {
+    BDS_REQUIRE(host_grids && workspace, "composite_fwd: mode 2 needs grids and workspace");
+    CompWorkspace w = carve_comp(d, e);
+    p.bil.n_levels = e->bil.n_levels;
+    for (int l = 0; l < e->bil.n_levels; ++l) {
+      int nodes = e->bil.L[l] * e->bil.GY[l] * e->bil.GX[l];
+      float* base = reinterpret_cast<float*>(static_cast<char*>(workspace) + w.grid_cl[l]);
+      p.bil.grid_cl[l] = base;
+      p.bil.L[l] = e->bil.L[l]; p.bil.GY[l] = e->bil.GY[l]; p.bil.GX[l] = e->bil.GX[l];
+      for (int c = 0; c < d->n_cams; ++c) {
+        const float* src = host_grids[c * e->bil.n_levels + l];
+        if (!src) continue;  // camera outside the band
+        repack_grids_kernel<<<ceil_div(nodes * 12, 256), 256, 0, stream>>>(src, base + (size_t)c * nodes * 12, nodes);
+        BDS_CHECK_LAUNCH();
+      }
+    }
+  }
+  switch (e->mode) {
+    case 0: composite_fwd_kernel<0><<<n_tiles, 256, 0, stream>>>(p); break;
+    case 1: composite_fwd_kernel<1><<<n_tiles, 256, 0, stream>>>(p); break;
+    default: composite_fwd_kernel<2><<<n_tiles, 256, 0, stream>>>(p); break;
+  }
+  BDS_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int bds_composite_bwd(const bds_render_desc* d, const bds_epilogue_desc* e, const float* sorted_splats,
+                                 const int32_t* sorted_slots, const int32_t* tile_offsets, const float* backgrounds,
+                                 const float* sky, const float* const* host_grids, const float* out_rgb_gauss,
+                                 const float* out_depth, const float* out_alpha, const int32_t* last_ids,
+                                 const float* v_rgb, const float* v_rgb_gauss, const float* v_depth,
+                                 const float* v_alpha, float* v_splats, float* v_sky, float* const* host_v_grids,
+                                 float* v_backgrounds, void* workspace, bds_stream_t stream_) {
+  (void)sorted_slots;
+  if (int rc = check_render_desc(d)) return rc;
+  CompParams p{};
+  if (int rc = fill_common(p, d, e)) return rc;
+  const int n_tiles = (d->row_end - d->row_begin) * p.tile_w;
+  if (n_tiles == 0) return 0;
+  BDS_REQUIRE(tile_offsets && out_alpha && last_ids && v_rgb && v_splats, "composite_bwd: null pointer");
+  if (e->mode != 0) BDS_REQUIRE(out_rgb_gauss && out_depth, "composite_bwd: modes 1/2 need rgb_gauss and depth");
+  if (e->mode == 0 && e->channels == 4 && e->expected_depth)
+    BDS_REQUIRE(out_depth, "composite_bwd: ED mode needs the normalised depth output (out_depth)");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  p.recs = reinterpret_cast<const float4*>(sorted_splats);
+  p.tile_offsets = tile_offsets;
+  p.backgrounds = backgrounds; p.sky = sky;
+  p.out_rgbg = const_cast<float*>(out_rgb_gauss); p.out_depth = const_cast<float*>(out_depth);
+  p.out_alpha = const_cast<float*>(out_alpha); p.last_ids = const_cast<int32_t*>(last_ids);
+  p.v_rgb = v_rgb; p.v_rgbg = v_rgb_gauss; p.v_depth = v_depth; p.v_alpha = v_alpha;
+  p.v_splats = v_splats; p.v_sky = v_sky; p.v_backgrounds = v_backgrounds;
+  CompWorkspace w = carve_comp(d, e);
+  if (e->mode == 2) {
+    BDS_REQUIRE(host_grids && host_v_grids && workspace, "composite_bwd: mode 2 needs grids, v_grids and workspace");
+    p.bil.n_levels = e->bil.n_levels;
+    for (int l = 0; l < e->bil.n_levels; ++l) {
+      int nodes = e->bil.L[l] * e->bil.GY[l] * e->bil.GX[l];
+      float* base = reinterpret_cast<float*>(static_cast<char*>(workspace) + w.grid_cl[l]);
+      float* vbase = reinterpret_cast<float*>(static_cast<char*>(workspace) + w.v_grid_cl[l]);
+      p.bil.grid_cl[l] = base; p.bil.v_grid_cl[l] = vbase;
+      p.bil.L[l] = e->bil.L[l]; p.bil.GY[l] = e->bil.GY[l]; p.bil.GX[l] = e->bil.GX[l];
+      BDS_CHECK_CUDA(cudaMemsetAsync(vbase, 0, (size_t)d->n_cams * nodes * 12 * sizeof(float), stream));
+      for (int c = 0; c < d->n_cams; ++c) {
+        const float* src = host_grids[c * e->bil.n_levels + l];
+        if (!src) continue;
+        repack_grids_kernel<<<ceil_div(nodes * 12, 256), 256, 0, stream>>>(src, base + (size_t)c * nodes * 12, nodes);
+        BDS_CHECK_LAUNCH();
+      }
+    }
+  }
+  switch (e->mode) {
+    case 0: composite_bwd_kernel<0><<<n_tiles, 256, 0, stream>>>(p); break;
+    case 1: composite_bwd_kernel<1><<<n_tiles, 256, 0, stream>>>(p); break;
+    default: composite_bwd_kernel<2><<<n_tiles, 256, 0, stream>>>(p); break;
+  }
+  BDS_CHECK_LAUNCH();
+  if (e->mode == 2) {
+    for (int l = 0; l < e->bil.n_levels; ++l) {
+      int nodes = e->bil.L[l] * e->bil.GY[l] * e->bil.GX[l];
+      for (int c = 0; c < d->n_cams; ++c) {
+        float* dst = host_v_grids[c * e->bil.n_levels + l];
+        if (!dst) continue;
+        unpack_add_grids_kernel<<<ceil_div(nodes * 12, 256), 256, 0, stream>>>(p.bil.v_grid_cl[l] + (size_t)c * nodes * 12, dst,
+                                                                                nodes);
+        BDS_CHECK_LAUNCH();
+      }
+    }
+  }
+  return 0;
+}

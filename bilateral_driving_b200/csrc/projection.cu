@@ -1,0 +1,437 @@
+// Projection (+ optional fused activations and SH colour), tile counting with exact
+// ellipse-vs-tile culling, compaction of visible splats into packed 48-byte records; and its VJP.
+// Also the stand-alone spherical-harmonics entry points.
+//
+// One thread per (camera, Gaussian): 44-56 B read, <= 48 B written; HBM-bound pointwise work.
+// Replaces gsplat's fully_fused_projection_fwd/bwd + compute_sh_fwd/bwd for the reference call
+// sites models/trainers/base.py:393-408 and models/gaussians/vanilla.py:383-395.
+#include "projection_math.cuh"
+#include "sh_math.cuh"
+
+namespace bds {
+
+struct ProjParams {
+  bds_render_desc d;
+  int tile_w, tile_h;
+  const float *means, *quats, *scales, *opacities, *colors, *fdc, *frest, *viewmats, *Ks;
+  int colors_per_cam;
+  int32_t* radii;
+  float *means2d, *depths, *conics, *compensations;
+  int32_t* tiles_touched;
+  float* splats;
+  int32_t splat_cap;
+  int32_t* slot_of;
+  int32_t* counters;
+};
+
+BDS_D void load_cam(const float* __restrict__ viewmats, const float* __restrict__ Ks, int c, CamIntr& cam) {
+  const float* V = viewmats + 16 * c;
+  const float* K = Ks + 9 * c;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+#pragma unroll
+    for (int j = 0; j < 3; ++j) cam.R[i * 3 + j] = __ldg(V + i * 4 + j);
+    cam.t[i] = __ldg(V + i * 4 + 3);
+  }
+  cam.fx = __ldg(K); cam.fy = __ldg(K + 4); cam.cx = __ldg(K + 2); cam.cy = __ldg(K + 5);
+}
+
+BDS_D float sigmoidf(float x) { return 1.0f / (1.0f + __expf(-x)); }
+
+// rows of camera c covered by the band, as tile rows [ty0, ty1)
+BDS_HD void band_rows(const bds_render_desc& d, int tile_h, int c, int& ty0, int& ty1) {
+  int g0 = c * tile_h, g1 = g0 + tile_h;
+  int lo = d.row_begin > g0 ? d.row_begin : g0;
+  int hi = d.row_end < g1 ? d.row_end : g1;
+  if (hi <= lo) { ty0 = ty1 = 0; return; }
+  ty0 = lo - g0;
+  ty1 = hi - g0;
+}
+
+// tile rectangle of gsplat's isect_tiles (square 3-sigma bound) clipped to the band
+struct TileRect { int x0, x1, y0, y1; };
+BDS_HD TileRect tile_rect(float mx, float my, float radius, int tile_w, int tile_h, int ty0, int ty1) {
+  float tr = radius / (float)kTile, tx = mx / (float)kTile, ty = my / (float)kTile;
+  TileRect r;
+  float fx0 = floorf(tx - tr), fy0 = floorf(ty - tr), fx1 = ceilf(tx + tr), fy1 = ceilf(ty + tr);
+  r.x0 = (int)fminf(fmaxf(fx0, 0.f), (float)tile_w);
+  r.x1 = (int)fminf(fmaxf(fx1, 0.f), (float)tile_w);
+  r.y0 = (int)fminf(fmaxf(fy0, 0.f), (float)tile_h);
+  r.y1 = (int)fminf(fmaxf(fy1, 0.f), (float)tile_h);
+  if (r.y0 < ty0) r.y0 = ty0;
+  if (r.y1 > ty1) r.y1 = ty1;
+  if (r.y1 < r.y0) r.y1 = r.y0;
+  return r;
+}
+
+__global__ void __launch_bounds__(256) project_fwd_kernel(ProjParams p) {
+  const int N = p.d.n_gauss;
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  bool in_range = idx < (int64_t)N * p.d.n_cams;
+  int c = in_range ? (int)(idx / N) : 0;
+  int n = in_range ? (int)(idx - (int64_t)c * N) : 0;
+  bool emit = false;
+  float rec[12];
+  int n_tiles = 0;
+  int radius_i = 0;
+  if (in_range) {
+    int ty0, ty1;
+    band_rows(p.d, p.tile_h, c, ty0, ty1);
+    if (ty1 > ty0) {
+      CamIntr cam;
+      load_cam(p.viewmats, p.Ks, c, cam);
+      float mu[3] = {p.means[3 * (size_t)n], p.means[3 * (size_t)n + 1], p.means[3 * (size_t)n + 2]};
+      float q[4] = {p.quats[4 * (size_t)n], p.quats[4 * (size_t)n + 1], p.quats[4 * (size_t)n + 2], p.quats[4 * (size_t)n + 3]};
+      float s[3] = {p.scales[3 * (size_t)n], p.scales[3 * (size_t)n + 1], p.scales[3 * (size_t)n + 2]};
+      if (p.d.raw_params) { s[0] = __expf(s[0]); s[1] = __expf(s[1]); s[2] = __expf(s[2]); }
+      Proj o;
+      bool vis = project_gaussian(mu, q, s, cam, p.d.width, p.d.height, p.d.eps2d, p.d.near_plane, p.d.far_plane,
+                                  p.d.radius_clip, o);
+      if (vis) {
+        radius_i = (int)o.radius;
+        if (p.means2d) { p.means2d[2 * idx] = o.mx; p.means2d[2 * idx + 1] = o.my; }
+        if (p.depths) p.depths[idx] = o.z;
+        if (p.conics) { p.conics[3 * idx] = o.a; p.conics[3 * idx + 1] = o.b; p.conics[3 * idx + 2] = o.c; }
+        if (p.compensations) p.compensations[idx] = o.comp;
+        float op = p.opacities[n];
+        if (p.d.raw_params) op = sigmoidf(op);
+        if (p.d.antialiased) op *= o.comp;
+        float qa = 0.5f * kLog2e * o.a, qb = kLog2e * o.b, qc = 0.5f * kLog2e * o.c;
+        float sigma_cut = __log2f(255.0f * op);  // alpha >= 1/255  <=>  sigma' <= log2(255 o)
+        if (op >= kAlphaMin) {
+          TileRect tr = tile_rect(o.mx, o.my, o.radius, p.tile_w, p.tile_h, ty0, ty1);
+          for (int ty = tr.y0; ty < tr.y1; ++ty)
+            for (int tx = tr.x0; tx < tr.x1; ++tx)
+              n_tiles += tile_hit(o.mx, o.my, qa, qb, qc, sigma_cut, tx, ty, p.d.width, p.d.height) ? 1 : 0;
+        }
+        if (n_tiles > 0) {
+          emit = true;
+          rec[0] = o.mx; rec[1] = o.my; rec[2] = qa; rec[3] = qb; rec[4] = qc; rec[5] = op;
+          if (p.d.sh_degree >= 0) {
+            // view direction = mean - camera position, camera position = -R^T t  (vanilla.py:384-385)
+            float cp[3] = {-(cam.R[0] * cam.t[0] + cam.R[3] * cam.t[1] + cam.R[6] * cam.t[2]),
+                           -(cam.R[1] * cam.t[0] + cam.R[4] * cam.t[1] + cam.R[7] * cam.t[2]),
+                           -(cam.R[2] * cam.t[0] + cam.R[5] * cam.t[1] + cam.R[8] * cam.t[2])};
+            float dx = mu[0] - cp[0], dy = mu[1] - cp[1], dz = mu[2] - cp[2];
+            float inv = rsqrtf(dx * dx + dy * dy + dz * dz);
+            float b[16];
+            sh_basis(p.d.sh_degree, dx * inv, dy * inv, dz * inv, b);
+            int nb = (p.d.sh_degree + 1) * (p.d.sh_degree + 1);
+            if (nb > p.d.sh_K) nb = p.d.sh_K;
+            float col[3];
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) col[ch] = b[0] * __ldg(p.fdc + 3 * (size_t)n + ch);
+            const float* fr = p.frest + (size_t)n * (p.d.sh_K - 1) * 3;
+            for (int k = 1; k < nb; ++k) {
+#pragma unroll
+              for (int ch = 0; ch < 3; ++ch) col[ch] = fmaf(b[k], __ldg(fr + (k - 1) * 3 + ch), col[ch]);
+            }
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) rec[6 + ch] = fminf(fmaxf(col[ch] + 0.5f, 0.f), 1.f);
+          } else {
+            const float* cp = p.colors + (p.colors_per_cam ? 3 * (size_t)idx : 3 * (size_t)n);
+            rec[6] = cp[0]; rec[7] = cp[1]; rec[8] = cp[2];
+          }
+          rec[9] = o.z;
+          rec[10] = __int_as_float((int)idx);
+          rec[11] = sigma_cut;
+        }
+      }
+    }
+  }
+  // warp-aggregated compaction: one atomic per warp
+  unsigned ballot = __ballot_sync(0xffffffffu, emit);
+  int slot = -1;
+  if (ballot) {
+    int lane = threadIdx.x & 31;
+    int leader = __ffs(ballot) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(p.counters, __popc(ballot));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (emit) {
+      slot = base + __popc(ballot & ((1u << lane) - 1u));
+      if (slot >= p.splat_cap) {  // capacity overflow: flag, drop the record
+        p.counters[1] = 1;
+        slot = -1;
+        n_tiles = 0;
+      }
+    }
+  }
+  if (in_range) {
+    if (p.radii) p.radii[idx] = radius_i;
+    p.tiles_touched[idx] = n_tiles;
+    p.slot_of[idx] = slot;
+    if (slot >= 0) {
+      float4* dst = reinterpret_cast<float4*>(p.splats + (size_t)slot * 12);
+      dst[0] = make_float4(rec[0], rec[1], rec[2], rec[3]);
+      dst[1] = make_float4(rec[4], rec[5], rec[6], rec[7]);
+      dst[2] = make_float4(rec[8], rec[9], rec[10], rec[11]);
+    }
+  }
+}
+
+struct ProjBwdParams {
+  bds_render_desc d;
+  const float *means, *quats, *scales, *opacities, *colors, *fdc, *frest, *viewmats, *Ks;
+  int colors_per_cam;
+  const float* splats;
+  const int32_t* counters;
+  const float* v_splats;
+  const float *v_means2d_extra, *v_depths_extra, *v_conics_extra;
+  float *v_means, *v_quats, *v_scales, *v_opacities, *v_colors, *v_fdc, *v_frest, *v_viewmats, *v_means2d, *absgrad;
+};
+
+__global__ void __launch_bounds__(256) project_bwd_kernel(ProjBwdParams p) {
+  int n_slots = p.counters[0];
+  int slot = blockIdx.x * blockDim.x + threadIdx.x;
+  bool active = slot < n_slots;
+  float vview[12];
+#pragma unroll
+  for (int k = 0; k < 12; ++k) vview[k] = 0.f;
+  int c = 0;
+  if (active) {
+    const float4* rp = reinterpret_cast<const float4*>(p.splats + (size_t)slot * 12);
+    float4 r0 = rp[0], r1 = rp[1], r2 = rp[2];
+    const float4* vp = reinterpret_cast<const float4*>(p.v_splats + (size_t)slot * 12);
+    float4 g0 = vp[0], g1 = vp[1], g2 = vp[2];
+    int64_t idx = (int64_t)__float_as_int(r2.z);
+    const int N = p.d.n_gauss;
+    c = (int)(idx / N);
+    int n = (int)(idx - (int64_t)c * N);
+    // v_splats = {v_x, v_y, v_a', v_b', v_c', v_op, v_r, v_g, v_b, v_depth, |v_x|, |v_y|}
+    float vmx = g0.x, vmy = g0.y;
+    float va = g0.z * (0.5f * kLog2e), vb = g0.w * kLog2e, vc = g1.x * (0.5f * kLog2e);
+    float vop = g1.y, vr = g1.z, vg = g1.w, vbl = g2.x, vz = g2.y;
+    if (p.v_means2d) { p.v_means2d[2 * idx] = vmx; p.v_means2d[2 * idx + 1] = vmy; }
+    if (p.absgrad) { p.absgrad[2 * idx] = g2.z; p.absgrad[2 * idx + 1] = g2.w; }
+    if (p.v_means2d_extra) { vmx += p.v_means2d_extra[2 * idx]; vmy += p.v_means2d_extra[2 * idx + 1]; }
+    if (p.v_depths_extra) vz += p.v_depths_extra[idx];
+    if (p.v_conics_extra) { va += p.v_conics_extra[3 * idx]; vb += p.v_conics_extra[3 * idx + 1]; vc += p.v_conics_extra[3 * idx + 2]; }
+    CamIntr cam;
+    load_cam(p.viewmats, p.Ks, c, cam);
+    float mu[3] = {p.means[3 * (size_t)n], p.means[3 * (size_t)n + 1], p.means[3 * (size_t)n + 2]};
+    float q[4] = {p.quats[4 * (size_t)n], p.quats[4 * (size_t)n + 1], p.quats[4 * (size_t)n + 2], p.quats[4 * (size_t)n + 3]};
+    float sraw[3] = {p.scales[3 * (size_t)n], p.scales[3 * (size_t)n + 1], p.scales[3 * (size_t)n + 2]};
+    float s[3] = {sraw[0], sraw[1], sraw[2]};
+    if (p.d.raw_params) { s[0] = __expf(s[0]); s[1] = __expf(s[1]); s[2] = __expf(s[2]); }
+    // opacity (+ antialias compensation)
+    float op_in = p.opacities[n];
+    float op = p.d.raw_params ? sigmoidf(op_in) : op_in;
+    float vcomp = 0.f;
+    if (p.d.antialiased) {
+      float comp = r1.y / fmaxf(op, 1e-30f);  // record opacity = op * comp
+      vcomp = vop * op;
+      vop = vop * comp;
+    }
+    if (p.d.raw_params) vop *= op * (1.f - op);
+    red_add(p.v_opacities + n, vop);
+    // colours
+    if (p.d.sh_degree >= 0) {
+      float cp[3] = {-(cam.R[0] * cam.t[0] + cam.R[3] * cam.t[1] + cam.R[6] * cam.t[2]),
+                     -(cam.R[1] * cam.t[0] + cam.R[4] * cam.t[1] + cam.R[7] * cam.t[2]),
+                     -(cam.R[2] * cam.t[0] + cam.R[5] * cam.t[1] + cam.R[8] * cam.t[2])};
+      float dx = mu[0] - cp[0], dy = mu[1] - cp[1], dz = mu[2] - cp[2];
+      float inv = rsqrtf(dx * dx + dy * dy + dz * dz);
+      float b[16];
+      sh_basis(p.d.sh_degree, dx * inv, dy * inv, dz * inv, b);
+      int nb = (p.d.sh_degree + 1) * (p.d.sh_degree + 1);
+      if (nb > p.d.sh_K) nb = p.d.sh_K;
+      // clamp(+0.5, 0, 1) passes gradient strictly inside (torch.clamp: also at the bounds; measure zero)
+      float vcol[3] = {(r1.z > 0.f && r1.z < 1.f) ? vr : 0.f, (r1.w > 0.f && r1.w < 1.f) ? vg : 0.f,
+                       (r2.x > 0.f && r2.x < 1.f) ? vbl : 0.f};
+      if (vcol[0] != 0.f || vcol[1] != 0.f || vcol[2] != 0.f) {
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) red_add(p.v_fdc + 3 * (size_t)n + ch, b[0] * vcol[ch]);
+        float* fr = p.v_frest + (size_t)n * (p.d.sh_K - 1) * 3;
+        for (int k = 1; k < nb; ++k) {
+#pragma unroll
+          for (int ch = 0; ch < 3; ++ch) red_add(fr + (k - 1) * 3 + ch, b[k] * vcol[ch]);
+        }
+      }
+    } else if (p.v_colors) {
+      float* cp = p.v_colors + (p.colors_per_cam ? 3 * (size_t)idx : 3 * (size_t)n);
+      red_add(cp, vr); red_add(cp + 1, vg); red_add(cp + 2, vbl);
+    }
+    // geometry
+    float v_mu[3] = {0.f, 0.f, 0.f}, v_q[4] = {0.f, 0.f, 0.f, 0.f}, v_s[3] = {0.f, 0.f, 0.f}, v_R[9], v_t[3];
+    project_gaussian_vjp(mu, q, s, cam, p.d.width, p.d.height, p.d.eps2d, vmx, vmy, vz, va, vb, vc, vcomp, v_mu, v_q,
+                         v_s, v_R, v_t);
+    if (p.d.raw_params) { v_s[0] *= s[0]; v_s[1] *= s[1]; v_s[2] *= s[2]; }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      red_add(p.v_means + 3 * (size_t)n + k, v_mu[k]);
+      red_add(p.v_scales + 3 * (size_t)n + k, v_s[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) red_add(p.v_quats + 4 * (size_t)n + k, v_q[k]);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      vview[i * 4] = v_R[i * 3]; vview[i * 4 + 1] = v_R[i * 3 + 1]; vview[i * 4 + 2] = v_R[i * 3 + 2];
+      vview[i * 4 + 3] = v_t[i];
+    }
+  }
+  if (p.v_viewmats) {
+    // slots are not grouped by camera: reduce per camera over the warp, then one atomic per value
+    for (int cam_i = 0; cam_i < p.d.n_cams; ++cam_i) {
+      bool mine = active && c == cam_i;
+      if (!__any_sync(0xffffffffu, mine)) continue;
+#pragma unroll
+      for (int k = 0; k < 12; ++k) {
+        float v = warp_sum(mine ? vview[k] : 0.f);
+        if ((threadIdx.x & 31) == 0 && v != 0.f) red_add(p.v_viewmats + 16 * cam_i + k, v);
+      }
+    }
+  }
+}
+
+// stand-alone SH ---------------------------------------------------------------------------------
+__global__ void sh_fwd_kernel(int n, int degree, int K, const float* __restrict__ dirs,
+                              const float* __restrict__ coeffs, float* __restrict__ out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float x = dirs[3 * (size_t)i], y = dirs[3 * (size_t)i + 1], z = dirs[3 * (size_t)i + 2];
+  float inv = rsqrtf(x * x + y * y + z * z);
+  float b[16];
+  sh_basis(degree, x * inv, y * inv, z * inv, b);
+  int nb = (degree + 1) * (degree + 1);
+  if (nb > K) nb = K;
+  const float* cf = coeffs + (size_t)i * K * 3;
+  float c0 = 0.f, c1 = 0.f, c2 = 0.f;
+  for (int k = 0; k < nb; ++k) {
+    c0 = fmaf(b[k], cf[3 * k], c0);
+    c1 = fmaf(b[k], cf[3 * k + 1], c1);
+    c2 = fmaf(b[k], cf[3 * k + 2], c2);
+  }
+  out[3 * (size_t)i] = c0; out[3 * (size_t)i + 1] = c1; out[3 * (size_t)i + 2] = c2;
+}
+
+__global__ void sh_bwd_kernel(int n, int degree, int K, const float* __restrict__ dirs,
+                              const float* __restrict__ coeffs, const float* __restrict__ v_out,
+                              float* __restrict__ v_coeffs, float* __restrict__ v_dirs) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float x = dirs[3 * (size_t)i], y = dirs[3 * (size_t)i + 1], z = dirs[3 * (size_t)i + 2];
+  float inv = rsqrtf(x * x + y * y + z * z);
+  float nx = x * inv, ny = y * inv, nz = z * inv;
+  float b[16];
+  sh_basis(degree, nx, ny, nz, b);
+  int nb = (degree + 1) * (degree + 1);
+  if (nb > K) nb = K;
+  float g0 = v_out[3 * (size_t)i], g1 = v_out[3 * (size_t)i + 1], g2 = v_out[3 * (size_t)i + 2];
+  float* vc = v_coeffs + (size_t)i * K * 3;
+  for (int k = 0; k < K; ++k) {
+    float bk = k < nb ? b[k] : 0.f;
+    vc[3 * k] = bk * g0; vc[3 * k + 1] = bk * g1; vc[3 * k + 2] = bk * g2;
+  }
+  if (v_dirs) {
+    float dbx[16], dby[16], dbz[16];
+    sh_basis_grad(degree, nx, ny, nz, dbx, dby, dbz);
+    const float* cf = coeffs + (size_t)i * K * 3;
+    float vx = 0.f, vy = 0.f, vz = 0.f;
+    for (int k = 0; k < nb; ++k) {
+      float w = cf[3 * k] * g0 + cf[3 * k + 1] * g1 + cf[3 * k + 2] * g2;
+      vx = fmaf(dbx[k], w, vx); vy = fmaf(dby[k], w, vy); vz = fmaf(dbz[k], w, vz);
+    }
+    float dot = nx * vx + ny * vy + nz * vz;  // through the normalisation
+    v_dirs[3 * (size_t)i] = (vx - nx * dot) * inv;
+    v_dirs[3 * (size_t)i + 1] = (vy - ny * dot) * inv;
+    v_dirs[3 * (size_t)i + 2] = (vz - nz * dot) * inv;
+  }
+}
+
+int check_render_desc(const bds_render_desc* d) {
+  BDS_REQUIRE(d, "render desc is null");
+  BDS_REQUIRE(d->n_gauss >= 0 && d->n_cams >= 1, "render desc: bad n_gauss/n_cams");
+  BDS_REQUIRE(d->width >= 1 && d->height >= 1, "render desc: empty image");
+  BDS_REQUIRE((int64_t)d->n_gauss * d->n_cams < (int64_t)1 << 31, "render desc: n_gauss*n_cams must fit int32");
+  int tile_h = (d->height + kTile - 1) / kTile;
+  BDS_REQUIRE(d->row_begin >= 0 && d->row_end >= d->row_begin && d->row_end <= d->n_cams * tile_h,
+              "render desc: band [%d,%d) outside [0,%d]", d->row_begin, d->row_end, d->n_cams * tile_h);
+  BDS_REQUIRE(d->sh_degree <= 3, "render desc: sh_degree <= 3 supported");
+  if (d->sh_degree >= 0) BDS_REQUIRE(d->sh_K >= 1 && d->sh_K <= 16, "render desc: sh_K out of range");
+  return 0;
+}
+
+}  // namespace bds
+
+using namespace bds;
+
+extern "C" int bds_project_fwd(const bds_render_desc* d, const float* means, const float* quats, const float* scales,
+                               const float* opacities, const float* colors, int colors_per_cam,
+                               const float* features_dc, const float* features_rest, const float* viewmats,
+                               const float* Ks, int32_t* radii, float* means2d, float* depths, float* conics,
+                               float* compensations, int32_t* tiles_touched, float* splats, int32_t splat_cap,
+                               int32_t* slot_of, int32_t* counters, bds_stream_t stream) {
+  if (int rc = check_render_desc(d)) return rc;
+  int64_t total = (int64_t)d->n_gauss * d->n_cams;
+  if (total == 0) return 0;
+  BDS_REQUIRE(means && quats && scales && opacities && viewmats && Ks && tiles_touched && splats && slot_of && counters,
+              "project_fwd: null pointer");
+  if (d->sh_degree >= 0)
+    BDS_REQUIRE(features_dc && (features_rest || d->sh_K == 1), "project_fwd: SH path needs features_dc/rest");
+  else
+    BDS_REQUIRE(colors, "project_fwd: colors required when sh_degree < 0");
+  ProjParams p;
+  p.d = *d;
+  p.tile_w = (d->width + kTile - 1) / kTile;
+  p.tile_h = (d->height + kTile - 1) / kTile;
+  p.means = means; p.quats = quats; p.scales = scales; p.opacities = opacities; p.colors = colors;
+  p.fdc = features_dc; p.frest = features_rest; p.viewmats = viewmats; p.Ks = Ks; p.colors_per_cam = colors_per_cam;
+  p.radii = radii; p.means2d = means2d; p.depths = depths; p.conics = conics; p.compensations = compensations;
+  p.tiles_touched = tiles_touched; p.splats = splats; p.splat_cap = splat_cap; p.slot_of = slot_of; p.counters = counters;
+  project_fwd_kernel<<<ceil_div(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  BDS_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int bds_project_bwd(const bds_render_desc* d, const float* means, const float* quats, const float* scales,
+                               const float* opacities, const float* colors, int colors_per_cam,
+                               const float* features_dc, const float* features_rest, const float* viewmats,
+                               const float* Ks, const float* splats, const int32_t* counters, const float* v_splats,
+                               const float* v_means2d_extra, const float* v_depths_extra, const float* v_conics_extra,
+                               float* v_means, float* v_quats, float* v_scales, float* v_opacities, float* v_colors,
+                               float* v_features_dc, float* v_features_rest, float* v_viewmats, float* v_means2d,
+                               float* absgrad, bds_stream_t stream) {
+  if (int rc = check_render_desc(d)) return rc;
+  int64_t total = (int64_t)d->n_gauss * d->n_cams;
+  if (total == 0) return 0;
+  BDS_REQUIRE(means && quats && scales && opacities && viewmats && Ks && splats && counters && v_splats,
+              "project_bwd: null input pointer");
+  BDS_REQUIRE(v_means && v_quats && v_scales && v_opacities, "project_bwd: null output pointer");
+  if (d->sh_degree >= 0) BDS_REQUIRE(v_features_dc && (v_features_rest || d->sh_K == 1), "project_bwd: SH grads missing");
+  ProjBwdParams p;
+  p.d = *d;
+  p.means = means; p.quats = quats; p.scales = scales; p.opacities = opacities; p.colors = colors;
+  p.fdc = features_dc; p.frest = features_rest; p.viewmats = viewmats; p.Ks = Ks; p.colors_per_cam = colors_per_cam;
+  p.splats = splats; p.counters = counters; p.v_splats = v_splats;
+  p.v_means2d_extra = v_means2d_extra; p.v_depths_extra = v_depths_extra; p.v_conics_extra = v_conics_extra;
+  p.v_means = v_means; p.v_quats = v_quats; p.v_scales = v_scales; p.v_opacities = v_opacities; p.v_colors = v_colors;
+  p.v_fdc = v_features_dc; p.v_frest = v_features_rest; p.v_viewmats = v_viewmats; p.v_means2d = v_means2d;
+  p.absgrad = absgrad;
+  // the slot count lives on the device; launch over the worst case (every (cam, gauss) visible) and
+  // let threads beyond counters[0] exit - the grid is cheap next to an extra host sync
+  project_bwd_kernel<<<ceil_div(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  BDS_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int bds_sh_fwd(int n, int degree, int K, const float* dirs, const float* coeffs, float* out,
+                          bds_stream_t stream) {
+  BDS_REQUIRE(n >= 0 && degree >= 0 && degree <= 3 && K >= 1, "sh_fwd: degree in [0,3], K >= 1");
+  if (n == 0) return 0;
+  BDS_REQUIRE(dirs && coeffs && out, "sh_fwd: null pointer");
+  sh_fwd_kernel<<<ceil_div(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(n, degree, K, dirs, coeffs, out);
+  BDS_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int bds_sh_bwd(int n, int degree, int K, const float* dirs, const float* coeffs, const float* v_out,
+                          float* v_coeffs, float* v_dirs, bds_stream_t stream) {
+  BDS_REQUIRE(n >= 0 && degree >= 0 && degree <= 3 && K >= 1, "sh_bwd: degree in [0,3], K >= 1");
+  if (n == 0) return 0;
+  BDS_REQUIRE(dirs && coeffs && v_out && v_coeffs, "sh_bwd: null pointer");
+  sh_bwd_kernel<<<ceil_div(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(n, degree, K, dirs, coeffs, v_out, v_coeffs,
+                                                                                v_dirs);
+  BDS_CHECK_LAUNCH();
+  return 0;
+}

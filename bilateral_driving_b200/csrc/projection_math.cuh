@@ -297,4 +297,21 @@ BDS_HD float min_sigma_rect(float gx, float gy, float qa, float qb, float qc, fl
 }
 constexpr float kCullMargin = 0.02f;  // slack on sigma' (log2 units) so rounding never culls a contributor
 
+// Does the splat reach alpha >= 1/255 on some pixel centre of tile (tx, ty)?  NOT inlined on the
+// device: the counting pass (projection.cu) and the emission pass (binning.cu) must take the very
+// same decision, so both call this one body compiled from this one source.
+#ifdef __CUDACC__
+static __host__ __device__ __noinline__
+#else
+static inline
+#endif
+bool tile_hit(float gx, float gy, float qa, float qb, float qc, float sigma_cut, int tx, int ty, int width,
+              int height) {
+  float xmin = (float)(tx * kTile) + 0.5f, ymin = (float)(ty * kTile) + 0.5f;
+  float xmax = fminf((float)(tx * kTile + kTile) - 0.5f, (float)width - 0.5f);
+  float ymax = fminf((float)(ty * kTile + kTile) - 0.5f, (float)height - 0.5f);
+  float s = min_sigma_rect(gx, gy, qa, qb, qc, xmin, xmax, ymin, ymax);
+  return !(s > sigma_cut + kCullMargin);
+}
+
 }  // namespace bds

@@ -1,0 +1,413 @@
+"""Differentiable Gaussian-splat render over the sm_100a kernels: one autograd Function that runs
+project(+activations+SH) -> bin/sort -> fused composite(+glue+bilateral) and its backward.
+
+Public entry points
+
+* ``rasterization(...)``         gsplat v1.3.0-shaped call the reference makes at
+                                 ``models/trainers/base.py:393-408`` (import seam
+                                 ``models/gaussians/basics.py:12``).
+* ``spherical_harmonics(...)``   ``gsplat.cuda._wrapper.spherical_harmonics`` as called at
+                                 ``models/gaussians/vanilla.py:383-389``.
+* ``render_fused(...)``          the whole hot path of one training step in one op: raw
+                                 ``VanillaGaussians`` parameters (vanilla.py:122-146 activations and SH
+                                 fused), reference glue (clamp, RGB+ED, sky composite:
+                                 base.py:414-417, scene_graph.py:287-294) and the multi-scale bilateral
+                                 chain (modules.py:505-584, scene_graph.py:112-117) fused in the
+                                 composite kernel.
+
+No torch/CPU fallback exists: every op raises if the tensors are not on a CUDA device.
+"""
+import ctypes as C
+import math
+import weakref
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from ._lib import (TILE, BdsError, BilateralDesc, EpilogueDesc, RenderDesc, check, lib, ptr, ptr_array,
+                   require_cuda, stream_ptr)
+
+NULL = C.c_void_p(0)
+
+
+@dataclass
+class RenderCfg:
+    width: int
+    height: int
+    near_plane: float = 0.01
+    far_plane: float = 1e10
+    radius_clip: float = 0.0
+    eps2d: float = 0.3
+    antialiased: bool = False
+    row_begin: int = 0
+    row_end: int = -1          # -1 = all tile rows of all cameras
+    raw_params: bool = False   # log-scales / logit opacities (VanillaGaussians fast path)
+    sh_degree: int = -1        # >= 0: colours from features_dc / features_rest
+    mode: int = 0              # 0 gsplat outputs, 1 + reference glue, 2 + bilateral chain (full-res guidance)
+    channels: int = 3
+    expected_depth: bool = False
+    bil_sizes: Tuple = ()      # ((grid_X, grid_Y, grid_W), ...)
+    absgrad: bool = False
+    dense_info: bool = True    # write gsplat-shaped means2d / depths / conics
+    splat_capacity: Optional[int] = None
+
+    def tiles(self):
+        return (self.width + TILE - 1) // TILE, (self.height + TILE - 1) // TILE
+
+
+def _desc(cfg: RenderCfg, N: int, Cn: int, sh_K: int) -> RenderDesc:
+    tw, th = cfg.tiles()
+    d = RenderDesc()
+    d.n_gauss, d.n_cams, d.width, d.height = N, Cn, cfg.width, cfg.height
+    d.near_plane, d.far_plane, d.radius_clip, d.eps2d = cfg.near_plane, min(cfg.far_plane, 3.0e38), cfg.radius_clip, cfg.eps2d
+    d.antialiased = int(cfg.antialiased)
+    d.row_begin = cfg.row_begin
+    d.row_end = Cn * th if cfg.row_end < 0 else cfg.row_end
+    d.raw_params = int(cfg.raw_params)
+    d.sh_degree = cfg.sh_degree
+    d.sh_K = sh_K
+    return d
+
+
+def _epilogue(cfg: RenderCfg) -> EpilogueDesc:
+    e = EpilogueDesc()
+    e.mode, e.channels, e.expected_depth = cfg.mode, cfg.channels, int(cfg.expected_depth)
+    if cfg.mode == 2:
+        e.bil = BilateralDesc.make(cfg.bil_sizes, None)
+    return e
+
+
+def band_pixel_rows(cfg: RenderCfg, Cn: int) -> Tuple[int, int]:
+    """Stacked pixel rows (c*H + y) covered by the band [row_begin, row_end) of tile rows."""
+    tw, th = cfg.tiles()
+    rb = cfg.row_begin
+    re = Cn * th if cfg.row_end < 0 else cfg.row_end
+
+    def row_of(gr):
+        c, ty = divmod(gr, th)
+        return c * cfg.height + min(ty * TILE, cfg.height)
+
+    return row_of(rb), (row_of(re) if re < Cn * th else Cn * cfg.height)
+
+
+class _RenderFn(torch.autograd.Function):
+    """Inputs (tensors, may be None): means, quats, scales, opacities, colors, features_dc,
+    features_rest, viewmats, Ks, backgrounds, sky, *grids (C * n_levels slots [12,L,GY,GX]).
+    Outputs: out_rgb, out_rgb_gauss, out_depth, out_alpha, means2d (dense or empty), radii."""
+
+    @staticmethod
+    def forward(ctx, cfg: RenderCfg, holder: dict, means, quats, scales, opacities, colors, fdc, frest, viewmats,
+                Ks, backgrounds, sky, *grids):
+        require_cuda(means, quats, scales, opacities, colors, fdc, frest, viewmats, Ks, backgrounds, sky, *grids)
+        dev = means.device
+        f32 = dict(device=dev, dtype=torch.float32)
+        i32 = dict(device=dev, dtype=torch.int32)
+        cont = lambda t: None if t is None else t.contiguous().float()  # noqa: E731
+        means, quats, scales, opacities, colors, fdc, frest, viewmats, Ks, backgrounds, sky = map(
+            cont, (means, quats, scales, opacities, colors, fdc, frest, viewmats, Ks, backgrounds, sky))
+        grids = [None if g is None else g.contiguous().float() for g in grids]
+        N, Cn = means.shape[0], viewmats.shape[0]
+        sh_K = 0
+        if cfg.sh_degree >= 0:
+            sh_K = 1 + (0 if frest is None else frest.shape[1])
+        d = _desc(cfg, N, Cn, sh_K)
+        e = _epilogue(cfg)
+        tw, th = cfg.tiles()
+        n_band_tiles = (d.row_end - d.row_begin) * tw
+        r0, r1 = band_pixel_rows(cfg, Cn)
+        P = (r1 - r0) * cfg.width
+        colors_per_cam = int(colors is not None and colors.dim() == 3)
+
+        radii = torch.zeros(Cn, N, **i32)
+        if cfg.dense_info:
+            means2d = torch.zeros(Cn, N, 2, **f32)
+            depths = torch.zeros(Cn, N, **f32)
+            conics = torch.zeros(Cn, N, 3, **f32)
+        else:
+            means2d = depths = conics = None
+        comps = torch.zeros(Cn, N, **f32) if (cfg.antialiased and cfg.dense_info) else None
+        tiles_touched = torch.empty(Cn, N, **i32)
+        slot_of = torch.empty(Cn, N, **i32)
+        counters = torch.zeros(4, **i32)
+        cap = cfg.splat_capacity or max(Cn * N, 1)
+        splats = torch.empty(cap, 12, **f32)
+        st = stream_ptr()
+        check(lib.bds_project_fwd(C.byref(d), ptr(means), ptr(quats), ptr(scales), ptr(opacities), ptr(colors),
+                                  colors_per_cam, ptr(fdc), ptr(frest), ptr(viewmats), ptr(Ks), ptr(radii),
+                                  ptr(means2d), ptr(depths), ptr(conics), ptr(comps), ptr(tiles_touched), ptr(splats),
+                                  C.c_int32(cap), ptr(slot_of), ptr(counters), st), "bds_project_fwd")
+        offsets = torch.empty(Cn * N, device=dev, dtype=torch.int64)
+        stats = torch.zeros(1, device=dev, dtype=torch.int64)
+        ws0 = torch.empty(int(lib.bds_bin_count_workspace_bytes(C.c_int64(Cn * N))), device=dev, dtype=torch.uint8)
+        check(lib.bds_bin_count(C.byref(d), ptr(tiles_touched), ptr(offsets), ptr(stats), ptr(ws0), st), "bds_bin_count")
+        # the one host sync of the step: intersection count (sizes the sort) + slot count / overflow flag
+        host = torch.cat([stats, counters[:2].to(torch.int64)]).tolist()
+        n_isect, n_slots, overflow = int(host[0]), int(host[1]), int(host[2])
+        if overflow:
+            raise BdsError(f"splat capacity {cap} exceeded ({n_slots} visible splats); raise RenderCfg.splat_capacity")
+        sorted_splats = torch.empty(max(n_isect, 1), 12, **f32)
+        tile_offsets = torch.empty(n_band_tiles + 1, **i32)
+        ws1 = torch.empty(int(lib.bds_bin_sort_workspace_bytes(C.byref(d), C.c_int64(n_isect))), device=dev,
+                          dtype=torch.uint8)
+        check(lib.bds_bin_sort(C.byref(d), C.c_int64(n_isect), ptr(radii), ptr(tiles_touched), ptr(slot_of),
+                               ptr(offsets), ptr(splats), ptr(sorted_splats), NULL, ptr(tile_offsets), ptr(ws1), st),
+              "bds_bin_sort")
+        del ws1, offsets
+        ch = cfg.channels if cfg.mode == 0 else 3
+        out_rgb = torch.empty(P, ch, **f32)
+        out_alpha = torch.empty(P, **f32)
+        last_ids = torch.empty(P, **i32)
+        out_rgbg = torch.empty(P, 3, **f32) if cfg.mode != 0 else None
+        out_depth = torch.empty(P, **f32) if cfg.mode != 0 else None
+        ws2 = torch.empty(int(lib.bds_composite_workspace_bytes(C.byref(d), C.byref(e))), device=dev, dtype=torch.uint8)
+        check(lib.bds_composite_fwd(C.byref(d), C.byref(e), ptr(sorted_splats), ptr(tile_offsets), ptr(backgrounds),
+                                    ptr(sky), ptr_array(grids) if grids else NULL, ptr(out_rgb), ptr(out_rgbg),
+                                    ptr(out_depth), ptr(out_alpha), ptr(last_ids), ptr(ws2), st), "bds_composite_fwd")
+        ctx.cfg, ctx.d, ctx.e, ctx.holder = cfg, d, e, holder
+        ctx.n_slots, ctx.n_isect, ctx.colors_per_cam, ctx.n_grids = n_slots, n_isect, colors_per_cam, len(grids)
+        ctx.has = dict(colors=colors is not None, sky=sky is not None, bg=backgrounds is not None)
+        ctx.save_for_backward(means, quats, scales, opacities, colors, fdc, frest, viewmats, Ks, backgrounds, sky,
+                              splats, counters, sorted_splats, tile_offsets, out_rgbg, out_depth, out_alpha, last_ids,
+                              out_rgb if (cfg.mode == 0 and cfg.channels == 4 and cfg.expected_depth) else None, *grids)
+        holder.update(n_isect=n_isect, n_visible=n_slots, depths=depths, conics=conics, tiles_touched=tiles_touched,
+                      tile_offsets=tile_offsets, compensations=comps, sorted_splats=sorted_splats, last_ids=last_ids)
+        m2d = means2d if means2d is not None else torch.empty(0, **f32)
+        ctx.mark_non_differentiable(radii)
+        return (out_rgb, out_rgbg if out_rgbg is not None else torch.empty(0, **f32),
+                out_depth if out_depth is not None else torch.empty(0, **f32), out_alpha, m2d, radii)
+
+    @staticmethod
+    def backward(ctx, v_rgb, v_rgbg, v_depth, v_alpha, v_means2d_extra, _v_radii):
+        cfg, d, e = ctx.cfg, ctx.d, ctx.e
+        (means, quats, scales, opacities, colors, fdc, frest, viewmats, Ks, backgrounds, sky, splats, counters,
+         sorted_splats, tile_offsets, out_rgbg, out_depth, out_alpha, last_ids, out_rgb_ed, *grids) = ctx.saved_tensors
+        dev = means.device
+        f32 = dict(device=dev, dtype=torch.float32)
+        N, Cn = means.shape[0], viewmats.shape[0]
+        st = stream_ptr()
+        cont = lambda t: None if t is None else t.contiguous().float()  # noqa: E731
+        v_rgb, v_rgbg, v_depth, v_alpha = map(cont, (v_rgb, v_rgbg, v_depth, v_alpha))
+        if v_rgb is None:
+            v_rgb = torch.zeros(out_alpha.shape[0], cfg.channels if cfg.mode == 0 else 3, **f32)
+        if cfg.mode == 0:
+            v_rgbg = None
+            v_depth_in = None
+            depth_for_ed = out_rgb_ed[:, 3].contiguous() if out_rgb_ed is not None else None
+        else:
+            depth_for_ed = out_depth
+            v_depth_in = v_depth
+            if v_rgbg is not None and v_rgbg.numel() == 0:
+                v_rgbg = None
+        v_splats = torch.zeros(max(ctx.n_slots, 1), 12, **f32)
+        need = ctx.needs_input_grad  # (cfg, holder, means, quats, scales, opac, colors, fdc, frest, viewmats, Ks, bg, sky, *grids)
+        v_sky = torch.empty_like(sky) if (sky is not None and need[12]) else None
+        v_bg = torch.zeros_like(backgrounds) if (backgrounds is not None and need[11]) else None
+        v_grids = [None if g is None else torch.zeros_like(g) for g in grids]
+        ws2 = torch.empty(int(lib.bds_composite_workspace_bytes(C.byref(d), C.byref(e))), device=dev, dtype=torch.uint8)
+        check(lib.bds_composite_bwd(C.byref(d), C.byref(e), ptr(sorted_splats), NULL, ptr(tile_offsets), ptr(backgrounds),
+                                    ptr(sky), ptr_array(grids) if grids else NULL, ptr(out_rgbg), ptr(depth_for_ed),
+                                    ptr(out_alpha), ptr(last_ids), ptr(v_rgb), ptr(v_rgbg), ptr(v_depth_in), ptr(v_alpha),
+                                    ptr(v_splats), ptr(v_sky), ptr_array(v_grids) if grids else NULL, ptr(v_bg), ptr(ws2),
+                                    st), "bds_composite_bwd")
+        v_means = torch.zeros_like(means)
+        v_quats = torch.zeros_like(quats)
+        v_scales = torch.zeros_like(scales)
+        v_opac = torch.zeros_like(opacities)
+        v_colors = torch.zeros_like(colors) if colors is not None else None
+        v_fdc = torch.zeros_like(fdc) if fdc is not None else None
+        v_frest = torch.zeros_like(frest) if frest is not None else None
+        v_view = torch.zeros_like(viewmats) if need[9] else None
+        want_taps = cfg.dense_info
+        v_m2d = torch.zeros(Cn, N, 2, **f32) if want_taps else None
+        absg = torch.zeros(Cn, N, 2, **f32) if (want_taps and cfg.absgrad) else None
+        extra = None
+        if v_means2d_extra is not None and v_means2d_extra.numel() > 0:
+            extra = v_means2d_extra.contiguous().float()
+        check(lib.bds_project_bwd(C.byref(d), ptr(means), ptr(quats), ptr(scales), ptr(opacities), ptr(colors),
+                                  ctx.colors_per_cam, ptr(fdc), ptr(frest), ptr(viewmats), ptr(Ks), ptr(splats),
+                                  ptr(counters), ptr(v_splats), ptr(extra), NULL, NULL, ptr(v_means), ptr(v_quats),
+                                  ptr(v_scales), ptr(v_opac), ptr(v_colors), ptr(v_fdc), ptr(v_frest), ptr(v_view),
+                                  ptr(v_m2d), ptr(absg), st), "bds_project_bwd")
+        # densification taps (base.py:279-297 reads info["means2d"].grad / .absgrad)
+        ref = ctx.holder.get("means2d_ref")
+        m2d = ref() if ref is not None else None
+        if m2d is not None and want_taps:
+            total = v_m2d if extra is None else v_m2d + extra
+            if m2d.retains_grad or m2d.is_leaf:
+                m2d.grad = total
+            if absg is not None:
+                m2d.absgrad = absg
+        ctx.holder["v_splats"] = v_splats
+        return (None, None, v_means, v_quats, v_scales, v_opac, v_colors, v_fdc, v_frest, v_view, None, v_bg, v_sky,
+                *v_grids)
+
+
+def _run(cfg: RenderCfg, means, quats, scales, opacities, colors, fdc, frest, viewmats, Ks, backgrounds, sky, grids):
+    holder: dict = {}
+    outs = _RenderFn.apply(cfg, holder, means, quats, scales, opacities, colors, fdc, frest, viewmats, Ks, backgrounds,
+                           sky, *grids)
+    out_rgb, out_rgbg, out_depth, out_alpha, means2d, radii = outs
+    if means2d.numel() > 0:
+        holder["means2d_ref"] = weakref.ref(means2d)
+    return out_rgb, out_rgbg, out_depth, out_alpha, means2d, radii, holder
+
+
+def _as_int(v) -> int:
+    """width / height arrive as python ints or 0-dim (CUDA) int64 tensors (pixel_source.py:653-654)."""
+    return int(v.item()) if torch.is_tensor(v) else int(v)
+
+
+def rasterization(means, quats, scales, opacities, colors, viewmats, Ks, width, height, near_plane=0.01,
+                  far_plane=1e10, radius_clip=0.0, eps2d=0.3, sh_degree=None, packed=True, tile_size=16,
+                  backgrounds=None, render_mode="RGB", sparse_grad=False, absgrad=False, rasterize_mode="classic",
+                  channel_chunk=32, distributed=False, covars=None, **unsupported):
+    """gsplat v1.3.0-shaped ``rasterization``.  Returns
+    ``(render_colors [C,H,W,D], render_alphas [C,H,W,1], info)``.
+
+    ``packed`` only changes the layout of gsplat's intermediate tensors, not the images: it is
+    accepted and the (unpacked) info layout the reference trainer reads is always returned.
+    """
+    if unsupported:
+        raise NotImplementedError(f"unsupported rasterization arguments: {sorted(unsupported)}")
+    if sparse_grad:
+        raise NotImplementedError("sparse_grad=True is not built (reference config: sparse_grad: false)")
+    if distributed:
+        raise NotImplementedError("gsplat's distributed=True path is not built; see bilateral_driving_b200.dist")
+    if covars is not None:
+        raise NotImplementedError("covars input is not built (the reference passes quats/scales)")
+    if tile_size != 16:
+        raise NotImplementedError("tile_size must be 16")
+    if render_mode not in ("RGB", "D", "ED", "RGB+D", "RGB+ED"):
+        raise ValueError(f"unknown render_mode {render_mode}")
+    if rasterize_mode not in ("classic", "antialiased"):
+        raise ValueError(f"unknown rasterize_mode {rasterize_mode}")
+    if render_mode in ("D", "ED"):
+        raise NotImplementedError("depth-only render modes are not built (reference uses RGB and RGB+ED)")
+    W, H = _as_int(width), _as_int(height)
+    N, Cn = means.shape[0], viewmats.shape[0]
+    assert quats.shape == (N, 4) and scales.shape == (N, 3) and opacities.shape == (N,), "bad Gaussian shapes"
+    assert viewmats.shape == (Cn, 4, 4) and Ks.shape == (Cn, 3, 3), "bad camera shapes"
+    if sh_degree is not None:
+        # gsplat would evaluate SH itself and apply clamp(sh + 0.5, min=0); the reference never passes
+        # sh_degree (it evaluates colours first, vanilla.py:383-389). The fused SH fast path with the
+        # reference's own clamp(+0.5, 0, 1) is render_fused().
+        raise NotImplementedError("pass evaluated colours (as the reference does); use render_fused for the SH fast path")
+    if colors.shape[-1] != 3:
+        raise NotImplementedError("only 3-channel colours are built (reference: rgbs [N,3])")
+    fdc = frest = None
+    colors_in, deg = colors, -1
+    D = 4 if render_mode in ("RGB+D", "RGB+ED") else 3
+    bg = backgrounds
+    if bg is not None and D == 4:
+        bg = torch.cat([bg, torch.zeros(bg.shape[0], 1, device=bg.device, dtype=bg.dtype)], dim=-1)
+    cfg = RenderCfg(width=W, height=H, near_plane=float(near_plane), far_plane=float(far_plane),
+                    radius_clip=float(radius_clip), eps2d=float(eps2d), antialiased=rasterize_mode == "antialiased",
+                    sh_degree=deg, mode=0, channels=D, expected_depth=render_mode == "RGB+ED", absgrad=bool(absgrad))
+    out_rgb, _, _, out_alpha, means2d, radii, holder = _run(cfg, means, quats, scales, opacities, colors_in, fdc, frest,
+                                                            viewmats, Ks, bg, None, [])
+    renders = out_rgb.view(Cn, H, W, D)
+    alphas = out_alpha.view(Cn, H, W, 1)
+    tw, th = cfg.tiles()
+    info = {
+        "camera_ids": None, "gaussian_ids": None, "radii": radii, "means2d": means2d, "depths": holder["depths"],
+        "conics": holder["conics"], "opacities": opacities.expand(Cn, N) if opacities.dim() == 1 else opacities,
+        "tile_width": tw, "tile_height": th, "tiles_per_gauss": holder["tiles_touched"],
+        "isect_offsets": holder["tile_offsets"][:-1].view(Cn, th, tw), "width": W, "height": H, "tile_size": 16,
+        "n_cameras": Cn, "n_isect": holder["n_isect"], "n_visible": holder["n_visible"],
+    }
+    return renders, alphas, info
+
+
+class _SHFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, degree, dirs, coeffs):
+        require_cuda(dirs, coeffs)
+        d2 = dirs.reshape(-1, 3).contiguous().float()
+        K = coeffs.shape[-2]
+        c2 = coeffs.reshape(-1, K, 3).contiguous().float()
+        out = torch.empty(d2.shape[0], 3, device=d2.device, dtype=torch.float32)
+        check(lib.bds_sh_fwd(d2.shape[0], degree, K, ptr(d2), ptr(c2), ptr(out), stream_ptr()), "bds_sh_fwd")
+        ctx.save_for_backward(d2, c2)
+        ctx.degree, ctx.shape_d, ctx.shape_c = degree, dirs.shape, coeffs.shape
+        return out.view(*dirs.shape[:-1], 3)
+
+    @staticmethod
+    def backward(ctx, v_out):
+        d2, c2 = ctx.saved_tensors
+        K = c2.shape[1]
+        v_out = v_out.reshape(-1, 3).contiguous().float()
+        v_c = torch.empty_like(c2)
+        v_d = torch.empty_like(d2) if ctx.needs_input_grad[1] else None
+        check(lib.bds_sh_bwd(d2.shape[0], ctx.degree, K, ptr(d2), ptr(c2), ptr(v_out), ptr(v_c), ptr(v_d), stream_ptr()),
+              "bds_sh_bwd")
+        return None, (None if v_d is None else v_d.view(ctx.shape_d)), v_c.view(ctx.shape_c)
+
+
+def spherical_harmonics(degrees_to_use: int, dirs, coeffs, masks=None):
+    """gsplat.cuda._wrapper.spherical_harmonics: dirs [...,3], coeffs [...,K,3] -> [...,3]."""
+    assert (degrees_to_use + 1) ** 2 <= coeffs.shape[-2], coeffs.shape
+    assert dirs.shape[:-1] == coeffs.shape[:-2], (dirs.shape, coeffs.shape)
+    assert dirs.shape[-1] == 3 and coeffs.shape[-1] == 3
+    out = _SHFn.apply(int(degrees_to_use), dirs, coeffs)
+    if masks is not None:
+        out = out * masks[..., None]
+    return out
+
+
+def num_sh_bases(degree: int) -> int:
+    """gsplat.cuda_legacy._wrapper.num_sh_bases."""
+    if degree > 4:
+        raise ValueError("degree <= 4")
+    return (degree + 1) ** 2
+
+
+def quat_to_rotmat(quat):
+    """gsplat.cuda_legacy._torch_impl.quat_to_rotmat (plain torch glue used by the node models)."""
+    assert quat.shape[-1] == 4, quat.shape
+    w, x, y, z = torch.unbind(torch.nn.functional.normalize(quat, dim=-1), dim=-1)
+    mat = torch.stack(
+        [1 - 2 * (y ** 2 + z ** 2), 2 * (x * y - w * z), 2 * (x * z + w * y),
+         2 * (x * y + w * z), 1 - 2 * (x ** 2 + z ** 2), 2 * (y * z - w * x),
+         2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x ** 2 + y ** 2)], dim=-1)
+    return mat.reshape(quat.shape[:-1] + (3, 3))
+
+
+def render_fused(params: Dict[str, torch.Tensor], viewmats, Ks, width: int, height: int, sky=None,
+                 grid_slots: Optional[Sequence[Sequence[torch.Tensor]]] = None, bil_sizes=(), sh_degree: int = 3,
+                 near_plane: float = 0.1, far_plane: float = 1e10, radius_clip: float = 0.0, absgrad: bool = True,
+                 row_begin: int = 0, row_end: int = -1, activated: bool = False, dense_info: bool = False,
+                 antialiased: bool = False):
+    """One fused pass of the hot path for C cameras.
+
+    ``params``: ``_means [N,3], _scales (log) [N,3], _quats [N,4], _opacities (logit) [N] or [N,1],
+    _features_dc [N,3], _features_rest [N,K-1,3]`` (``activated=True``: scales/opacities already
+    activated and ``_rgbs [N,3]`` given instead of SH features).
+    ``grid_slots[c][l]`` = camera c's grid slot ``[12,L,GY,GX]`` of level l (mode 2), or None for
+    mode 1 (reference glue only; run the low-res-guidance bilateral afterwards).
+    Returns dict(rgb, rgb_gaussians, depth, opacity [band pixels ...], radii, info).
+    """
+    Cn = viewmats.shape[0]
+    mode = 2 if grid_slots is not None else 1
+    cfg = RenderCfg(width=width, height=height, near_plane=near_plane, far_plane=far_plane, radius_clip=radius_clip,
+                    antialiased=antialiased, row_begin=row_begin, row_end=row_end, raw_params=not activated,
+                    sh_degree=-1 if activated else sh_degree, mode=mode, channels=4, expected_depth=True,
+                    bil_sizes=tuple(tuple(s) for s in bil_sizes), absgrad=absgrad, dense_info=dense_info)
+    grids: List[Optional[torch.Tensor]] = []
+    if mode == 2:
+        assert len(grid_slots) == Cn and all(len(g) == len(bil_sizes) for g in grid_slots if g is not None)
+        for c in range(Cn):
+            grids += list(grid_slots[c]) if grid_slots[c] is not None else [None] * len(bil_sizes)
+    opac = params["_opacities"].reshape(-1)
+    if activated:
+        out = _run(cfg, params["_means"], params["_quats"], params["_scales"], opac, params["_rgbs"], None, None,
+                   viewmats, Ks, None, sky, grids)
+    else:
+        out = _run(cfg, params["_means"], params["_quats"], params["_scales"], opac, None, params["_features_dc"],
+                   params["_features_rest"], viewmats, Ks, None, sky, grids)
+    out_rgb, out_rgbg, out_depth, out_alpha, means2d, radii, holder = out
+    r0, r1 = band_pixel_rows(cfg, Cn)
+    rows = r1 - r0
+    return dict(rgb=out_rgb.view(rows, width, 3), rgb_gaussians=out_rgbg.view(rows, width, 3),
+                depth=out_depth.view(rows, width, 1), opacity=out_alpha.view(rows, width, 1), radii=radii,
+                means2d=means2d, info=holder, pixel_rows=(r0, r1))

@@ -143,8 +143,8 @@ int bds_bin_count(const bds_render_desc* d, const int32_t* tiles_touched, int64_
 size_t bds_bin_sort_workspace_bytes(const bds_render_desc* d, int64_t n_isect);
 /* sorted_splats [n_isect,12]; sorted_slots [n_isect] int32 (record -> splat slot);
  * tile_offsets [n_band_tiles + 1] int32 where band tile t = (global_row - row_begin)*tile_w + tx */
-int bds_bin_sort(const bds_render_desc* d, int64_t n_isect, const int32_t* radii, const float* means2d,
-                 const float* depths, const int32_t* slot_of, const int64_t* isect_offsets,
+int bds_bin_sort(const bds_render_desc* d, int64_t n_isect, const int32_t* radii,
+                 const int32_t* tiles_touched, const int32_t* slot_of, const int64_t* isect_offsets,
                  const float* splats, float* sorted_splats, int32_t* sorted_slots,
                  int32_t* tile_offsets, void* workspace, bds_stream_t stream);
 

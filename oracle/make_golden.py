@@ -114,10 +114,12 @@ def raster_small():
         cols.append((sh_ref.spherical_harmonics(3, dirs, coeffs) + 0.5).clamp(0, 1))
     r, a, info = R.rasterization(leaves["_means"], quats, scales, opac, torch.stack(cols), vm, Ks, W, H,
                                  near_plane=0.1, render_mode="RGB+ED")
-    Gr = torch.randn(r.shape, generator=gen(3), dtype=r.dtype)
-    Ga = torch.randn(a.shape, generator=gen(4), dtype=r.dtype)
+    keep = (~info["ambiguous"])[..., None].to(r.dtype)  # ambiguous pixels carry no loss
+    Gr = torch.randn(r.shape, generator=gen(3), dtype=r.dtype) * keep
+    Ga = torch.randn(a.shape, generator=gen(4), dtype=r.dtype) * keep
     ((r * Gr).sum() + (a * Ga).sum()).backward()
     out = dict(render=r.detach().numpy(), alpha=a.detach().numpy(), ambiguous=info["ambiguous"].numpy(),
+               Gr=Gr.numpy(), Ga=Ga.numpy(),
                radii=info["radii"].numpy(), means2d=info["means2d"].detach().numpy(),
                conics=info["conics"].detach().numpy(), depths=info["depths"].detach().numpy(),
                n_isect=np.array(info["n_isect"]))
