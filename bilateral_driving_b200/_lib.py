@@ -66,6 +66,8 @@ def _load():
     lib.bds_last_error.restype = C.c_char_p
     lib.bds_abi_version.restype = C.c_int
     lib.bds_device_arch.restype = C.c_int
+    if hasattr(lib, "bds_launch_count"):
+        lib.bds_launch_count.restype = C.c_ulonglong
     for name in ("bds_bilateral_workspace_bytes", "bds_bin_count_workspace_bytes",
                  "bds_bin_sort_workspace_bytes", "bds_composite_workspace_bytes"):
         if hasattr(lib, name):
@@ -77,7 +79,7 @@ lib = _load()
 
 # every symbol include/bds.h declares; tests/test_abi.py checks they are all exported
 ABI_SYMBOLS = (
-    "bds_last_error", "bds_abi_version", "bds_device_arch",
+    "bds_last_error", "bds_abi_version", "bds_device_arch", "bds_launch_count",
     "bds_bilateral_workspace_bytes", "bds_bilateral_fwd", "bds_bilateral_bwd",
     "bds_bilagrid_slice_fwd", "bds_bilagrid_slice_bwd", "bds_tv_fwd_bwd",
     "bds_sh_fwd", "bds_sh_bwd",

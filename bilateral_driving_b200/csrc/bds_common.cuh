@@ -31,7 +31,14 @@ void set_error(const char* fmt, ...);
     }                                 \
   } while (0)
 
-#define BDS_CHECK_LAUNCH() BDS_CHECK_CUDA(cudaGetLastError())
+extern unsigned long long g_launches;  // kernels launched by this library (statistics only)
+}  // namespace bds
+#define BDS_CHECK_LAUNCH()      \
+  do {                          \
+    ++bds::g_launches;          \
+    BDS_CHECK_CUDA(cudaGetLastError()); \
+  } while (0)
+namespace bds {
 
 static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }

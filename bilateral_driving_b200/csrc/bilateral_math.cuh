@@ -22,9 +22,17 @@ struct LinTap {
   int i0, i1;
   float t;
 };
+// IEEE division even under --use_fast_math: the resize taps must round like torch's fp32 ones
+BDS_HD float div_rn(float a, float b) {
+#ifdef __CUDA_ARCH__
+  return __fdiv_rn(a, b);
+#else
+  return a / b;
+#endif
+}
 BDS_HD LinTap lin_src(int d, int in_size, int out_size) {
   LinTap r;
-  float scale = (float)in_size / (float)out_size;
+  float scale = div_rn((float)in_size, (float)out_size);
   float s = scale * ((float)d + 0.5f) - 0.5f;
   if (s < 0.f) s = 0.f;
   int i0 = (int)s;
@@ -38,7 +46,7 @@ BDS_HD LinTap lin_src(int d, int in_size, int out_size) {
 // torch.linspace(0, 1, n)[j] in fp32 (symmetric evaluation, as ATen does)
 BDS_HD float lin01(int j, int n) {
   if (n <= 1) return 0.f;
-  float step = 1.0f / (float)(n - 1);
+  float step = div_rn(1.0f, (float)(n - 1));
   return (j < n / 2) ? step * (float)j : 1.0f - step * (float)(n - 1 - j);
 }
 

@@ -346,8 +346,9 @@ extern "C" size_t bds_bin_count_workspace_bytes(int64_t n_elems) { return scan_w
 extern "C" int bds_bin_count(const bds_render_desc* d, const int32_t* tiles_touched, int64_t* isect_offsets,
                              int64_t* n_isect_dev, void* workspace, bds_stream_t stream) {
   if (int rc = check_render_desc(d)) return rc;
-  BDS_REQUIRE(tiles_touched && isect_offsets && n_isect_dev && workspace, "bin_count: null pointer");
   int64_t n = (int64_t)d->n_gauss * d->n_cams;
+  BDS_REQUIRE(n_isect_dev, "bin_count: null n_isect pointer");
+  if (n > 0) BDS_REQUIRE(tiles_touched && isect_offsets && workspace, "bin_count: null pointer");
   return exclusive_scan<int32_t, int64_t>(tiles_touched, isect_offsets, n, n_isect_dev, workspace,
                                           static_cast<cudaStream_t>(stream));
 }
@@ -363,7 +364,9 @@ extern "C" int bds_bin_sort(const bds_render_desc* d, int64_t n_isect, const int
                             void* workspace, bds_stream_t stream_) {
   if (int rc = check_render_desc(d)) return rc;
   BDS_REQUIRE(n_isect >= 0 && n_isect < ((int64_t)1 << 31), "bin_sort: n_isect must fit int32 (got %lld)", (long long)n_isect);
-  BDS_REQUIRE(radii && tiles_touched && slot_of && isect_offsets && splats && tile_offsets && workspace, "bin_sort: null pointer");
+  BDS_REQUIRE(tile_offsets, "bin_sort: null tile_offsets");
+  if (n_isect > 0)
+    BDS_REQUIRE(radii && tiles_touched && slot_of && isect_offsets && splats && workspace, "bin_sort: null pointer");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const int tile_w = (d->width + kTile - 1) / kTile, tile_h = (d->height + kTile - 1) / kTile;
   const int n_tiles = (d->row_end - d->row_begin) * tile_w;

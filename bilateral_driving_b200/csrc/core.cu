@@ -5,6 +5,7 @@
 
 namespace bds {
 static thread_local char g_err[1024] = "";
+unsigned long long g_launches = 0;
 void set_error(const char* fmt, ...) {
   va_list ap;
   va_start(ap, fmt);
@@ -22,3 +23,4 @@ extern "C" int bds_device_arch(void) {
   BDS_CHECK_CUDA(cudaGetDeviceProperties(&prop, dev));
   return prop.major * 10 + prop.minor;
 }
+extern "C" unsigned long long bds_launch_count(void) { return bds::g_launches; }

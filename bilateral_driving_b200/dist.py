@@ -1,0 +1,53 @@
+"""Multi-GPU sharding of the render path (new: the reference is single-GPU).
+
+The unit of work is a tile row of one camera.  All C*tile_rows rows of the rig are laid end to end
+and rank r of G renders the contiguous band ``[R*r/G, R*(r+1)/G)`` - camera sharding when G divides
+the number of cameras, tile sharding otherwise (8 GPUs, 6 cameras).  Full-resolution guidance needs
+no halo.  Every rank holds a full parameter replica; after the local backward ONE all-reduce (sum)
+over a flat fp32 buffer [Gaussian grads | grid grads] gives every rank the single-GPU gradient.
+"""
+from typing import Iterable, List, Sequence, Tuple
+
+import torch
+
+from ._lib import TILE
+
+
+def band_for_rank(rank: int, world: int, n_cams: int, height: int) -> Tuple[int, int]:
+    tile_h = (height + TILE - 1) // TILE
+    total = n_cams * tile_h
+    return (total * rank) // world, (total * (rank + 1)) // world
+
+
+def band_pixel_rows(rb: int, re: int, n_cams: int, height: int) -> Tuple[int, int]:
+    tile_h = (height + TILE - 1) // TILE
+
+    def row_of(gr):
+        c, ty = divmod(gr, tile_h)
+        return c * height + min(ty * TILE, height)
+
+    return row_of(rb), (row_of(re) if re < n_cams * tile_h else n_cams * height)
+
+
+def cameras_in_band(rb: int, re: int, height: int) -> List[int]:
+    tile_h = (height + TILE - 1) // TILE
+    if re <= rb:
+        return []
+    return list(range(rb // tile_h, (re - 1) // tile_h + 1))
+
+
+def allreduce_grads(tensors: Sequence[torch.Tensor], group=None) -> None:
+    """One all-reduce (SUM) over a single flat buffer holding every gradient; results are copied
+    back in place.  No-op for a single process."""
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return
+    grads = [t for t in tensors if t is not None]
+    flat = torch.cat([g.reshape(-1) for g in grads])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    off = 0
+    for g in grads:
+        n = g.numel()
+        g.copy_(flat[off:off + n].view_as(g))
+        off += n

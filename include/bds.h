@@ -34,6 +34,8 @@ const char* bds_last_error(void);
 int bds_abi_version(void);
 /* returns the compute capability major*10+minor of the current device, or <0 */
 int bds_device_arch(void);
+/* number of kernels this library has launched so far in this process (statistics for bench.py) */
+unsigned long long bds_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------
  * Bilateral grids.  Replaces bilateral/lib_bilagrid.py:171-230 (slice), :317-368

@@ -163,3 +163,32 @@ def identity_grid(L, GY, GX, dtype=torch.float32):
     g[5] = 1
     g[10] = 1
     return g
+
+
+def guidance_ambiguous(rgb, grids, guidance_factor=(4, 4, 2), margin=1e-4):
+    """Pixels whose guidance gradient may legitimately differ between two fp32 implementations:
+    the guidance coordinate fz = luma*(L-1) of some level sits within ``margin`` of a lattice plane
+    (the slab difference dA/dz jumps there) or of the clamp bounds 0 / L-1 (the gradient switches
+    off there).  For low-resolution guidance the full-res taps feeding such a low-res pixel are
+    flagged.  Outputs and grid gradients are continuous across these planes; only d/d(rgb) is not."""
+    H, W, _ = rgb.shape
+    amb = torch.zeros(H, W, dtype=torch.bool)
+    with torch.no_grad():
+        for lvl, g in enumerate(grids):
+            L = g.shape[1]
+            if L <= 1:
+                continue
+            f = 1 if guidance_factor is None else guidance_factor[lvl]
+            low = rgb if f == 1 else resize_bilinear(rgb, H // f, W // f)
+            fz = luma_of(low) * (L - 1)
+            near = ((fz - fz.round()).abs() < margin) & (fz > -margin) & (fz < L - 1 + margin)
+            if f == 1:
+                amb |= near
+            else:
+                y0, y1, _ = lin_src(H // f, H, rgb.dtype)
+                x0, x1, _ = lin_src(W // f, W, rgb.dtype)
+                ys, xs = torch.nonzero(near, as_tuple=True)
+                for yy in (y0, y1):
+                    for xx in (x0, x1):
+                        amb[yy[ys], xx[xs]] = True
+    return amb

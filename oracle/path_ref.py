@@ -42,5 +42,9 @@ def render_path(params, viewmats, Ks, width, height, sky=None, grid_slots=None, 
     else:
         rgb = torch.stack([B.multiscale_forward(grid_slots[c], rgb_in[c], guidance_factor)
                            for c in range(viewmats.shape[0])])
+    amb = info["ambiguous"]
+    if grid_slots is not None:
+        amb = amb | torch.stack([B.guidance_ambiguous(rgb_in[c].detach(), grid_slots[c], guidance_factor)
+                                 for c in range(viewmats.shape[0])])
     return dict(rgb=rgb, rgb_gaussians=rgb_g, depth=depth, opacity=alphas, original_rgb=rgb_in,
-                ambiguous=info["ambiguous"], info=info)
+                ambiguous=amb, info=info)

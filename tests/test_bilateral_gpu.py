@@ -87,8 +87,16 @@ def test_against_oracle(H, W, gf):
     c_grids = [g.detach().clone().cuda().requires_grad_(True) for g in grids]
     c_y = multiscale_bilateral(c_rgb, c_grids, sizes, gf)
     (c_y * G.cuda()).sum().backward()
-    assert (c_y.detach().cpu() - o_y.detach().float()).abs().max() < 1e-5
-    assert _rel(c_rgb.grad.cpu(), o_rgb.grad.float()) < 1e-3
+    # 1e-5 abs where the guidance resampling ratio is an integer (1080p: 270x480 / 540x960, the
+    # reference's case); at non-integer ratios the fp32 tap weights of ANY implementation (torch's
+    # included) carry ~1e-5 rounding, which this per-pixel-random guidance image amplifies
+    exact_ratio = gf is None or all(H % f == 0 and W % f == 0 for f in gf)
+    assert (c_y.detach().cpu() - o_y.detach().float()).abs().max() < (1e-5 if exact_ratio else 1e-4)
+    # d/d(rgb) jumps where the guidance coordinate crosses a lattice plane: exclude those pixels
+    amb = B.guidance_ambiguous(rgb, grids, gf)
+    assert float(amb.float().mean()) < 0.02
+    keep = (~amb)[..., None]
+    assert _rel(c_rgb.grad.cpu() * keep, o_rgb.grad.float() * keep) < 1e-3
     for a, b in zip(c_grids, o_grids):
         assert _rel(a.grad.cpu(), b.grad.float()) < 1e-3
 
