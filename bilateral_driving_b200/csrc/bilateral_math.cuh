@@ -70,6 +70,7 @@ BDS_HD float luma_coord(float luma, int L) {
 struct Tri {
   int n00, n01, n10, n11;  // (y0,x0) (y0,x1) (y1,x0) (y1,x1) node offsets inside slab z0
   int dz;                  // node offset from slab z0 to slab z1 (0 when clamped)
+  int x0, y0, z0;          // lower lattice node of the cell
   float wx1, wy1, wz1;     // upper weights; lower = 1 - upper
   bool z_inside;           // 0 < fz < L-1 (strict): guidance gradient flows
 };
@@ -86,6 +87,7 @@ BDS_HD Tri tri_setup(float fx, float fy, float fz, int L, int GY, int GX) {
   int x1 = x0 + 1 < GX ? x0 + 1 : x0;  // weight of the clamped corner is exactly 0
   int y1 = y0 + 1 < GY ? y0 + 1 : y0;
   int z1 = z0 + 1 < L ? z0 + 1 : z0;
+  t.x0 = x0; t.y0 = y0; t.z0 = z0;
   int base = (z0 * GY) * GX;
   t.n00 = base + y0 * GX + x0;
   t.n01 = base + y0 * GX + x1;

@@ -265,9 +265,101 @@ BDS_D float warp_transpose_reduce16(float v[16]) {
   return v[0] + __shfl_xor_sync(kFull, v[0], 1);
 }
 
+// ---- block-cooperative bilateral backward (MODE 2) ---------------------------------------------
+// Grid-node gradients of one tile land in a handful of lattice nodes (a 16x16 tile spans a fraction
+// of a grid cell at 1080p): they are accumulated in shared memory - per pixel the 4 xy-corner x 12
+// channel products are spread over 48 "component" threads, 5 groups of 48 threads take disjoint pixel
+// subsets into private windows (no shared-memory atomics) - and leave as one global reduction per
+// touched (node, channel) per tile instead of 96 per pixel per level.
+constexpr int kWinGroups = 5;
+constexpr int kWinNodes = 3;                   // window is kWinNodes x kWinNodes lattice nodes in xy
+constexpr int kWinMaxL = 16;
+constexpr int kStageFloats = 16;               // per pixel: vA[12], wx1, wy1, wz1, packed
+constexpr int kWinFloats = kWinNodes * kWinNodes * kWinMaxL * 12;
+constexpr size_t kBwdSmemBil = (size_t)(256 * kStageFloats + kWinGroups * kWinFloats) * sizeof(float);
+constexpr size_t kBwdSmemRec = (size_t)kStages * kChunk * kRecBytes;
+constexpr size_t kBwdSmem = kBwdSmemBil > kBwdSmemRec ? kBwdSmemBil : kBwdSmemRec;
+
+// One level: every thread brings its pixel's vAff / Tri (valid = pixel inside the image); the block
+// accumulates into v_grid (global, [L][GY][GX][12]) through the shared windows.
+BDS_D void level_grad_accumulate(float* smem, const Tri& t, const float vAff[12], bool valid, int tile_x0,
+                                 int tile_y0, int W, int H, int L, int GY, int GX, float* __restrict__ v_grid) {
+  float* stage = smem;
+  float* win = smem + 256 * kStageFloats;
+  // window origin = cell of the tile's first pixel (uniform over the block)
+  const float fx0 = fminf(fmaxf(lattice_coord(tile_x0, W, GX), 0.f), (float)(GX - 1));
+  const float fy0 = fminf(fmaxf(lattice_coord(tile_y0, H, GY), 0.f), (float)(GY - 1));
+  const int nx0 = (int)floorf(fx0), ny0 = (int)floorf(fy0);
+  const bool use_win = L <= kWinMaxL;
+  if (use_win) {
+    const int nwin = kWinGroups * kWinNodes * kWinNodes * L * 12;
+    for (int i = threadIdx.x; i < nwin; i += 256) win[i] = 0.f;
+  }
+  // stage this pixel's contribution
+  {
+    float4* sp = reinterpret_cast<float4*>(stage + threadIdx.x * kStageFloats);
+    int ox = t.x0 - nx0, oy = t.y0 - ny0;
+    int z1 = t.dz != 0 ? 1 : 0;
+    int packed = valid ? (1 << 24) | (z1 << 20) | (t.z0 << 12) | ((oy & 63) << 6) | (ox & 63) : 0;
+    sp[0] = make_float4(vAff[0], vAff[1], vAff[2], vAff[3]);
+    sp[1] = make_float4(vAff[4], vAff[5], vAff[6], vAff[7]);
+    sp[2] = make_float4(vAff[8], vAff[9], vAff[10], vAff[11]);
+    sp[3] = make_float4(t.wx1, t.wy1, t.wz1, __int_as_float(packed));
+  }
+  __syncthreads();
+  if (threadIdx.x < kWinGroups * 48) {
+    const int grp = threadIdx.x / 48, comp = threadIdx.x - grp * 48;
+    const int corner = comp / 12, ch = comp - corner * 12;
+    const int dx = corner & 1, dy = corner >> 1;
+    float* mywin = win + grp * (kWinNodes * kWinNodes * L * 12);
+    const int per = (256 + kWinGroups - 1) / kWinGroups;
+    const int p0 = grp * per, p1 = min(256, p0 + per);
+    for (int px = p0; px < p1; ++px) {
+      const float* sp = stage + px * kStageFloats;
+      int packed = __float_as_int(sp[15]);
+      if (!(packed >> 24)) continue;
+      int ox = packed & 63, oy = (packed >> 6) & 63, z0 = (packed >> 12) & 255, z1 = (packed >> 20) & 1;
+      if (ox & 32) ox -= 64;   // sign-extend the 6-bit offsets
+      if (oy & 32) oy -= 64;
+      float wx1 = sp[12], wy1 = sp[13], wz1 = sp[14];
+      float w = (dx ? wx1 : 1.f - wx1) * (dy ? wy1 : 1.f - wy1) * sp[ch];
+      if (w == 0.f) continue;
+      int nx = ox + dx, ny = oy + dy;
+      float w0 = w * (1.f - wz1), w1 = w * wz1;
+      if (use_win && nx >= 0 && nx < kWinNodes && ny >= 0 && ny < kWinNodes) {
+        float* c0 = mywin + ((z0 * kWinNodes + ny) * kWinNodes + nx) * 12 + ch;
+        *c0 += w0;
+        if (z1) c0[kWinNodes * kWinNodes * 12] += w1;
+      } else {  // tile spans more than the window (tiny images / huge grids): global reductions
+        int gx = min(nx0 + nx, GX - 1), gy = min(ny0 + ny, GY - 1);
+        float* g0 = v_grid + ((size_t)(z0 * GY + gy) * GX + gx) * 12 + ch;
+        if (w0 != 0.f) red_add(g0, w0);
+        if (z1 && w1 != 0.f) red_add(g0 + (size_t)GY * GX * 12, w1);
+      }
+    }
+  }
+  __syncthreads();
+  if (use_win) {
+    const int per_win = kWinNodes * kWinNodes * L * 12;
+    for (int e = threadIdx.x; e < per_win; e += 256) {
+      float v = 0.f;
+#pragma unroll
+      for (int gq = 0; gq < kWinGroups; ++gq) v += win[gq * per_win + e];
+      if (v != 0.f) {
+        int ch = e % 12, node = e / 12;
+        int nx = node % kWinNodes, ny = (node / kWinNodes) % kWinNodes, z = node / (kWinNodes * kWinNodes);
+        int gx = nx0 + nx, gy = ny0 + ny;
+        if (gx < GX && gy < GY) red_add(v_grid + ((size_t)(z * GY + gy) * GX + gx) * 12 + ch, v);
+      }
+    }
+  }
+  __syncthreads();
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(256) composite_bwd_kernel(CompParams p) {
-  __shared__ __align__(128) float4 srec[kStages][kChunk * 3];
+  extern __shared__ __align__(128) unsigned char dyn_smem[];
+  float4 (*srec)[kChunk * 3] = reinterpret_cast<float4 (*)[kChunk * 3]>(dyn_smem);
   __shared__ __align__(8) uint64_t bars[kStages];
   __shared__ int s_last[8];
 
@@ -279,9 +371,12 @@ __global__ void __launch_bounds__(256) composite_bwd_kernel(CompParams p) {
   float vA = 0.f, Tfin = 1.f;
   int last = -1;
   float bgv[4] = {0.f, 0.f, 0.f, 0.f};
+  float A = 0.f;
+  float gr = 0.f, gg2 = 0.f, gb = 0.f;           // cotangent of rgb_in (modes 1/2)
+  float rg = 0.f, gg = 0.f, bg = 0.f, sk[3] = {0.f, 0.f, 0.f};
   if (g.inside) {
     last = p.last_ids[g.pix];
-    const float A = p.out_alpha[g.pix];
+    A = p.out_alpha[g.pix];
     Tfin = 1.f - A;
     if (p.v_alpha) vA = p.v_alpha[g.pix];
     if (MODE == 0) {
@@ -300,66 +395,78 @@ __global__ void __launch_bounds__(256) composite_bwd_kernel(CompParams p) {
         }
       }
     } else {
-      float rg = p.out_rgbg[g.pix * 3], gg = p.out_rgbg[g.pix * 3 + 1], bg = p.out_rgbg[g.pix * 3 + 2];
-      float sk[3] = {0.f, 0.f, 0.f};
+      rg = p.out_rgbg[g.pix * 3]; gg = p.out_rgbg[g.pix * 3 + 1]; bg = p.out_rgbg[g.pix * 3 + 2];
       if (p.sky) { sk[0] = p.sky[g.pix * 3]; sk[1] = p.sky[g.pix * 3 + 1]; sk[2] = p.sky[g.pix * 3 + 2]; }
-      float gr = p.v_rgb[g.pix * 3], gg2 = p.v_rgb[g.pix * 3 + 1], gb = p.v_rgb[g.pix * 3 + 2];
-      if (MODE == 2) {
-        // recompute the chain, then walk it backwards (appendix A.3 of SURVEY.md)
-        float x0r = fmaf(sk[0], Tfin, rg), x0g = fmaf(sk[1], Tfin, gg), x0b = fmaf(sk[2], Tfin, bg);
-        float lum = luma_of(x0r, x0g, x0b);
-        float Aall[BDS_MAX_LEVELS][12], xs[BDS_MAX_LEVELS][3];
-        Tri tri[BDS_MAX_LEVELS];
-        float r = x0r, gq = x0g, b = x0b;
+      gr = p.v_rgb[g.pix * 3]; gg2 = p.v_rgb[g.pix * 3 + 1]; gb = p.v_rgb[g.pix * 3 + 2];
+    }
+  }
+  if (MODE == 2) {
+    // chain backward (appendix A.3 of SURVEY.md); every thread takes part in the cooperative
+    // grid-gradient accumulation, pixels outside the image contribute nothing
+    const float x0r = fmaf(sk[0], Tfin, rg), x0g = fmaf(sk[1], Tfin, gg), x0b = fmaf(sk[2], Tfin, bg);
+    const float lum = luma_of(x0r, x0g, x0b);
+    const int pxc = min(g.px, p.W - 1), pyc = min(g.py, p.H - 1);
+    float xs[BDS_MAX_LEVELS][3];
+    {
+      float r = x0r, gq = x0g, b = x0b;
 #pragma unroll
-        for (int l = 0; l < BDS_MAX_LEVELS; ++l) {
-          if (l < p.bil.n_levels) {
-            const float* grid = p.bil.grid_cl[l] + (size_t)g.cam * p.bil.L[l] * p.bil.GY[l] * p.bil.GX[l] * 12;
-            tri[l] = tri_setup(lattice_coord(g.px, p.W, p.bil.GX[l]), lattice_coord(g.py, p.H, p.bil.GY[l]),
-                               luma_coord(lum, p.bil.L[l]), p.bil.L[l], p.bil.GY[l], p.bil.GX[l]);
-            xs[l][0] = r; xs[l][1] = gq; xs[l][2] = b;
-            tri_fetch<false>(grid, tri[l], Aall[l], nullptr);
-            affine_apply(Aall[l], r, gq, b);
-          }
+      for (int l = 0; l < BDS_MAX_LEVELS; ++l) {
+        if (l < p.bil.n_levels) {
+          const float* grid = p.bil.grid_cl[l] + (size_t)g.cam * p.bil.L[l] * p.bil.GY[l] * p.bil.GX[l] * 12;
+          Tri t = tri_setup(lattice_coord(pxc, p.W, p.bil.GX[l]), lattice_coord(pyc, p.H, p.bil.GY[l]),
+                            luma_coord(lum, p.bil.L[l]), p.bil.L[l], p.bil.GY[l], p.bil.GX[l]);
+          xs[l][0] = r; xs[l][1] = gq; xs[l][2] = b;
+          float Al[12];
+          tri_fetch<false>(grid, t, Al, nullptr);
+          affine_apply(Al, r, gq, b);
         }
-        float v_lum = 0.f;
+      }
+    }
+    float v_lum = 0.f;
+    const int tile_x0 = (blockIdx.x % p.tile_w) * kTile;
+    const int tile_y0 = ((p.row_begin + blockIdx.x / p.tile_w) % p.tile_h) * kTile;
 #pragma unroll
-        for (int l = BDS_MAX_LEVELS - 1; l >= 0; --l) {
-          if (l < p.bil.n_levels) {
-            size_t goff = (size_t)g.cam * p.bil.L[l] * p.bil.GY[l] * p.bil.GX[l] * 12;
-            float vAff[12];
+    for (int l = BDS_MAX_LEVELS - 1; l >= 0; --l) {
+      if (l < p.bil.n_levels) {
+        const size_t goff = (size_t)g.cam * p.bil.L[l] * p.bil.GY[l] * p.bil.GX[l] * 12;
+        Tri t = tri_setup(lattice_coord(pxc, p.W, p.bil.GX[l]), lattice_coord(pyc, p.H, p.bil.GY[l]),
+                          luma_coord(lum, p.bil.L[l]), p.bil.L[l], p.bil.GY[l], p.bil.GX[l]);
+        float Al[12], dAdz[12], vAff[12];
+        tri_fetch<true>(p.bil.grid_cl[l] + goff, t, Al, dAdz);
 #pragma unroll
-            for (int k = 0; k < 12; ++k) vAff[k] = 0.f;
-            float nr, ng, nb;
-            affine_apply_bwd(Aall[l], xs[l][0], xs[l][1], xs[l][2], gr, gg2, gb, vAff, nr, ng, nb);
-            gr = nr; gg2 = ng; gb = nb;
-            tri_scatter(p.bil.v_grid_cl[l] + goff, tri[l], vAff);
-            if (tri[l].z_inside) {
-              float Ad[12], dAdz[12];
-              tri_fetch<true>(p.bil.grid_cl[l] + goff, tri[l], Ad, dAdz);
-              float s = 0.f;
+        for (int k = 0; k < 12; ++k) vAff[k] = 0.f;
+        float nr, ng, nb;
+        affine_apply_bwd(Al, xs[l][0], xs[l][1], xs[l][2], gr, gg2, gb, vAff, nr, ng, nb);
+        gr = nr; gg2 = ng; gb = nb;
+        if (t.z_inside) {
+          float sdot = 0.f;
 #pragma unroll
-              for (int k = 0; k < 12; ++k) s = fmaf(vAff[k], dAdz[k], s);
-              v_lum += s * (float)(p.bil.L[l] - 1);
-            }
-          }
+          for (int k = 0; k < 12; ++k) sdot = fmaf(vAff[k], dAdz[k], sdot);
+          v_lum += sdot * (float)(p.bil.L[l] - 1);
         }
-        gr += v_lum * kLumaR; gg2 += v_lum * kLumaG; gb += v_lum * kLumaB;
+        level_grad_accumulate(reinterpret_cast<float*>(dyn_smem), t, vAff, g.inside, tile_x0, tile_y0, p.W, p.H,
+                              p.bil.L[l], p.bil.GY[l], p.bil.GX[l], p.bil.v_grid_cl[l] + goff);
       }
-      // (gr, gg2, gb) = cotangent of rgb_in = rgb_gauss + sky * (1 - A)
-      if (p.v_sky) { p.v_sky[g.pix * 3] = gr * Tfin; p.v_sky[g.pix * 3 + 1] = gg2 * Tfin; p.v_sky[g.pix * 3 + 2] = gb * Tfin; }
-      vA -= sk[0] * gr + sk[1] * gg2 + sk[2] * gb;
-      float vr = gr, vg = gg2, vb = gb;
-      if (p.v_rgbg) { vr += p.v_rgbg[g.pix * 3]; vg += p.v_rgbg[g.pix * 3 + 1]; vb += p.v_rgbg[g.pix * 3 + 2]; }
-      vC[0] = rg < 1.f ? vr : 0.f;   // clamp(max=1) passes gradient below the bound
-      vC[1] = gg < 1.f ? vg : 0.f;
-      vC[2] = bg < 1.f ? vb : 0.f;
-      if (p.v_depth) {
-        float Ac = fmaxf(A, 1e-10f);
-        float vd = p.v_depth[g.pix];
-        vC[3] = vd / Ac;
-        if (A >= 1e-10f) vA -= vd * p.out_depth[g.pix] / Ac;
-      }
+    }
+    gr += v_lum * kLumaR; gg2 += v_lum * kLumaG; gb += v_lum * kLumaB;
+    // the staging / window bytes are about to be overwritten by TMA (async proxy): order the
+    // generic-proxy accesses above before it (the __syncthreads below publishes it block-wide)
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (MODE != 0 && g.inside) {
+    // (gr, gg2, gb) = cotangent of rgb_in = rgb_gauss + sky * (1 - A)
+    if (p.v_sky) { p.v_sky[g.pix * 3] = gr * Tfin; p.v_sky[g.pix * 3 + 1] = gg2 * Tfin; p.v_sky[g.pix * 3 + 2] = gb * Tfin; }
+    vA -= sk[0] * gr + sk[1] * gg2 + sk[2] * gb;
+    float vr = gr, vg = gg2, vb = gb;
+    if (p.v_rgbg) { vr += p.v_rgbg[g.pix * 3]; vg += p.v_rgbg[g.pix * 3 + 1]; vb += p.v_rgbg[g.pix * 3 + 2]; }
+    vC[0] = rg < 1.f ? vr : 0.f;   // clamp(max=1) passes gradient below the bound
+    vC[1] = gg < 1.f ? vg : 0.f;
+    vC[2] = bg < 1.f ? vb : 0.f;
+    if (p.v_depth) {
+      float Ac = fmaxf(A, 1e-10f);
+      float vd = p.v_depth[g.pix];
+      vC[3] = vd / Ac;
+      if (A >= 1e-10f) vA -= vd * p.out_depth[g.pix] / Ac;
     }
   }
 
@@ -642,9 +749,13 @@ extern "C" int bds_composite_bwd(const bds_render_desc* d, const bds_epilogue_de
     }
   }
   switch (e->mode) {
-    case 0: composite_bwd_kernel<0><<<n_tiles, 256, 0, stream>>>(p); break;
-    case 1: composite_bwd_kernel<1><<<n_tiles, 256, 0, stream>>>(p); break;
-    default: composite_bwd_kernel<2><<<n_tiles, 256, 0, stream>>>(p); break;
+    case 0: composite_bwd_kernel<0><<<n_tiles, 256, kBwdSmemRec, stream>>>(p); break;
+    case 1: composite_bwd_kernel<1><<<n_tiles, 256, kBwdSmemRec, stream>>>(p); break;
+    default:
+      BDS_CHECK_CUDA(cudaFuncSetAttribute(composite_bwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)kBwdSmem));
+      composite_bwd_kernel<2><<<n_tiles, 256, kBwdSmem, stream>>>(p);
+      break;
   }
   BDS_CHECK_LAUNCH();
   if (e->mode == 2) {
