@@ -151,41 +151,78 @@ struct EmitParams {
   uint32_t* vals;
 };
 
+constexpr int kCoopTiles = 32;  // work-split threshold only (same value as projection.cu); not a result
+
 __global__ void __launch_bounds__(256) emit_keys_kernel(EmitParams p) {
   const int N = p.d.n_gauss;
+  const int lane = threadIdx.x & 31;
   int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (int64_t)N * p.d.n_cams) return;
-  int slot = p.slot_of[idx];
-  if (slot < 0) return;
-  int c = (int)(idx / N);
-  int ty0, ty1;
-  band_rows2(p.d, p.tile_h, c, ty0, ty1);
-  const float4* rp = reinterpret_cast<const float4*>(p.splats + (size_t)slot * 12);
-  float4 r0 = __ldg(rp), r1 = __ldg(rp + 1), r2 = __ldg(rp + 2);
-  float radius = (float)p.radii[idx];
-  // same rectangle + same hit test as the counting pass in project_fwd_kernel
-  float tr = radius / (float)kTile, txf = r0.x / (float)kTile, tyf = r0.y / (float)kTile;
-  int x0 = (int)fminf(fmaxf(floorf(txf - tr), 0.f), (float)p.tile_w);
-  int x1 = (int)fminf(fmaxf(ceilf(txf + tr), 0.f), (float)p.tile_w);
-  int y0 = (int)fminf(fmaxf(floorf(tyf - tr), 0.f), (float)p.tile_h);
-  int y1 = (int)fminf(fmaxf(ceilf(tyf + tr), 0.f), (float)p.tile_h);
-  if (y0 < ty0) y0 = ty0;
-  if (y1 > ty1) y1 = ty1;
-  uint64_t depth_bits = (uint64_t)(uint32_t)__float_as_int(r2.y);
-  int64_t o = p.offsets[idx];
-  const int64_t o_end = o + p.tiles_touched[idx];
-  // tile_hit is the same non-inlined body the counting pass ran, so the counts agree; the o_end
-  // guard and the sentinel padding (a key that sorts behind every real tile) only make a
-  // disagreement memory-safe should a toolchain ever break that.
-  for (int ty = y0; ty < y1; ++ty) {
-    for (int tx = x0; tx < x1; ++tx) {
-      if (tile_hit(r0.x, r0.y, r0.z, r0.w, r1.x, r2.w, tx, ty, p.d.width, p.d.height) && o < o_end) {
-        uint64_t band_tile = (uint64_t)((c * p.tile_h + ty - p.d.row_begin) * p.tile_w + tx);
-        p.keys[o] = (band_tile << 32) | depth_bits;
-        p.vals[o] = (uint32_t)slot;
-        ++o;
+  const bool in_range = idx < (int64_t)N * p.d.n_cams;
+  const int slot = in_range ? p.slot_of[idx] : -1;
+  const bool active = slot >= 0;
+  const int c = in_range ? (int)(idx / N) : 0;
+  float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0, r2 = r0;
+  TileRect tr = {0, 0, 0, 0};
+  long long o = 0, o_end = 0;
+  if (active) {
+    int ty0, ty1;
+    band_rows2(p.d, p.tile_h, c, ty0, ty1);
+    const float4* rp = reinterpret_cast<const float4*>(p.splats + (size_t)slot * 12);
+    r0 = __ldg(rp); r1 = __ldg(rp + 1); r2 = __ldg(rp + 2);
+    // same candidate rectangle + same hit test (both non-inlined bodies) as the counting pass
+    tr = candidate_rect(r0.x, r0.y, (float)p.radii[idx], r0.z, r0.w, r1.x, r2.w, p.tile_w, p.tile_h, ty0, ty1);
+    o = p.offsets[idx];
+    o_end = o + p.tiles_touched[idx];
+  }
+  const uint64_t depth_bits = (uint64_t)(uint32_t)__float_as_int(r2.y);
+  const int ncand = active ? (tr.x1 - tr.x0) * (tr.y1 - tr.y0) : 0;
+  // The o_end guard and the sentinel padding (a key that sorts behind every real tile) only make a
+  // count / emission disagreement memory-safe should a toolchain ever break the shared-body contract.
+  if (active && ncand <= kCoopTiles) {
+    for (int ty = tr.y0; ty < tr.y1; ++ty) {
+      for (int tx = tr.x0; tx < tr.x1; ++tx) {
+        if (tile_hit(r0.x, r0.y, r0.z, r0.w, r1.x, r2.w, tx, ty, p.d.width, p.d.height) && o < o_end) {
+          uint64_t band_tile = (uint64_t)((c * p.tile_h + ty - p.d.row_begin) * p.tile_w + tx);
+          p.keys[o] = (band_tile << 32) | depth_bits;
+          p.vals[o] = (uint32_t)slot;
+          ++o;
+        }
       }
     }
+  }
+  unsigned big = __ballot_sync(0xffffffffu, ncand > kCoopTiles);
+  while (big) {
+    const int src = __ffs(big) - 1;
+    big &= big - 1;
+    const int bx0 = __shfl_sync(0xffffffffu, tr.x0, src), bx1 = __shfl_sync(0xffffffffu, tr.x1, src);
+    const int by0 = __shfl_sync(0xffffffffu, tr.y0, src), by1 = __shfl_sync(0xffffffffu, tr.y1, src);
+    const float gx = __shfl_sync(0xffffffffu, r0.x, src), gy = __shfl_sync(0xffffffffu, r0.y, src);
+    const float ga = __shfl_sync(0xffffffffu, r0.z, src), gb = __shfl_sync(0xffffffffu, r0.w, src);
+    const float gc = __shfl_sync(0xffffffffu, r1.x, src), gcut = __shfl_sync(0xffffffffu, r2.w, src);
+    const int gcam = __shfl_sync(0xffffffffu, c, src), gslot = __shfl_sync(0xffffffffu, slot, src);
+    const unsigned dlo = __shfl_sync(0xffffffffu, (unsigned)depth_bits, src);
+    long long go = __shfl_sync(0xffffffffu, o, src);
+    const long long gend = __shfl_sync(0xffffffffu, o_end, src);
+    const int w = bx1 - bx0, total = w * (by1 - by0);
+    for (int base = 0; base < total; base += 32) {
+      int i = base + lane;
+      bool hit = false;
+      int tx = 0, ty = 0;
+      if (i < total) {
+        ty = by0 + i / w;
+        tx = bx0 + i - (i / w) * w;
+        hit = tile_hit(gx, gy, ga, gb, gc, gcut, tx, ty, p.d.width, p.d.height);
+      }
+      unsigned hm = __ballot_sync(0xffffffffu, hit);
+      long long pos = go + __popc(hm & ((1u << lane) - 1u));
+      if (hit && pos < gend) {
+        uint64_t band_tile = (uint64_t)((gcam * p.tile_h + ty - p.d.row_begin) * p.tile_w + tx);
+        p.keys[pos] = (band_tile << 32) | (uint64_t)dlo;
+        p.vals[pos] = (uint32_t)gslot;
+      }
+      go += __popc(hm);
+    }
+    if (lane == src) o = go < o_end ? go : o_end;
   }
   for (; o < o_end; ++o) {
     p.keys[o] = ((uint64_t)p.n_tiles << 32) | depth_bits;

@@ -268,10 +268,10 @@ BDS_D float warp_transpose_reduce16(float v[16]) {
 // ---- block-cooperative bilateral backward (MODE 2) ---------------------------------------------
 // Grid-node gradients of one tile land in a handful of lattice nodes (a 16x16 tile spans a fraction
 // of a grid cell at 1080p): they are accumulated in shared memory - per pixel the 4 xy-corner x 12
-// channel products are spread over 48 "component" threads, 5 groups of 48 threads take disjoint pixel
-// subsets into private windows (no shared-memory atomics) - and leave as one global reduction per
+// channel products are spread over the lanes of a warp pair, 4 warp pairs take disjoint pixel
+// quarters into private windows (no shared-memory atomics) - and leave as one global reduction per
 // touched (node, channel) per tile instead of 96 per pixel per level.
-constexpr int kWinGroups = 5;
+constexpr int kWinGroups = 4;                  // one per warp pair
 constexpr int kWinNodes = 3;                   // window is kWinNodes x kWinNodes lattice nodes in xy
 constexpr int kWinMaxL = 16;
 constexpr int kStageFloats = 16;               // per pixel: vA[12], wx1, wy1, wz1, packed
@@ -307,35 +307,46 @@ BDS_D void level_grad_accumulate(float* smem, const Tri& t, const float vAff[12]
     sp[3] = make_float4(t.wx1, t.wy1, t.wz1, __int_as_float(packed));
   }
   __syncthreads();
-  if (threadIdx.x < kWinGroups * 48) {
-    const int grp = threadIdx.x / 48, comp = threadIdx.x - grp * 48;
-    const int corner = comp / 12, ch = comp - corner * 12;
+  {
+    // Two warps form a group with a private window and a quarter of the tile's pixels.  All four
+    // xy-corners of a channel live in ONE warp (warp role 0: channels 0-7, role 1: channels 8-11), and
+    // the warp walks the pixels in lock step, so two lanes never update the same window word at the
+    // same time: within a pixel the four corners are four different nodes, and different pixels are
+    // separated by the __syncwarp below.  No shared-memory atomics needed.
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int grp = warp >> 1, role = warp & 1;
+    const int ch = role * 8 + (lane >> 2), corner = lane & 3;
+    const bool worker = ch < 12;
     const int dx = corner & 1, dy = corner >> 1;
     float* mywin = win + grp * (kWinNodes * kWinNodes * L * 12);
-    const int per = (256 + kWinGroups - 1) / kWinGroups;
-    const int p0 = grp * per, p1 = min(256, p0 + per);
+    const int per = 256 / kWinGroups;
+    const int p0 = grp * per, p1 = p0 + per;
     for (int px = p0; px < p1; ++px) {
       const float* sp = stage + px * kStageFloats;
-      int packed = __float_as_int(sp[15]);
-      if (!(packed >> 24)) continue;
-      int ox = packed & 63, oy = (packed >> 6) & 63, z0 = (packed >> 12) & 255, z1 = (packed >> 20) & 1;
-      if (ox & 32) ox -= 64;   // sign-extend the 6-bit offsets
-      if (oy & 32) oy -= 64;
-      float wx1 = sp[12], wy1 = sp[13], wz1 = sp[14];
-      float w = (dx ? wx1 : 1.f - wx1) * (dy ? wy1 : 1.f - wy1) * sp[ch];
-      if (w == 0.f) continue;
-      int nx = ox + dx, ny = oy + dy;
-      float w0 = w * (1.f - wz1), w1 = w * wz1;
-      if (use_win && nx >= 0 && nx < kWinNodes && ny >= 0 && ny < kWinNodes) {
-        float* c0 = mywin + ((z0 * kWinNodes + ny) * kWinNodes + nx) * 12 + ch;
-        *c0 += w0;
-        if (z1) c0[kWinNodes * kWinNodes * 12] += w1;
-      } else {  // tile spans more than the window (tiny images / huge grids): global reductions
-        int gx = min(nx0 + nx, GX - 1), gy = min(ny0 + ny, GY - 1);
-        float* g0 = v_grid + ((size_t)(z0 * GY + gy) * GX + gx) * 12 + ch;
-        if (w0 != 0.f) red_add(g0, w0);
-        if (z1 && w1 != 0.f) red_add(g0 + (size_t)GY * GX * 12, w1);
+      const int packed = __float_as_int(sp[15]);
+      if (worker && (packed >> 24)) {
+        int ox = packed & 63, oy = (packed >> 6) & 63;
+        const int z0 = (packed >> 12) & 255, z1 = (packed >> 20) & 1;
+        if (ox & 32) ox -= 64;   // sign-extend the 6-bit offsets
+        if (oy & 32) oy -= 64;
+        const float wx1 = sp[12], wy1 = sp[13], wz1 = sp[14];
+        const float w = (dx ? wx1 : 1.f - wx1) * (dy ? wy1 : 1.f - wy1) * sp[ch];
+        if (w != 0.f) {
+          const int nx = ox + dx, ny = oy + dy;
+          const float w0 = w * (1.f - wz1), w1 = w * wz1;
+          if (use_win && nx >= 0 && nx < kWinNodes && ny >= 0 && ny < kWinNodes) {
+            float* c0 = mywin + ((z0 * kWinNodes + ny) * kWinNodes + nx) * 12 + ch;
+            *c0 += w0;
+            if (z1) c0[kWinNodes * kWinNodes * 12] += w1;
+          } else {  // tile spans more than the window (tiny images / huge grids): global reductions
+            const int gx = min(nx0 + nx, GX - 1), gy = min(ny0 + ny, GY - 1);
+            float* g0 = v_grid + ((size_t)(z0 * GY + gy) * GX + gx) * 12 + ch;
+            if (w0 != 0.f) red_add(g0, w0);
+            if (z1 && w1 != 0.f) red_add(g0 + (size_t)GY * GX * 12, w1);
+          }
+        }
       }
+      __syncwarp();
     }
   }
   __syncthreads();

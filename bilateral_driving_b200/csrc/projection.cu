@@ -48,102 +48,119 @@ BDS_HD void band_rows(const bds_render_desc& d, int tile_h, int c, int& ty0, int
   ty1 = hi - g0;
 }
 
-// tile rectangle of gsplat's isect_tiles (square 3-sigma bound) clipped to the band
-struct TileRect { int x0, x1, y0, y1; };
-BDS_HD TileRect tile_rect(float mx, float my, float radius, int tile_w, int tile_h, int ty0, int ty1) {
-  float tr = radius / (float)kTile, tx = mx / (float)kTile, ty = my / (float)kTile;
-  TileRect r;
-  float fx0 = floorf(tx - tr), fy0 = floorf(ty - tr), fx1 = ceilf(tx + tr), fy1 = ceilf(ty + tr);
-  r.x0 = (int)fminf(fmaxf(fx0, 0.f), (float)tile_w);
-  r.x1 = (int)fminf(fmaxf(fx1, 0.f), (float)tile_w);
-  r.y0 = (int)fminf(fmaxf(fy0, 0.f), (float)tile_h);
-  r.y1 = (int)fminf(fmaxf(fy1, 0.f), (float)tile_h);
-  if (r.y0 < ty0) r.y0 = ty0;
-  if (r.y1 > ty1) r.y1 = ty1;
-  if (r.y1 < r.y0) r.y1 = r.y0;
-  return r;
-}
+constexpr int kCoopTiles = 32;  // splats with more candidate tiles than this are enumerated by the whole warp
 
 __global__ void __launch_bounds__(256) project_fwd_kernel(ProjParams p) {
   const int N = p.d.n_gauss;
+  const int lane = threadIdx.x & 31;
   int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   bool in_range = idx < (int64_t)N * p.d.n_cams;
   int c = in_range ? (int)(idx / N) : 0;
   int n = in_range ? (int)(idx - (int64_t)c * N) : 0;
-  bool emit = false;
-  float rec[12];
-  int n_tiles = 0;
-  int radius_i = 0;
+  int n_tiles = 0, radius_i = 0;
+  // ---- phase 1: projection and candidate rectangle ------------------------------------------------
+  bool cand = false;
+  float mx = 0.f, my = 0.f, qa = 0.f, qb = 0.f, qc = 0.f, op = 0.f, sigma_cut = 0.f, depth = 0.f;
+  float mu[3] = {0.f, 0.f, 0.f};
+  TileRect tr = {0, 0, 0, 0};
+  CamIntr cam;
   if (in_range) {
     int ty0, ty1;
     band_rows(p.d, p.tile_h, c, ty0, ty1);
     if (ty1 > ty0) {
-      CamIntr cam;
       load_cam(p.viewmats, p.Ks, c, cam);
-      float mu[3] = {p.means[3 * (size_t)n], p.means[3 * (size_t)n + 1], p.means[3 * (size_t)n + 2]};
+      mu[0] = p.means[3 * (size_t)n]; mu[1] = p.means[3 * (size_t)n + 1]; mu[2] = p.means[3 * (size_t)n + 2];
       float q[4] = {p.quats[4 * (size_t)n], p.quats[4 * (size_t)n + 1], p.quats[4 * (size_t)n + 2], p.quats[4 * (size_t)n + 3]};
       float s[3] = {p.scales[3 * (size_t)n], p.scales[3 * (size_t)n + 1], p.scales[3 * (size_t)n + 2]};
       if (p.d.raw_params) { s[0] = __expf(s[0]); s[1] = __expf(s[1]); s[2] = __expf(s[2]); }
       Proj o;
-      bool vis = project_gaussian(mu, q, s, cam, p.d.width, p.d.height, p.d.eps2d, p.d.near_plane, p.d.far_plane,
-                                  p.d.radius_clip, o);
-      if (vis) {
+      if (project_gaussian(mu, q, s, cam, p.d.width, p.d.height, p.d.eps2d, p.d.near_plane, p.d.far_plane,
+                           p.d.radius_clip, o)) {
         radius_i = (int)o.radius;
         if (p.means2d) { p.means2d[2 * idx] = o.mx; p.means2d[2 * idx + 1] = o.my; }
         if (p.depths) p.depths[idx] = o.z;
         if (p.conics) { p.conics[3 * idx] = o.a; p.conics[3 * idx + 1] = o.b; p.conics[3 * idx + 2] = o.c; }
         if (p.compensations) p.compensations[idx] = o.comp;
-        float op = p.opacities[n];
+        op = p.opacities[n];
         if (p.d.raw_params) op = sigmoidf(op);
         if (p.d.antialiased) op *= o.comp;
-        float qa = 0.5f * kLog2e * o.a, qb = kLog2e * o.b, qc = 0.5f * kLog2e * o.c;
-        float sigma_cut = __log2f(255.0f * op);  // alpha >= 1/255  <=>  sigma' <= log2(255 o)
+        mx = o.mx; my = o.my; depth = o.z;
+        qa = 0.5f * kLog2e * o.a; qb = kLog2e * o.b; qc = 0.5f * kLog2e * o.c;
+        sigma_cut = __log2f(255.0f * op);  // alpha >= 1/255  <=>  sigma' <= log2(255 o)
         if (op >= kAlphaMin) {
-          TileRect tr = tile_rect(o.mx, o.my, o.radius, p.tile_w, p.tile_h, ty0, ty1);
-          for (int ty = tr.y0; ty < tr.y1; ++ty)
-            for (int tx = tr.x0; tx < tr.x1; ++tx)
-              n_tiles += tile_hit(o.mx, o.my, qa, qb, qc, sigma_cut, tx, ty, p.d.width, p.d.height) ? 1 : 0;
-        }
-        if (n_tiles > 0) {
-          emit = true;
-          rec[0] = o.mx; rec[1] = o.my; rec[2] = qa; rec[3] = qb; rec[4] = qc; rec[5] = op;
-          if (p.d.sh_degree >= 0) {
-            // view direction = mean - camera position, camera position = -R^T t  (vanilla.py:384-385)
-            float cp[3] = {-(cam.R[0] * cam.t[0] + cam.R[3] * cam.t[1] + cam.R[6] * cam.t[2]),
-                           -(cam.R[1] * cam.t[0] + cam.R[4] * cam.t[1] + cam.R[7] * cam.t[2]),
-                           -(cam.R[2] * cam.t[0] + cam.R[5] * cam.t[1] + cam.R[8] * cam.t[2])};
-            float dx = mu[0] - cp[0], dy = mu[1] - cp[1], dz = mu[2] - cp[2];
-            float inv = rsqrtf(dx * dx + dy * dy + dz * dz);
-            float b[16];
-            sh_basis(p.d.sh_degree, dx * inv, dy * inv, dz * inv, b);
-            int nb = (p.d.sh_degree + 1) * (p.d.sh_degree + 1);
-            if (nb > p.d.sh_K) nb = p.d.sh_K;
-            float col[3];
-#pragma unroll
-            for (int ch = 0; ch < 3; ++ch) col[ch] = b[0] * __ldg(p.fdc + 3 * (size_t)n + ch);
-            const float* fr = p.frest + (size_t)n * (p.d.sh_K - 1) * 3;
-            for (int k = 1; k < nb; ++k) {
-#pragma unroll
-              for (int ch = 0; ch < 3; ++ch) col[ch] = fmaf(b[k], __ldg(fr + (k - 1) * 3 + ch), col[ch]);
-            }
-#pragma unroll
-            for (int ch = 0; ch < 3; ++ch) rec[6 + ch] = fminf(fmaxf(col[ch] + 0.5f, 0.f), 1.f);
-          } else {
-            const float* cp = p.colors + (p.colors_per_cam ? 3 * (size_t)idx : 3 * (size_t)n);
-            rec[6] = cp[0]; rec[7] = cp[1]; rec[8] = cp[2];
-          }
-          rec[9] = o.z;
-          rec[10] = __int_as_float((int)idx);
-          rec[11] = sigma_cut;
+          tr = candidate_rect(mx, my, o.radius, qa, qb, qc, sigma_cut, p.tile_w, p.tile_h, ty0, ty1);
+          cand = (tr.x1 > tr.x0) && (tr.y1 > tr.y0);
         }
       }
     }
+  }
+  // ---- phase 2: exact tile count; big rectangles are enumerated by the whole warp ----------------
+  const int ncand = cand ? (tr.x1 - tr.x0) * (tr.y1 - tr.y0) : 0;
+  if (cand && ncand <= kCoopTiles) {
+    for (int ty = tr.y0; ty < tr.y1; ++ty)
+      for (int tx = tr.x0; tx < tr.x1; ++tx)
+        n_tiles += tile_hit(mx, my, qa, qb, qc, sigma_cut, tx, ty, p.d.width, p.d.height) ? 1 : 0;
+  }
+  unsigned big = __ballot_sync(0xffffffffu, ncand > kCoopTiles);
+  while (big) {
+    const int src = __ffs(big) - 1;
+    big &= big - 1;
+    const int bx0 = __shfl_sync(0xffffffffu, tr.x0, src), bx1 = __shfl_sync(0xffffffffu, tr.x1, src);
+    const int by0 = __shfl_sync(0xffffffffu, tr.y0, src), by1 = __shfl_sync(0xffffffffu, tr.y1, src);
+    const float gx = __shfl_sync(0xffffffffu, mx, src), gy = __shfl_sync(0xffffffffu, my, src);
+    const float ga = __shfl_sync(0xffffffffu, qa, src), gb = __shfl_sync(0xffffffffu, qb, src);
+    const float gc = __shfl_sync(0xffffffffu, qc, src), gcut = __shfl_sync(0xffffffffu, sigma_cut, src);
+    const int w = bx1 - bx0, total = w * (by1 - by0);
+    int cnt = 0;
+    for (int base = 0; base < total; base += 32) {
+      int i = base + lane;
+      bool hit = false;
+      if (i < total) {
+        int ty = by0 + i / w, tx = bx0 + i - (i / w) * w;
+        hit = tile_hit(gx, gy, ga, gb, gc, gcut, tx, ty, p.d.width, p.d.height);
+      }
+      cnt += __popc(__ballot_sync(0xffffffffu, hit));
+    }
+    if (lane == src) n_tiles = cnt;
+  }
+  // ---- phase 3: packed record (SH colour only for splats that reach some tile) ---------------------
+  const bool emit = n_tiles > 0;
+  float rec[12];
+  if (emit) {
+    rec[0] = mx; rec[1] = my; rec[2] = qa; rec[3] = qb; rec[4] = qc; rec[5] = op;
+    if (p.d.sh_degree >= 0) {
+      // view direction = mean - camera position, camera position = -R^T t  (vanilla.py:384-385)
+      float cp[3] = {-(cam.R[0] * cam.t[0] + cam.R[3] * cam.t[1] + cam.R[6] * cam.t[2]),
+                     -(cam.R[1] * cam.t[0] + cam.R[4] * cam.t[1] + cam.R[7] * cam.t[2]),
+                     -(cam.R[2] * cam.t[0] + cam.R[5] * cam.t[1] + cam.R[8] * cam.t[2])};
+      float dx = mu[0] - cp[0], dy = mu[1] - cp[1], dz = mu[2] - cp[2];
+      float inv = rsqrtf(dx * dx + dy * dy + dz * dz);
+      float b[16];
+      sh_basis(p.d.sh_degree, dx * inv, dy * inv, dz * inv, b);
+      int nb = (p.d.sh_degree + 1) * (p.d.sh_degree + 1);
+      if (nb > p.d.sh_K) nb = p.d.sh_K;
+      float col[3];
+#pragma unroll
+      for (int ch = 0; ch < 3; ++ch) col[ch] = b[0] * __ldg(p.fdc + 3 * (size_t)n + ch);
+      const float* fr = p.frest + (size_t)n * (p.d.sh_K - 1) * 3;
+      for (int k = 1; k < nb; ++k) {
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) col[ch] = fmaf(b[k], __ldg(fr + (k - 1) * 3 + ch), col[ch]);
+      }
+#pragma unroll
+      for (int ch = 0; ch < 3; ++ch) rec[6 + ch] = fminf(fmaxf(col[ch] + 0.5f, 0.f), 1.f);
+    } else {
+      const float* cp = p.colors + (p.colors_per_cam ? 3 * (size_t)idx : 3 * (size_t)n);
+      rec[6] = cp[0]; rec[7] = cp[1]; rec[8] = cp[2];
+    }
+    rec[9] = depth;
+    rec[10] = __int_as_float((int)idx);
+    rec[11] = sigma_cut;
   }
   // warp-aggregated compaction: one atomic per warp
   unsigned ballot = __ballot_sync(0xffffffffu, emit);
   int slot = -1;
   if (ballot) {
-    int lane = threadIdx.x & 31;
     int leader = __ffs(ballot) - 1;
     int base = 0;
     if (lane == leader) base = atomicAdd(p.counters, __popc(ballot));

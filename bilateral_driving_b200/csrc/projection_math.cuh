@@ -314,4 +314,44 @@ bool tile_hit(float gx, float gy, float qa, float qb, float qc, float sigma_cut,
   return !(s > sigma_cut + kCullMargin);
 }
 
+
+// Candidate tile rectangle of one splat inside the band rows [ty0, ty1) of its camera: gsplat's
+// isect_tiles square (3-sigma radius) bound intersected with the bounding box of the alpha >= 1/255
+// ellipse {sigma' <= sigma_cut}.  Only a candidate set: tile_hit() decides.  NOT inlined, for the same
+// reason as tile_hit (count and emission must agree).
+struct TileRect { int x0, x1, y0, y1; };
+#ifdef __CUDACC__
+static __host__ __device__ __noinline__
+#else
+static inline
+#endif
+TileRect candidate_rect(float mx, float my, float radius, float qa, float qb, float qc, float sigma_cut, int tile_w,
+                        int tile_h, int ty0, int ty1) {
+  const float inv = 1.0f / (float)kTile;
+  float tr = radius * inv, tx = mx * inv, ty = my * inv;
+  TileRect r;
+  r.x0 = (int)fminf(fmaxf(floorf(tx - tr), 0.f), (float)tile_w);
+  r.x1 = (int)fminf(fmaxf(ceilf(tx + tr), 0.f), (float)tile_w);
+  r.y0 = (int)fminf(fmaxf(floorf(ty - tr), 0.f), (float)tile_h);
+  r.y1 = (int)fminf(fmaxf(ceilf(ty + tr), 0.f), (float)tile_h);
+  // ellipse bounding box (pixel-centre coordinates), with slack
+  float det = qa * qc - 0.25f * qb * qb;
+  float cut = sigma_cut + 2.f * kCullMargin;
+  if (det > 0.f && cut > 0.f) {
+    float hx = sqrtf(cut * qc / det) + 0.05f, hy = sqrtf(cut * qa / det) + 0.05f;
+    // tile t covers pixel centres [16 t + 0.5, 16 t + 15.5]
+    float lx = ceilf((mx - hx - 15.5f) * inv), ux = floorf((mx + hx - 0.5f) * inv) + 1.f;
+    float ly = ceilf((my - hy - 15.5f) * inv), uy = floorf((my + hy - 0.5f) * inv) + 1.f;
+    if (lx > (float)r.x0) r.x0 = (int)fminf(lx, (float)tile_w);
+    if (ux < (float)r.x1) r.x1 = (int)fmaxf(ux, 0.f);
+    if (ly > (float)r.y0) r.y0 = (int)fminf(ly, (float)tile_h);
+    if (uy < (float)r.y1) r.y1 = (int)fmaxf(uy, 0.f);
+  }
+  if (r.y0 < ty0) r.y0 = ty0;
+  if (r.y1 > ty1) r.y1 = ty1;
+  if (r.x1 < r.x0) r.x1 = r.x0;
+  if (r.y1 < r.y0) r.y1 = r.y0;
+  return r;
+}
+
 }  // namespace bds

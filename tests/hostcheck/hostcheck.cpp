@@ -81,3 +81,26 @@ int hc_tri(float fx, float fy, float fz, int L, int GY, int GX, int* nodes, floa
   return t.z_inside ? 1 : 0;
 }
 }
+
+// candidate_rect must contain every tile that tile_hit accepts inside the gsplat square bound.
+// Returns the number of hit tiles outside the candidate rectangle (must be 0) and writes
+// stats[0] = tiles in the square bound, stats[1] = candidate tiles, stats[2] = hit tiles.
+extern "C" int hc_candidate_rect_check(float mx, float my, float radius, float qa, float qb, float qc,
+                                       float sigma_cut, int width, int height, int* stats) {
+  int tile_w = (width + kTile - 1) / kTile, tile_h = (height + kTile - 1) / kTile;
+  TileRect c = candidate_rect(mx, my, radius, qa, qb, qc, sigma_cut, tile_w, tile_h, 0, tile_h);
+  float tr = radius / kTile, tx = mx / kTile, ty = my / kTile;
+  int x0 = (int)fminf(fmaxf(floorf(tx - tr), 0.f), (float)tile_w), x1 = (int)fminf(fmaxf(ceilf(tx + tr), 0.f), (float)tile_w);
+  int y0 = (int)fminf(fmaxf(floorf(ty - tr), 0.f), (float)tile_h), y1 = (int)fminf(fmaxf(ceilf(ty + tr), 0.f), (float)tile_h);
+  int outside = 0, hits = 0;
+  for (int y = y0; y < y1; ++y)
+    for (int x = x0; x < x1; ++x)
+      if (tile_hit(mx, my, qa, qb, qc, sigma_cut, x, y, width, height)) {
+        ++hits;
+        if (!(x >= c.x0 && x < c.x1 && y >= c.y0 && y < c.y1)) ++outside;
+      }
+  stats[0] = (x1 - x0) * (y1 - y0);
+  stats[1] = (c.x1 - c.x0) * (c.y1 - c.y0);
+  stats[2] = hits;
+  return outside;
+}

@@ -172,3 +172,27 @@ def test_resize_taps_and_trilinear_stencil(hc):
         ref = B.trilerp(g, torch.tensor(fx).double(), torch.tensor(fy).double(), torch.tensor(fz).double())
         assert (ours - ref).abs().max() < 1e-5
         assert inside == int(0 < fz < 3)
+
+
+def test_candidate_rect_contains_every_hit_tile(hc):
+    """The ellipse-bbox pruning of the tile enumeration never drops a tile the exact test accepts."""
+    rng = np.random.default_rng(1)
+    hc.hc_candidate_rect_check.argtypes = [C.c_float] * 7 + [C.c_int, C.c_int, C.POINTER(C.c_int)]
+    tot = np.zeros(3, np.int64)
+    for _ in range(3000):
+        W, H = 1920, 1080
+        sx, sy = np.exp(rng.uniform(np.log(0.6), np.log(120.0), 2))  # pixel sigmas
+        rho = rng.uniform(-0.95, 0.95)
+        cov = np.array([[sx * sx, rho * sx * sy], [rho * sx * sy, sy * sy]])
+        con = np.linalg.inv(cov)
+        lam = 0.5 * (cov[0, 0] + cov[1, 1]) + np.sqrt(max(0.01, (0.5 * (cov[0, 0] + cov[1, 1])) ** 2 - np.linalg.det(cov)))
+        radius = float(np.ceil(3 * np.sqrt(lam)))
+        op = float(np.clip(rng.uniform(0.0, 1.0) ** 2, 1.0 / 255 + 1e-4, 1.0))
+        LOG2E = 1.4426950408889634
+        qa, qb, qc = 0.5 * LOG2E * con[0, 0], LOG2E * con[0, 1], 0.5 * LOG2E * con[1, 1]
+        mx, my = rng.uniform(-100, W + 100), rng.uniform(-100, H + 100)
+        stats = (C.c_int * 3)()
+        bad = hc.hc_candidate_rect_check(mx, my, radius, qa, qb, qc, float(np.log2(255 * op)), W, H, stats)
+        assert bad == 0
+        tot += np.array(list(stats))
+    assert tot[2] > 0 and tot[1] < tot[0]  # it does prune, and hits exist
