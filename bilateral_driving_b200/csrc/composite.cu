@@ -267,21 +267,25 @@ BDS_D float warp_transpose_reduce16(float v[16]) {
 
 // ---- block-cooperative bilateral backward (MODE 2) ---------------------------------------------
 // Grid-node gradients of one tile land in a handful of lattice nodes (a 16x16 tile spans a fraction
-// of a grid cell at 1080p): they are accumulated in shared memory - per pixel the 4 xy-corner x 12
-// channel products are spread over the lanes of a warp pair, 4 warp pairs take disjoint pixel
-// quarters into private windows (no shared-memory atomics) - and leave as one global reduction per
-// touched (node, channel) per tile instead of 96 per pixel per level.
-constexpr int kWinGroups = 4;                  // one per warp pair
+// of a grid cell at 1080p).  They are accumulated in shared memory and leave as one global reduction
+// per touched (node, channel) per tile instead of 96 per pixel per level:
+//   * every thread stages its pixel: vA[12], the 4 xy-corner weights, the 2 z weights and the word
+//     offset of its cell inside a 3x3x(L+1) node window (pixels whose cell falls outside the window -
+//     tiny images / huge grids - scatter straight to global memory instead);
+//   * half-warps (16 lanes = 4 xy-corners x 4 channels) sweep pixel lists: half-warp h serves channel
+//     quad h % 3 of pixel fifth h / 3 into that fifth's private window.  All four corners of a channel
+//     sit in one half-warp that handles one pixel at a time, and different half-warps touch different
+//     channels or different windows, so plain read-modify-writes never collide (no shared atomics,
+//     which are CAS loops for fp32).
+constexpr int kWinGroups = 5;
 constexpr int kWinNodes = 3;                   // window is kWinNodes x kWinNodes lattice nodes in xy
 constexpr int kWinMaxL = 16;
-constexpr int kStageFloats = 16;               // per pixel: vA[12], wx1, wy1, wz1, packed
-constexpr int kWinFloats = kWinNodes * kWinNodes * kWinMaxL * 12;
+constexpr int kStageFloats = 20;               // per pixel: vA[12] | wxy[4] | wz0, wz1, base, pad
+constexpr int kWinFloats = kWinNodes * kWinNodes * (kWinMaxL + 1) * 12;
 constexpr size_t kBwdSmemBil = (size_t)(256 * kStageFloats + kWinGroups * kWinFloats) * sizeof(float);
 constexpr size_t kBwdSmemRec = (size_t)kStages * kChunk * kRecBytes;
 constexpr size_t kBwdSmem = kBwdSmemBil > kBwdSmemRec ? kBwdSmemBil : kBwdSmemRec;
 
-// One level: every thread brings its pixel's vAff / Tri (valid = pixel inside the image); the block
-// accumulates into v_grid (global, [L][GY][GX][12]) through the shared windows.
 BDS_D void level_grad_accumulate(float* smem, const Tri& t, const float vAff[12], bool valid, int tile_x0,
                                  int tile_y0, int W, int H, int L, int GY, int GX, float* __restrict__ v_grid) {
   float* stage = smem;
@@ -291,59 +295,49 @@ BDS_D void level_grad_accumulate(float* smem, const Tri& t, const float vAff[12]
   const float fy0 = fminf(fmaxf(lattice_coord(tile_y0, H, GY), 0.f), (float)(GY - 1));
   const int nx0 = (int)floorf(fx0), ny0 = (int)floorf(fy0);
   const bool use_win = L <= kWinMaxL;
-  if (use_win) {
-    const int nwin = kWinGroups * kWinNodes * kWinNodes * L * 12;
-    for (int i = threadIdx.x; i < nwin; i += 256) win[i] = 0.f;
-  }
-  // stage this pixel's contribution
+  const int slab = kWinNodes * kWinNodes * 12;           // floats per z slab
+  const int per_win = slab * (L + 1);                    // + one dummy slab so z0 + 1 is always in range
+  if (use_win)
+    for (int i = threadIdx.x; i < kWinGroups * per_win; i += 256) win[i] = 0.f;
+  // ---- stage this pixel
   {
+    const int ox = t.x0 - nx0, oy = t.y0 - ny0;
+    const bool in_win = use_win && ox >= 0 && ox + 1 < kWinNodes && oy >= 0 && oy + 1 < kWinNodes;
+    int base = -1;
+    if (valid) {
+      if (in_win) base = ((t.z0 * kWinNodes + oy) * kWinNodes + ox) * 12;
+      else tri_scatter(v_grid, t, vAff);
+    }
+    const float wx0 = 1.f - t.wx1, wy0 = 1.f - t.wy1;
     float4* sp = reinterpret_cast<float4*>(stage + threadIdx.x * kStageFloats);
-    int ox = t.x0 - nx0, oy = t.y0 - ny0;
-    int z1 = t.dz != 0 ? 1 : 0;
-    int packed = valid ? (1 << 24) | (z1 << 20) | (t.z0 << 12) | ((oy & 63) << 6) | (ox & 63) : 0;
     sp[0] = make_float4(vAff[0], vAff[1], vAff[2], vAff[3]);
     sp[1] = make_float4(vAff[4], vAff[5], vAff[6], vAff[7]);
     sp[2] = make_float4(vAff[8], vAff[9], vAff[10], vAff[11]);
-    sp[3] = make_float4(t.wx1, t.wy1, t.wz1, __int_as_float(packed));
+    sp[3] = make_float4(wx0 * wy0, t.wx1 * wy0, wx0 * t.wy1, t.wx1 * t.wy1);
+    sp[4] = make_float4(1.f - t.wz1, t.dz != 0 ? t.wz1 : 0.f, __int_as_float(base), 0.f);
   }
   __syncthreads();
-  {
-    // Two warps form a group with a private window and a quarter of the tile's pixels.  All four
-    // xy-corners of a channel live in ONE warp (warp role 0: channels 0-7, role 1: channels 8-11), and
-    // the warp walks the pixels in lock step, so two lanes never update the same window word at the
-    // same time: within a pixel the four corners are four different nodes, and different pixels are
-    // separated by the __syncwarp below.  No shared-memory atomics needed.
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int grp = warp >> 1, role = warp & 1;
-    const int ch = role * 8 + (lane >> 2), corner = lane & 3;
-    const bool worker = ch < 12;
-    const int dx = corner & 1, dy = corner >> 1;
-    float* mywin = win + grp * (kWinNodes * kWinNodes * L * 12);
-    const int per = 256 / kWinGroups;
-    const int p0 = grp * per, p1 = p0 + per;
-    for (int px = p0; px < p1; ++px) {
-      const float* sp = stage + px * kStageFloats;
-      const int packed = __float_as_int(sp[15]);
-      if (worker && (packed >> 24)) {
-        int ox = packed & 63, oy = (packed >> 6) & 63;
-        const int z0 = (packed >> 12) & 255, z1 = (packed >> 20) & 1;
-        if (ox & 32) ox -= 64;   // sign-extend the 6-bit offsets
-        if (oy & 32) oy -= 64;
-        const float wx1 = sp[12], wy1 = sp[13], wz1 = sp[14];
-        const float w = (dx ? wx1 : 1.f - wx1) * (dy ? wy1 : 1.f - wy1) * sp[ch];
-        if (w != 0.f) {
-          const int nx = ox + dx, ny = oy + dy;
-          const float w0 = w * (1.f - wz1), w1 = w * wz1;
-          if (use_win && nx >= 0 && nx < kWinNodes && ny >= 0 && ny < kWinNodes) {
-            float* c0 = mywin + ((z0 * kWinNodes + ny) * kWinNodes + nx) * 12 + ch;
-            *c0 += w0;
-            if (z1) c0[kWinNodes * kWinNodes * 12] += w1;
-          } else {  // tile spans more than the window (tiny images / huge grids): global reductions
-            const int gx = min(nx0 + nx, GX - 1), gy = min(ny0 + ny, GY - 1);
-            float* g0 = v_grid + ((size_t)(z0 * GY + gy) * GX + gx) * 12 + ch;
-            if (w0 != 0.f) red_add(g0, w0);
-            if (z1 && w1 != 0.f) red_add(g0 + (size_t)GY * GX * 12, w1);
-          }
+  if (use_win) {
+    const int hw = threadIdx.x >> 4, l16 = threadIdx.x & 15;  // half-warp id 0..15, lane in half-warp
+    const int grp_raw = hw / 3, quad = hw - grp_raw * 3;
+    const bool worker = grp_raw < kWinGroups;          // half-warp 15 idles but keeps the warp in step
+    const int grp = worker ? grp_raw : 0;
+    const int corner = l16 & 3, ch = quad * 4 + (l16 >> 2);
+    const int coff = ((corner >> 1) * kWinNodes + (corner & 1)) * 12 + ch;  // (dy, dx) node + channel
+    float* mywin = win + grp * per_win + coff;
+    const int per = (256 + kWinGroups - 1) / kWinGroups;
+    const int p0 = grp * per, p1 = min(256, p0 + per);
+    for (int i = 0; i < per; ++i) {
+      const int px = p0 + i;
+      if (worker && px < p1) {
+        const float* sp = stage + px * kStageFloats;
+        const float4 m = *reinterpret_cast<const float4*>(sp + 16);
+        const int base = __float_as_int(m.z);
+        if (base >= 0) {
+          const float w = sp[12 + corner] * sp[ch];
+          float* c0 = mywin + base;
+          c0[0] = fmaf(w, m.x, c0[0]);
+          c0[slab] = fmaf(w, m.y, c0[slab]);
         }
       }
       __syncwarp();
@@ -351,15 +345,15 @@ BDS_D void level_grad_accumulate(float* smem, const Tri& t, const float vAff[12]
   }
   __syncthreads();
   if (use_win) {
-    const int per_win = kWinNodes * kWinNodes * L * 12;
-    for (int e = threadIdx.x; e < per_win; e += 256) {
+    const int n_out = slab * L;
+    for (int e = threadIdx.x; e < n_out; e += 256) {
       float v = 0.f;
 #pragma unroll
       for (int gq = 0; gq < kWinGroups; ++gq) v += win[gq * per_win + e];
       if (v != 0.f) {
-        int ch = e % 12, node = e / 12;
-        int nx = node % kWinNodes, ny = (node / kWinNodes) % kWinNodes, z = node / (kWinNodes * kWinNodes);
-        int gx = nx0 + nx, gy = ny0 + ny;
+        const int ch = e % 12, node = e / 12;
+        const int nx = node % kWinNodes, ny = (node / kWinNodes) % kWinNodes, z = node / (kWinNodes * kWinNodes);
+        const int gx = nx0 + nx, gy = ny0 + ny;
         if (gx < GX && gy < GY) red_add(v_grid + ((size_t)(z * GY + gy) * GX + gx) * 12 + ch, v);
       }
     }
