@@ -1,0 +1,79 @@
+"""CPU, world_size 2, gloo: the host-side multi-GPU logic (tile-row bands + the single flat gradient
+all-reduce) without a GPU."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from bilateral_driving_b200.dist import allreduce_grads, band_for_rank, band_pixel_rows, cameras_in_band
+
+
+def test_bands_partition_the_rig():
+    H, C = 1080, 6
+    tile_h = 68
+    for world in (1, 2, 3, 4, 6, 8):
+        covered = []
+        rows = []
+        for r in range(world):
+            rb, re = band_for_rank(r, world, C, H)
+            covered += list(range(rb, re))
+            r0, r1 = band_pixel_rows(rb, re, C, H)
+            rows.append((r0, r1))
+            cams = cameras_in_band(rb, re, H)
+            assert cams == sorted(set(g // tile_h for g in range(rb, re)))
+        assert covered == list(range(C * tile_h))
+        assert rows[0][0] == 0 and rows[-1][1] == C * H
+        for a, b in zip(rows[:-1], rows[1:]):
+            assert a[1] == b[0]
+    # 6 GPUs, 6 cameras -> one camera each; 8 GPUs -> bands cut cameras (tile sharding)
+    assert [cameras_in_band(*band_for_rank(r, 6, C, H), H) for r in range(6)] == [[c] for c in range(6)]
+    assert any(len(cameras_in_band(*band_for_rank(r, 8, C, H), H)) == 2 for r in range(8))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        # a toy "loss" that is a sum over pixel rows: each rank owns its band of rows, gradients add up
+        H, C, W = 40, 3, 8
+        g = torch.Generator(); g.manual_seed(0)
+        w = torch.randn(5, generator=g, requires_grad=True)
+        img = torch.randn(C * H, W, generator=g)
+        rb, re = band_for_rank(rank, world, C, H)
+        r0, r1 = band_pixel_rows(rb, re, C, H)
+        loss = (img[r0:r1].sum(1)[:, None] * w[None, :]).sum() / (C * H * W)
+        loss.backward()
+        grid_grad = torch.full((3,), float(rank + 1))
+        allreduce_grads([w.grad, None, grid_grad])
+        full = (img.sum(1)[:, None] * torch.ones(1, 5)).sum(0) / (C * H * W)
+        ok = torch.allclose(w.grad, full, atol=1e-6) and torch.allclose(grid_grad, torch.full((3,), 3.0))
+        ret[rank] = bool(ok)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_band_sharded_gradients_allreduce_gloo():
+    world = 2
+    port = _free_port()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
+    assert dict(ret) == {0: True, 1: True}
+
+
+def test_allreduce_is_noop_without_process_group():
+    t = torch.ones(3)
+    allreduce_grads([t])
+    assert torch.equal(t, torch.ones(3))
