@@ -142,9 +142,9 @@ struct EmitParams {
   bds_render_desc d;
   int tile_w, tile_h;
   const int32_t* radii;
-  const int32_t* slot_of;
   const int32_t* tiles_touched;
   int n_tiles;
+  int n_slots;
   const int64_t* offsets;
   const float* splats;
   uint64_t* keys;
@@ -154,21 +154,22 @@ struct EmitParams {
 constexpr int kCoopTiles = 32;  // work-split threshold only (same value as projection.cu); not a result
 
 __global__ void __launch_bounds__(256) emit_keys_kernel(EmitParams p) {
+  // one thread per compact splat record (slot); emission ORDER is fixed by the id-ordered offsets
   const int N = p.d.n_gauss;
   const int lane = threadIdx.x & 31;
-  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const bool in_range = idx < (int64_t)N * p.d.n_cams;
-  const int slot = in_range ? p.slot_of[idx] : -1;
-  const bool active = slot >= 0;
-  const int c = in_range ? (int)(idx / N) : 0;
+  const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool active = slot < p.n_slots;
   float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0, r2 = r0;
   TileRect tr = {0, 0, 0, 0};
   long long o = 0, o_end = 0;
+  int c = 0;
   if (active) {
-    int ty0, ty1;
-    band_rows2(p.d, p.tile_h, c, ty0, ty1);
     const float4* rp = reinterpret_cast<const float4*>(p.splats + (size_t)slot * 12);
     r0 = __ldg(rp); r1 = __ldg(rp + 1); r2 = __ldg(rp + 2);
+    const int64_t idx = (int64_t)__float_as_int(r2.z);
+    c = (int)(idx / N);
+    int ty0, ty1;
+    band_rows2(p.d, p.tile_h, c, ty0, ty1);
     // same candidate rectangle + same hit test (both non-inlined bodies) as the counting pass
     tr = candidate_rect(r0.x, r0.y, (float)p.radii[idx], r0.z, r0.w, r1.x, r2.w, p.tile_w, p.tile_h, ty0, ty1);
     o = p.offsets[idx];
@@ -395,15 +396,15 @@ extern "C" size_t bds_bin_sort_workspace_bytes(const bds_render_desc* d, int64_t
   return carve_sort(n_isect).total + 256;
 }
 
-extern "C" int bds_bin_sort(const bds_render_desc* d, int64_t n_isect, const int32_t* radii,
-                            const int32_t* tiles_touched, const int32_t* slot_of, const int64_t* isect_offsets,
+extern "C" int bds_bin_sort(const bds_render_desc* d, int64_t n_isect, int32_t n_slots, const int32_t* radii,
+                            const int32_t* tiles_touched, const int64_t* isect_offsets,
                             const float* splats, float* sorted_splats, int32_t* sorted_slots, int32_t* tile_offsets,
                             void* workspace, bds_stream_t stream_) {
   if (int rc = check_render_desc(d)) return rc;
   BDS_REQUIRE(n_isect >= 0 && n_isect < ((int64_t)1 << 31), "bin_sort: n_isect must fit int32 (got %lld)", (long long)n_isect);
   BDS_REQUIRE(tile_offsets, "bin_sort: null tile_offsets");
   if (n_isect > 0)
-    BDS_REQUIRE(radii && tiles_touched && slot_of && isect_offsets && splats && workspace, "bin_sort: null pointer");
+    BDS_REQUIRE(radii && tiles_touched && isect_offsets && splats && workspace && n_slots > 0, "bin_sort: null pointer");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const int tile_w = (d->width + kTile - 1) / kTile, tile_h = (d->height + kTile - 1) / kTile;
   const int n_tiles = (d->row_end - d->row_begin) * tile_w;
@@ -421,10 +422,9 @@ extern "C" int bds_bin_sort(const bds_render_desc* d, int64_t n_isect, const int
   void* scan_ws = ws + w.scan;
 
   EmitParams ep;
-  ep.d = *d; ep.tile_w = tile_w; ep.tile_h = tile_h; ep.radii = radii; ep.slot_of = slot_of; ep.tiles_touched = tiles_touched; ep.n_tiles = n_tiles; ep.offsets = isect_offsets;
+  ep.d = *d; ep.tile_w = tile_w; ep.tile_h = tile_h; ep.radii = radii; ep.tiles_touched = tiles_touched; ep.n_tiles = n_tiles; ep.n_slots = n_slots; ep.offsets = isect_offsets;
   ep.splats = splats; ep.keys = keys[0]; ep.vals = vals[0];
-  int64_t total = (int64_t)d->n_gauss * d->n_cams;
-  emit_keys_kernel<<<ceil_div(total, 256), 256, 0, stream>>>(ep);
+  emit_keys_kernel<<<ceil_div(n_slots, 256), 256, 0, stream>>>(ep);
   BDS_CHECK_LAUNCH();
 
   const int nblocks = ceil_div(n_isect, kRsTile);

@@ -297,8 +297,10 @@ BDS_D void level_grad_accumulate(float* smem, const Tri& t, const float vAff[12]
   const bool use_win = L <= kWinMaxL;
   const int slab = kWinNodes * kWinNodes * 12;           // floats per z slab
   const int per_win = slab * (L + 1);                    // + one dummy slab so z0 + 1 is always in range
-  if (use_win)
-    for (int i = threadIdx.x; i < kWinGroups * per_win; i += 256) win[i] = 0.f;
+  if (use_win) {
+    float4* w4 = reinterpret_cast<float4*>(win);
+    for (int i = threadIdx.x; i < kWinGroups * per_win / 4; i += 256) w4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
   // ---- stage this pixel
   {
     const int ox = t.x0 - nx0, oy = t.y0 - ny0;
@@ -318,43 +320,62 @@ BDS_D void level_grad_accumulate(float* smem, const Tri& t, const float vAff[12]
   }
   __syncthreads();
   if (use_win) {
-    const int hw = threadIdx.x >> 4, l16 = threadIdx.x & 15;  // half-warp id 0..15, lane in half-warp
-    const int grp_raw = hw / 3, quad = hw - grp_raw * 3;
-    const bool worker = grp_raw < kWinGroups;          // half-warp 15 idles but keeps the warp in step
-    const int grp = worker ? grp_raw : 0;
-    const int corner = l16 & 3, ch = quad * 4 + (l16 >> 2);
-    const int coff = ((corner >> 1) * kWinNodes + (corner & 1)) * 12 + ch;  // (dy, dx) node + channel
+    // 12 lanes of a half-warp = 4 xy-corners x 3 channel quads serve ONE pixel per step with float4
+    // read-modify-writes; half-warp g (g < kWinGroups) sweeps pixel fifth g into its private window.
+    const int hw = threadIdx.x >> 4, l16 = threadIdx.x & 15;
+    const bool worker = hw < kWinGroups && l16 < 12;
+    const int grp = hw < kWinGroups ? hw : 0;
+    const int corner = l16 / 3, quad = l16 - corner * 3;
+    const int coff = ((corner >> 1) * kWinNodes + (corner & 1)) * 12 + quad * 4;  // (dy, dx) node + channel quad
     float* mywin = win + grp * per_win + coff;
     const int per = (256 + kWinGroups - 1) / kWinGroups;
     const int p0 = grp * per, p1 = min(256, p0 + per);
-    for (int i = 0; i < per; ++i) {
-      const int px = p0 + i;
-      if (worker && px < p1) {
-        const float* sp = stage + px * kStageFloats;
-        const float4 m = *reinterpret_cast<const float4*>(sp + 16);
-        const int base = __float_as_int(m.z);
-        if (base >= 0) {
-          const float w = sp[12 + corner] * sp[ch];
-          float* c0 = mywin + base;
-          c0[0] = fmaf(w, m.x, c0[0]);
-          c0[slab] = fmaf(w, m.y, c0[slab]);
+    if (threadIdx.x < 32 * ((kWinGroups + 1) / 2)) {  // only the warps that hold a worker half-warp loop
+      for (int i = 0; i < per; ++i) {
+        const int px = p0 + i;
+        if (worker && px < p1) {
+          const float4* sp = reinterpret_cast<const float4*>(stage + px * kStageFloats);
+          const float4 m = sp[4];
+          const int base = __float_as_int(m.z);
+          if (base >= 0) {
+            const float4 va = sp[quad];
+            const float wc = stage[px * kStageFloats + 12 + corner];
+            const float w0 = wc * m.x, w1 = wc * m.y;
+            float4* c0 = reinterpret_cast<float4*>(mywin + base);
+            float4* c1 = reinterpret_cast<float4*>(mywin + base + slab);
+            float4 a = *c0, b = *c1;
+            a.x = fmaf(w0, va.x, a.x); a.y = fmaf(w0, va.y, a.y); a.z = fmaf(w0, va.z, a.z); a.w = fmaf(w0, va.w, a.w);
+            b.x = fmaf(w1, va.x, b.x); b.y = fmaf(w1, va.y, b.y); b.z = fmaf(w1, va.z, b.z); b.w = fmaf(w1, va.w, b.w);
+            *c0 = a;
+            *c1 = b;
+          }
         }
+        __syncwarp();
       }
-      __syncwarp();
     }
   }
   __syncthreads();
   if (use_win) {
-    const int n_out = slab * L;
-    for (int e = threadIdx.x; e < n_out; e += 256) {
-      float v = 0.f;
+    const int n_out4 = slab * L / 4;  // float4 entries; a float4 never straddles a node (12 floats per node)
+    const float4* win4 = reinterpret_cast<const float4*>(win);
+    for (int e = threadIdx.x; e < n_out4; e += 256) {
+      float4 v = win4[e];
 #pragma unroll
-      for (int gq = 0; gq < kWinGroups; ++gq) v += win[gq * per_win + e];
-      if (v != 0.f) {
-        const int ch = e % 12, node = e / 12;
+      for (int gq = 1; gq < kWinGroups; ++gq) {
+        const float4 u = win4[gq * (per_win / 4) + e];
+        v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w;
+      }
+      if (v.x != 0.f || v.y != 0.f || v.z != 0.f || v.w != 0.f) {
+        const int node = e / 3, ch0 = (e - node * 3) * 4;
         const int nx = node % kWinNodes, ny = (node / kWinNodes) % kWinNodes, z = node / (kWinNodes * kWinNodes);
         const int gx = nx0 + nx, gy = ny0 + ny;
-        if (gx < GX && gy < GY) red_add(v_grid + ((size_t)(z * GY + gy) * GX + gx) * 12 + ch, v);
+        if (gx < GX && gy < GY) {
+          float* dst = v_grid + ((size_t)(z * GY + gy) * GX + gx) * 12 + ch0;
+          if (v.x != 0.f) red_add(dst, v.x);
+          if (v.y != 0.f) red_add(dst + 1, v.y);
+          if (v.z != 0.f) red_add(dst + 2, v.z);
+          if (v.w != 0.f) red_add(dst + 3, v.w);
+        }
       }
     }
   }

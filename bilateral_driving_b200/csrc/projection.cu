@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(256) project_fwd_kernel(ProjParams p) {
   if (in_range) {
     if (p.radii) p.radii[idx] = radius_i;
     p.tiles_touched[idx] = n_tiles;
-    p.slot_of[idx] = slot;
+    if (p.slot_of) p.slot_of[idx] = slot;
     if (slot >= 0) {
       float4* dst = reinterpret_cast<float4*>(p.splats + (size_t)slot * 12);
       dst[0] = make_float4(rec[0], rec[1], rec[2], rec[3]);
@@ -382,7 +382,7 @@ extern "C" int bds_project_fwd(const bds_render_desc* d, const float* means, con
   if (int rc = check_render_desc(d)) return rc;
   int64_t total = (int64_t)d->n_gauss * d->n_cams;
   if (total == 0) return 0;
-  BDS_REQUIRE(means && quats && scales && opacities && viewmats && Ks && tiles_touched && splats && slot_of && counters,
+  BDS_REQUIRE(means && quats && scales && opacities && viewmats && Ks && tiles_touched && splats && counters,
               "project_fwd: null pointer");
   if (d->sh_degree >= 0)
     BDS_REQUIRE(features_dc && (features_rest || d->sh_K == 1), "project_fwd: SH path needs features_dc/rest");

@@ -97,6 +97,19 @@ BDS_HD bool project_gaussian(const float mu[3], const float q[4], const float s[
   o.y = cam.R[3] * mu[0] + cam.R[4] * mu[1] + cam.R[5] * mu[2] + cam.t[1];
   o.z = cam.R[6] * mu[0] + cam.R[7] * mu[1] + cam.R[8] * mu[2] + cam.t[2];
   if (o.z < near_plane || o.z > far_plane) return false;
+  {
+    // Cheap conservative screen cull before the covariance arithmetic (5/6 of a rig's Gaussians are
+    // outside any one camera): radius <= 3 sqrt(lambda_max) + 1 and lambda_max <= ||J||_F^2 smax^2 + 0.7
+    // (trace bound incl. the eps2d blur and the 0.01 floor), so a splat whose mean is further than that
+    // bound outside the image is culled by gsplat's own test as well.
+    float smax = fmaxf(s[0], fmaxf(s[1], s[2]));
+    float lx = 1.3f * (0.5f * (float)width / cam.fx), ly = 1.3f * (0.5f * (float)height / cam.fy);
+    float rzq = 1.0f / o.z;
+    float jf2 = (cam.fx * cam.fx * (1.f + lx * lx) + cam.fy * cam.fy * (1.f + ly * ly)) * rzq * rzq;
+    float rb = 3.f * sqrtf(jf2 * smax * smax + 0.7f + eps2d) * 1.001f + 2.f;
+    float px = cam.fx * o.x * rzq + cam.cx, py = cam.fy * o.y * rzq + cam.cy;
+    if (px + rb <= 0.f || px - rb >= (float)width || py + rb <= 0.f || py - rb >= (float)height) return false;
+  }
   float Rq[9], cov[6], Sc[9];
   quat_to_rotmat(q, Rq);
   covar_world(Rq, s, cov);

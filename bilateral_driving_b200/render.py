@@ -152,7 +152,6 @@ class _RenderFn(torch.autograd.Function):
             means2d = depths = conics = None
         comps = torch.zeros(Cn, N, **f32) if (cfg.antialiased and cfg.dense_info) else None
         tiles_touched = torch.empty(Cn, N, **i32)
-        slot_of = torch.empty(Cn, N, **i32)
         counters = torch.zeros(4, **i32)
         cap = cfg.splat_capacity or max(Cn * N, 1)
         splats = torch.empty(cap, 12, **f32)
@@ -160,7 +159,7 @@ class _RenderFn(torch.autograd.Function):
         check(lib.bds_project_fwd(C.byref(d), ptr(means), ptr(quats), ptr(scales), ptr(opacities), ptr(colors),
                                   colors_per_cam, ptr(fdc), ptr(frest), ptr(viewmats), ptr(Ks), ptr(radii),
                                   ptr(means2d), ptr(depths), ptr(conics), ptr(comps), ptr(tiles_touched), ptr(splats),
-                                  C.c_int32(cap), ptr(slot_of), ptr(counters), st), "bds_project_fwd")
+                                  C.c_int32(cap), NULL, ptr(counters), st), "bds_project_fwd")
         offsets = torch.empty(Cn * N, device=dev, dtype=torch.int64)
         stats = torch.zeros(1, device=dev, dtype=torch.int64)
         ws0 = torch.empty(int(lib.bds_bin_count_workspace_bytes(C.c_int64(Cn * N))), device=dev, dtype=torch.uint8)
@@ -174,7 +173,7 @@ class _RenderFn(torch.autograd.Function):
         tile_offsets = torch.empty(n_band_tiles + 1, **i32)
         ws1 = torch.empty(int(lib.bds_bin_sort_workspace_bytes(C.byref(d), C.c_int64(n_isect))), device=dev,
                           dtype=torch.uint8)
-        check(lib.bds_bin_sort(C.byref(d), C.c_int64(n_isect), ptr(radii), ptr(tiles_touched), ptr(slot_of),
+        check(lib.bds_bin_sort(C.byref(d), C.c_int64(n_isect), C.c_int32(n_slots), ptr(radii), ptr(tiles_touched),
                                ptr(offsets), ptr(splats), ptr(sorted_splats), NULL, ptr(tile_offsets), ptr(ws1), st),
               "bds_bin_sort")
         del ws1, offsets

@@ -123,7 +123,7 @@ typedef struct {
  * band), and compacts the visible splats into packed 48-byte records:
  *   splats [cap,12] = {x, y, a', b', c', opacity, r, g, b, depth, bits(flat id c*N+n), sigma_cut}
  * with (a',b',c') = log2(e) * (a/2, b, c/2) of the conic and sigma_cut = log2(255*opacity);
- * slot_of [C,N] int32 = record index or -1; counters[0] = number of records (device int32,
+ * slot_of [C,N] int32 = record index or -1 (optional, may be NULL); counters[0] = number of records (device int32,
  * caller zero-fills counters[0..3]); counters[1] is set to 1 on capacity overflow.
  * camera position for the SH view direction is taken from viewmats. */
 int bds_project_fwd(const bds_render_desc* d, const float* means, const float* quats,
@@ -145,8 +145,8 @@ int bds_bin_count(const bds_render_desc* d, const int32_t* tiles_touched, int64_
 size_t bds_bin_sort_workspace_bytes(const bds_render_desc* d, int64_t n_isect);
 /* sorted_splats [n_isect,12]; sorted_slots [n_isect] int32 (record -> splat slot);
  * tile_offsets [n_band_tiles + 1] int32 where band tile t = (global_row - row_begin)*tile_w + tx */
-int bds_bin_sort(const bds_render_desc* d, int64_t n_isect, const int32_t* radii,
-                 const int32_t* tiles_touched, const int32_t* slot_of, const int64_t* isect_offsets,
+int bds_bin_sort(const bds_render_desc* d, int64_t n_isect, int32_t n_slots /* = counters[0] */,
+                 const int32_t* radii, const int32_t* tiles_touched, const int64_t* isect_offsets,
                  const float* splats, float* sorted_splats, int32_t* sorted_slots,
                  int32_t* tile_offsets, void* workspace, bds_stream_t stream);
 
