@@ -410,7 +410,7 @@ BDS_D void level_grad_accumulate(float* smem, const Tri& t, const float vAff[12]
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(256, 3) composite_bwd_kernel(CompParams p) {
+__global__ void __launch_bounds__(256, 4) composite_bwd_kernel(CompParams p) {
   extern __shared__ __align__(128) unsigned char dyn_smem[];
   float4 (*srec)[kChunk * 3] = reinterpret_cast<float4 (*)[kChunk * 3]>(dyn_smem);
   __shared__ __align__(8) uint64_t bars[kStages];

@@ -37,13 +37,20 @@ def cameras_in_band(rb: int, re: int, height: int) -> List[int]:
 
 
 def allreduce_grads(tensors: Sequence[torch.Tensor], group=None) -> None:
-    """One all-reduce (SUM) over a single flat buffer holding every gradient; results are copied
-    back in place.  No-op for a single process."""
+    """One all-reduce (SUM) of every gradient: a single coalesced NCCL group launch in place on GPUs, a
+    single flat buffer elsewhere (gloo).  No-op for a single process."""
     import torch.distributed as dist
 
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return
     grads = [t for t in tensors if t is not None]
+    backend = dist.get_backend(group)
+    if backend == "nccl" and hasattr(dist, "_coalescing_manager"):
+        # one fused NCCL launch (ncclGroupStart/End) over the gradient tensors in place: no staging copy
+        with dist._coalescing_manager(group=group, device=grads[0].device, async_ops=False):
+            for g in grads:
+                dist.all_reduce(g, op=dist.ReduceOp.SUM, group=group)
+        return
     flat = torch.cat([g.reshape(-1) for g in grads])
     dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
     off = 0
