@@ -1,11 +1,12 @@
-// Tile binning: exclusive scan of per-(camera, Gaussian) tile counts, emission of
-// (band tile | fp32 depth bits) keys in Gaussian-id order, a stable LSD radix sort written for this
-// library (no CUB / thrust), per-tile start offsets and the gather of the packed 48-byte splat
-// records into sorted order so that the composite kernels read contiguous chunks (TMA bulk copies).
+// Tile binning: one scan of the per-(camera, Gaussian) tile counts (record total + id-ordered rank of
+// every emitting splat), a stable LSD radix sort written for this library (no CUB / thrust) used twice
+// - visible splats by fp32 depth bits, then the emitted (band tile, slot) records by tile -, per-tile
+// start offsets and the gather of the packed 48-byte splat records into sorted order so that the
+// composite kernels read contiguous chunks (TMA bulk copies).
 //
 // Replaces gsplat's isect_tiles + torch.cumsum + cub::DeviceRadixSort + isect_offset_encode for the
 // reference call at models/trainers/base.py:393-408.  Ordering contract = gsplat's: ascending
-// (camera, tile, depth bits), ties in Gaussian-id order (stable sort over id-ordered emission).
+// (camera, tile, depth bits), ties in Gaussian-id order.
 //
 // All kernels are HBM-bound integer / copy work: coalesced loads, grid sized to the data.
 #include "projection_math.cuh"
@@ -136,103 +137,7 @@ static int exclusive_scan(const TIn* in, TOut* out, int64_t n, int64_t* total_de
 }
 
 // ---------------------------------------------------------------------------------------------
-// key emission: one thread per (camera, Gaussian) with tiles_touched > 0
-// ---------------------------------------------------------------------------------------------
-struct EmitParams {
-  bds_render_desc d;
-  int tile_w, tile_h;
-  const int32_t* radii;
-  const int32_t* tiles_touched;
-  int n_tiles;
-  int n_slots;
-  const int64_t* offsets;
-  const float* splats;
-  uint64_t* keys;
-  uint32_t* vals;
-};
-
-constexpr int kCoopTiles = 32;  // work-split threshold only (same value as projection.cu); not a result
-
-__global__ void __launch_bounds__(256) emit_keys_kernel(EmitParams p) {
-  // one thread per compact splat record (slot); emission ORDER is fixed by the id-ordered offsets
-  const int N = p.d.n_gauss;
-  const int lane = threadIdx.x & 31;
-  const int slot = blockIdx.x * blockDim.x + threadIdx.x;
-  const bool active = slot < p.n_slots;
-  float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0, r2 = r0;
-  TileRect tr = {0, 0, 0, 0};
-  long long o = 0, o_end = 0;
-  int c = 0;
-  if (active) {
-    const float4* rp = reinterpret_cast<const float4*>(p.splats + (size_t)slot * 12);
-    r0 = __ldg(rp); r1 = __ldg(rp + 1); r2 = __ldg(rp + 2);
-    const int64_t idx = (int64_t)__float_as_int(r2.z);
-    c = (int)(idx / N);
-    int ty0, ty1;
-    band_rows2(p.d, p.tile_h, c, ty0, ty1);
-    // same candidate rectangle + same hit test (both non-inlined bodies) as the counting pass
-    tr = candidate_rect(r0.x, r0.y, (float)p.radii[idx], r0.z, r0.w, r1.x, r2.w, p.tile_w, p.tile_h, ty0, ty1);
-    o = p.offsets[idx];
-    o_end = o + p.tiles_touched[idx];
-  }
-  const uint64_t depth_bits = (uint64_t)(uint32_t)__float_as_int(r2.y);
-  const int ncand = active ? (tr.x1 - tr.x0) * (tr.y1 - tr.y0) : 0;
-  // The o_end guard and the sentinel padding (a key that sorts behind every real tile) only make a
-  // count / emission disagreement memory-safe should a toolchain ever break the shared-body contract.
-  if (active && ncand <= kCoopTiles) {
-    for (int ty = tr.y0; ty < tr.y1; ++ty) {
-      for (int tx = tr.x0; tx < tr.x1; ++tx) {
-        if (tile_hit(r0.x, r0.y, r0.z, r0.w, r1.x, r2.w, tx, ty, p.d.width, p.d.height) && o < o_end) {
-          uint64_t band_tile = (uint64_t)((c * p.tile_h + ty - p.d.row_begin) * p.tile_w + tx);
-          p.keys[o] = (band_tile << 32) | depth_bits;
-          p.vals[o] = (uint32_t)slot;
-          ++o;
-        }
-      }
-    }
-  }
-  unsigned big = __ballot_sync(0xffffffffu, ncand > kCoopTiles);
-  while (big) {
-    const int src = __ffs(big) - 1;
-    big &= big - 1;
-    const int bx0 = __shfl_sync(0xffffffffu, tr.x0, src), bx1 = __shfl_sync(0xffffffffu, tr.x1, src);
-    const int by0 = __shfl_sync(0xffffffffu, tr.y0, src), by1 = __shfl_sync(0xffffffffu, tr.y1, src);
-    const float gx = __shfl_sync(0xffffffffu, r0.x, src), gy = __shfl_sync(0xffffffffu, r0.y, src);
-    const float ga = __shfl_sync(0xffffffffu, r0.z, src), gb = __shfl_sync(0xffffffffu, r0.w, src);
-    const float gc = __shfl_sync(0xffffffffu, r1.x, src), gcut = __shfl_sync(0xffffffffu, r2.w, src);
-    const int gcam = __shfl_sync(0xffffffffu, c, src), gslot = __shfl_sync(0xffffffffu, slot, src);
-    const unsigned dlo = __shfl_sync(0xffffffffu, (unsigned)depth_bits, src);
-    long long go = __shfl_sync(0xffffffffu, o, src);
-    const long long gend = __shfl_sync(0xffffffffu, o_end, src);
-    const int w = bx1 - bx0, total = w * (by1 - by0);
-    for (int base = 0; base < total; base += 32) {
-      int i = base + lane;
-      bool hit = false;
-      int tx = 0, ty = 0;
-      if (i < total) {
-        ty = by0 + i / w;
-        tx = bx0 + i - (i / w) * w;
-        hit = tile_hit(gx, gy, ga, gb, gc, gcut, tx, ty, p.d.width, p.d.height);
-      }
-      unsigned hm = __ballot_sync(0xffffffffu, hit);
-      long long pos = go + __popc(hm & ((1u << lane) - 1u));
-      if (hit && pos < gend) {
-        uint64_t band_tile = (uint64_t)((gcam * p.tile_h + ty - p.d.row_begin) * p.tile_w + tx);
-        p.keys[pos] = (band_tile << 32) | (uint64_t)dlo;
-        p.vals[pos] = (uint32_t)gslot;
-      }
-      go += __popc(hm);
-    }
-    if (lane == src) o = go < o_end ? go : o_end;
-  }
-  for (; o < o_end; ++o) {
-    p.keys[o] = ((uint64_t)p.n_tiles << 32) | depth_bits;
-    p.vals[o] = (uint32_t)slot;
-  }
-}
-
-// ---------------------------------------------------------------------------------------------
-// LSD radix sort, 8-bit digits, (uint64 key, uint32 value), stable.  Per pass:
+// LSD radix sort, 8-bit digits, (KeyT key, uint32 value), stable.  Per pass:
 //   rs_hist_kernel     per-block digit histogram -> hist[digit][block]
 //   exclusive_scan     over the digit-major array -> global base of every (digit, block)
 //   rs_scatter_kernel  stable in-block ranking (warp match_any + per-warp counters) and scatter
@@ -242,7 +147,8 @@ constexpr int kRsItems = 16;
 constexpr int kRsTile = kRsThreads * kRsItems;  // 4096 keys per block
 constexpr int kRsWarps = kRsThreads / 32;
 
-__global__ void __launch_bounds__(kRsThreads) rs_hist_kernel(const uint64_t* __restrict__ keys, int64_t n, int shift,
+template <typename KeyT>
+__global__ void __launch_bounds__(kRsThreads) rs_hist_kernel(const KeyT* __restrict__ keys, int64_t n, int shift,
                                                              int nblocks, uint32_t* __restrict__ hist) {
   __shared__ uint32_t sh[256];
   sh[threadIdx.x] = 0;
@@ -257,11 +163,12 @@ __global__ void __launch_bounds__(kRsThreads) rs_hist_kernel(const uint64_t* __r
   hist[(size_t)threadIdx.x * nblocks + blockIdx.x] = sh[threadIdx.x];
 }
 
-__global__ void __launch_bounds__(kRsThreads) rs_scatter_kernel(const uint64_t* __restrict__ keys_in,
+template <typename KeyT>
+__global__ void __launch_bounds__(kRsThreads) rs_scatter_kernel(const KeyT* __restrict__ keys_in,
                                                                 const uint32_t* __restrict__ vals_in, int64_t n,
                                                                 int shift, int nblocks,
                                                                 const uint32_t* __restrict__ base,
-                                                                uint64_t* __restrict__ keys_out,
+                                                                KeyT* __restrict__ keys_out,
                                                                 uint32_t* __restrict__ vals_out) {
   __shared__ uint32_t warp_hist[kRsWarps][256];
   __shared__ uint32_t gbase[256];
@@ -271,13 +178,13 @@ __global__ void __launch_bounds__(kRsThreads) rs_scatter_kernel(const uint64_t* 
   __syncthreads();
   // warp w owns the contiguous segment [w*512, (w+1)*512) of the block tile, in rounds of 32
   int64_t seg = (int64_t)blockIdx.x * kRsTile + (int64_t)warp * (32 * kRsItems);
-  uint64_t key[kRsItems];
+  KeyT key[kRsItems];
   uint32_t rank[kRsItems];
 #pragma unroll
   for (int r = 0; r < kRsItems; ++r) {
     int64_t i = seg + r * 32 + lane;
     bool valid = i < n;
-    key[r] = valid ? keys_in[i] : ~0ull;
+    key[r] = valid ? keys_in[i] : (KeyT)0;
     uint32_t digit = valid ? ((uint32_t)(key[r] >> shift) & 255u) : 256u;  // 256 = "no element"
     unsigned peers = __match_any_sync(0xffffffffu, digit);
     uint32_t before = __popc(peers & ((1u << lane) - 1u));
@@ -314,8 +221,151 @@ __global__ void __launch_bounds__(kRsThreads) rs_scatter_kernel(const uint64_t* 
   }
 }
 
-// per-tile start offsets from the sorted keys (the role of isect_offset_encode)
-__global__ void __launch_bounds__(256) tile_offsets_kernel(const uint64_t* __restrict__ keys, int64_t n, int n_tiles,
+// sorts (keys[0], vals[0]) over bits [0, end_bit); returns the index (0/1) of the buffer holding the result
+template <typename KeyT>
+static int radix_sort_pairs(KeyT* keys[2], uint32_t* vals[2], int64_t n, int end_bit, uint32_t* hist, void* scan_ws,
+                            cudaStream_t stream, int* result_buf) {
+  const int nblocks = ceil_div(n, kRsTile);
+  int cur = 0;
+  for (int shift = 0; shift < end_bit; shift += 8) {
+    rs_hist_kernel<KeyT><<<nblocks, kRsThreads, 0, stream>>>(keys[cur], n, shift, nblocks, hist);
+    BDS_CHECK_LAUNCH();
+    if (int rc = exclusive_scan<uint32_t, uint32_t>(hist, hist, (int64_t)256 * nblocks, nullptr, scan_ws, stream)) return rc;
+    rs_scatter_kernel<KeyT><<<nblocks, kRsThreads, 0, stream>>>(keys[cur], vals[cur], n, shift, nblocks, hist,
+                                                                keys[cur ^ 1], vals[cur ^ 1]);
+    BDS_CHECK_LAUNCH();
+    cur ^= 1;
+  }
+  *result_buf = cur;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Two-stage ordering.  gsplat sorts every (tile, splat) record by a 64-bit (tile | depth) key; here the
+// visible splats (n_slots, ~7x fewer than records) are first sorted by (depth bits, Gaussian id), the
+// records are then emitted in that order and only need a STABLE sort on the tile index
+// (17 bits -> 3 passes of 20 B/record instead of 6 passes of 32 B/record).  Result: per tile ascending
+// (depth bits, id) - exactly the order of gsplat's stable 64-bit sort over id-ordered emission.
+// ---------------------------------------------------------------------------------------------
+constexpr int kRankShift = 40;  // bds_bin_count packs (rank of emitting splats << 40) | tile prefix
+
+// stage-1 input in Gaussian-id order: key = depth bits, value = slot (one thread per compact slot)
+__global__ void __launch_bounds__(256) stage1_fill_kernel(const float* __restrict__ splats, int n_slots,
+                                                          const int64_t* __restrict__ packed_prefix,
+                                                          uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+  int slot = blockIdx.x * blockDim.x + threadIdx.x;
+  if (slot >= n_slots) return;
+  const float* rec = splats + (size_t)slot * 12;
+  int64_t idx = (int64_t)__float_as_int(__ldg(rec + 10));
+  int64_t rank = packed_prefix[idx] >> kRankShift;
+  keys[rank] = (uint32_t)__float_as_int(__ldg(rec + 9));  // positive floats order like their bit patterns
+  vals[rank] = (uint32_t)slot;
+}
+
+// tiles_touched in depth-sorted order (input of the second scan)
+__global__ void __launch_bounds__(256) gather_tiles_kernel(const float* __restrict__ splats,
+                                                           const uint32_t* __restrict__ sorted_slots, int n_slots,
+                                                           const int32_t* __restrict__ tiles_touched,
+                                                           int32_t* __restrict__ out) {
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_slots) return;
+  int64_t idx = (int64_t)__float_as_int(__ldg(splats + (size_t)sorted_slots[r] * 12 + 10));
+  out[r] = tiles_touched[idx];
+}
+
+struct EmitParams {
+  bds_render_desc d;
+  int tile_w, tile_h;
+  const int32_t* radii;
+  const int32_t* tiles_sorted;   // [n_slots] tile counts in depth order
+  const int64_t* offsets;        // [n_slots] exclusive prefix of tiles_sorted
+  const uint32_t* sorted_slots;  // [n_slots] slots in (depth, id) order
+  int n_tiles;
+  int n_slots;
+  const float* splats;
+  uint32_t* keys;
+  uint32_t* vals;
+};
+
+constexpr int kCoopTiles = 32;  // work-split threshold only (same value as projection.cu); not a result
+
+// one thread per splat in (depth, id) order: emits (band tile, slot) for every tile it reaches
+__global__ void __launch_bounds__(256) emit_keys_kernel(EmitParams p) {
+  const int N = p.d.n_gauss;
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool active = r < p.n_slots;
+  const int slot = active ? (int)p.sorted_slots[r] : 0;
+  float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0, r2 = r0;
+  TileRect tr = {0, 0, 0, 0};
+  long long o = 0, o_end = 0;
+  int c = 0;
+  if (active) {
+    const float4* rp = reinterpret_cast<const float4*>(p.splats + (size_t)slot * 12);
+    r0 = __ldg(rp); r1 = __ldg(rp + 1); r2 = __ldg(rp + 2);
+    const int64_t idx = (int64_t)__float_as_int(r2.z);
+    c = (int)(idx / N);
+    int ty0, ty1;
+    band_rows2(p.d, p.tile_h, c, ty0, ty1);
+    // same candidate rectangle + same hit test (both non-inlined bodies) as the counting pass
+    tr = candidate_rect(r0.x, r0.y, (float)p.radii[idx], r0.z, r0.w, r1.x, r2.w, p.tile_w, p.tile_h, ty0, ty1);
+    o = p.offsets[r];
+    o_end = o + p.tiles_sorted[r];
+  }
+  const int ncand = active ? (tr.x1 - tr.x0) * (tr.y1 - tr.y0) : 0;
+  // The o_end guard and the sentinel padding (a key that sorts behind every real tile) only make a
+  // count / emission disagreement memory-safe should a toolchain ever break the shared-body contract.
+  if (active && ncand <= kCoopTiles) {
+    for (int ty = tr.y0; ty < tr.y1; ++ty) {
+      for (int tx = tr.x0; tx < tr.x1; ++tx) {
+        if (tile_hit(r0.x, r0.y, r0.z, r0.w, r1.x, r2.w, tx, ty, p.d.width, p.d.height) && o < o_end) {
+          p.keys[o] = (uint32_t)((c * p.tile_h + ty - p.d.row_begin) * p.tile_w + tx);
+          p.vals[o] = (uint32_t)slot;
+          ++o;
+        }
+      }
+    }
+  }
+  unsigned big = __ballot_sync(0xffffffffu, ncand > kCoopTiles);
+  while (big) {
+    const int src = __ffs(big) - 1;
+    big &= big - 1;
+    const int bx0 = __shfl_sync(0xffffffffu, tr.x0, src), bx1 = __shfl_sync(0xffffffffu, tr.x1, src);
+    const int by0 = __shfl_sync(0xffffffffu, tr.y0, src), by1 = __shfl_sync(0xffffffffu, tr.y1, src);
+    const float gx = __shfl_sync(0xffffffffu, r0.x, src), gy = __shfl_sync(0xffffffffu, r0.y, src);
+    const float ga = __shfl_sync(0xffffffffu, r0.z, src), gb = __shfl_sync(0xffffffffu, r0.w, src);
+    const float gc = __shfl_sync(0xffffffffu, r1.x, src), gcut = __shfl_sync(0xffffffffu, r2.w, src);
+    const int gcam = __shfl_sync(0xffffffffu, c, src), gslot = __shfl_sync(0xffffffffu, slot, src);
+    long long go = __shfl_sync(0xffffffffu, o, src);
+    const long long gend = __shfl_sync(0xffffffffu, o_end, src);
+    const int w = bx1 - bx0, total = w * (by1 - by0);
+    for (int base = 0; base < total; base += 32) {
+      int i = base + lane;
+      bool hit = false;
+      int tx = 0, ty = 0;
+      if (i < total) {
+        ty = by0 + i / w;
+        tx = bx0 + i - (i / w) * w;
+        hit = tile_hit(gx, gy, ga, gb, gc, gcut, tx, ty, p.d.width, p.d.height);
+      }
+      unsigned hm = __ballot_sync(0xffffffffu, hit);
+      long long pos = go + __popc(hm & ((1u << lane) - 1u));
+      if (hit && pos < gend) {
+        p.keys[pos] = (uint32_t)((gcam * p.tile_h + ty - p.d.row_begin) * p.tile_w + tx);
+        p.vals[pos] = (uint32_t)gslot;
+      }
+      go += __popc(hm);
+    }
+    if (lane == src) o = go < o_end ? go : o_end;
+  }
+  for (; o < o_end; ++o) {
+    p.keys[o] = (uint32_t)p.n_tiles;
+    p.vals[o] = (uint32_t)slot;
+  }
+}
+
+// per-tile start offsets from the sorted tile keys (the role of isect_offset_encode)
+__global__ void __launch_bounds__(256) tile_offsets_kernel(const uint32_t* __restrict__ keys, int64_t n, int n_tiles,
                                                            int32_t* __restrict__ offsets) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (n == 0) {
@@ -323,12 +373,12 @@ __global__ void __launch_bounds__(256) tile_offsets_kernel(const uint64_t* __res
     return;
   }
   if (i >= n) return;
-  int cur = (int)(keys[i] >> 32);
+  int cur = (int)keys[i];
   if (i == 0) {
-    for (int t = 0; t <= cur; ++t) offsets[t] = 0;
+    for (int t = 0; t <= cur && t <= n_tiles; ++t) offsets[t] = 0;
   } else {
-    int prev = (int)(keys[i - 1] >> 32);
-    for (int t = prev + 1; t <= cur; ++t) offsets[t] = (int32_t)i;
+    int prev = (int)keys[i - 1];
+    for (int t = prev + 1; t <= cur && t <= n_tiles; ++t) offsets[t] = (int32_t)i;
   }
   if (i == n - 1) {
     for (int t = cur + 1; t <= n_tiles; ++t) offsets[t] = (int32_t)n;
@@ -350,19 +400,21 @@ __global__ void __launch_bounds__(256) gather_records_kernel(const uint32_t* __r
 }
 
 struct SortWorkspace {
-  size_t keys_a, keys_b, vals_a, vals_b, hist, scan, total;
+  size_t keys_a, keys_b, vals_a, vals_b, s1k_a, s1k_b, s1v_a, s1v_b, tiles_sorted, offs2, hist, scan, total;
 };
-static SortWorkspace carve_sort(int64_t n_isect) {
+static SortWorkspace carve_sort(int64_t n_isect, int64_t n_slots) {
   SortWorkspace w;
   size_t off = 0;
-  size_t nk = (size_t)(n_isect > 0 ? n_isect : 1);
-  int nblocks = ceil_div((int64_t)nk, kRsTile);
-  w.keys_a = off; off += align_up(nk * 8, 256);
-  w.keys_b = off; off += align_up(nk * 8, 256);
-  w.vals_a = off; off += align_up(nk * 4, 256);
-  w.vals_b = off; off += align_up(nk * 4, 256);
-  w.hist = off; off += align_up((size_t)256 * nblocks * 4, 256);
-  w.scan = off; off += scan_workspace_bytes((int64_t)256 * nblocks);
+  size_t nk = (size_t)(n_isect > 0 ? n_isect : 1), ns = (size_t)(n_slots > 0 ? n_slots : 1);
+  size_t nmax = nk > ns ? nk : ns;
+  int nblocks = ceil_div((int64_t)nmax, kRsTile);
+  auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes, 256); return o; };
+  w.keys_a = take(nk * 4); w.keys_b = take(nk * 4); w.vals_a = take(nk * 4); w.vals_b = take(nk * 4);
+  w.s1k_a = take(ns * 4); w.s1k_b = take(ns * 4); w.s1v_a = take(ns * 4); w.s1v_b = take(ns * 4);
+  w.tiles_sorted = take(ns * 4); w.offs2 = take(ns * 8);
+  w.hist = take((size_t)256 * nblocks * 4);
+  size_t scan_n = (size_t)256 * nblocks;
+  w.scan = take(scan_workspace_bytes((int64_t)(scan_n > ns ? scan_n : ns)));
   w.total = off;
   return w;
 }
@@ -373,6 +425,17 @@ static int tile_bits_for(int n_tiles) {
   return bits;
 }
 
+// packs (tiles > 0) << kRankShift | tiles so that ONE scan yields both the record count and the id-ordered
+// rank of every emitting splat
+__global__ void __launch_bounds__(256) pack_counts_kernel(const int32_t* __restrict__ tiles, int64_t n,
+                                                          int64_t* __restrict__ packed) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int64_t t = tiles[i];
+  packed[i] = t > 0 ? (((int64_t)1 << kRankShift) | t) : 0;
+}
+__global__ void unpack_total_kernel(int64_t* total) { *total &= (((int64_t)1 << kRankShift) - 1); }
+
 int check_render_desc(const bds_render_desc* d);  // projection.cu
 
 }  // namespace bds
@@ -382,29 +445,40 @@ using namespace bds;
 extern "C" size_t bds_bin_count_workspace_bytes(int64_t n_elems) { return scan_workspace_bytes(n_elems) + 256; }
 
 extern "C" int bds_bin_count(const bds_render_desc* d, const int32_t* tiles_touched, int64_t* isect_offsets,
-                             int64_t* n_isect_dev, void* workspace, bds_stream_t stream) {
+                             int64_t* n_isect_dev, void* workspace, bds_stream_t stream_) {
   if (int rc = check_render_desc(d)) return rc;
   int64_t n = (int64_t)d->n_gauss * d->n_cams;
   BDS_REQUIRE(n_isect_dev, "bin_count: null n_isect pointer");
-  if (n > 0) BDS_REQUIRE(tiles_touched && isect_offsets && workspace, "bin_count: null pointer");
-  return exclusive_scan<int32_t, int64_t>(tiles_touched, isect_offsets, n, n_isect_dev, workspace,
-                                          static_cast<cudaStream_t>(stream));
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (n == 0) {
+    BDS_CHECK_CUDA(cudaMemsetAsync(n_isect_dev, 0, sizeof(int64_t), stream));
+    return 0;
+  }
+  BDS_REQUIRE(tiles_touched && isect_offsets && workspace, "bin_count: null pointer");
+  pack_counts_kernel<<<ceil_div(n, 256), 256, 0, stream>>>(tiles_touched, n, isect_offsets);
+  BDS_CHECK_LAUNCH();
+  if (int rc = exclusive_scan<int64_t, int64_t>(isect_offsets, isect_offsets, n, n_isect_dev, workspace, stream)) return rc;
+  unpack_total_kernel<<<1, 1, 0, stream>>>(n_isect_dev);
+  BDS_CHECK_LAUNCH();
+  return 0;
 }
 
 extern "C" size_t bds_bin_sort_workspace_bytes(const bds_render_desc* d, int64_t n_isect) {
-  (void)d;
-  return carve_sort(n_isect).total + 256;
+  int64_t ns = d ? (int64_t)d->n_gauss * d->n_cams : 1;  // upper bound of the visible splats
+  if (ns > n_isect && n_isect > 0) ns = n_isect;         // every slot emits at least one record
+  return carve_sort(n_isect, ns).total + 256;
 }
 
 extern "C" int bds_bin_sort(const bds_render_desc* d, int64_t n_isect, int32_t n_slots, const int32_t* radii,
-                            const int32_t* tiles_touched, const int64_t* isect_offsets,
-                            const float* splats, float* sorted_splats, int32_t* sorted_slots, int32_t* tile_offsets,
-                            void* workspace, bds_stream_t stream_) {
+                            const int32_t* tiles_touched, const int64_t* isect_offsets, const float* splats,
+                            float* sorted_splats, int32_t* sorted_slots, int32_t* tile_offsets, void* workspace,
+                            bds_stream_t stream_) {
   if (int rc = check_render_desc(d)) return rc;
   BDS_REQUIRE(n_isect >= 0 && n_isect < ((int64_t)1 << 31), "bin_sort: n_isect must fit int32 (got %lld)", (long long)n_isect);
   BDS_REQUIRE(tile_offsets, "bin_sort: null tile_offsets");
   if (n_isect > 0)
-    BDS_REQUIRE(radii && tiles_touched && isect_offsets && splats && workspace && n_slots > 0, "bin_sort: null pointer");
+    BDS_REQUIRE(radii && tiles_touched && isect_offsets && splats && workspace && n_slots > 0 && n_slots <= n_isect,
+                "bin_sort: null pointer or inconsistent n_slots");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const int tile_w = (d->width + kTile - 1) / kTile, tile_h = (d->height + kTile - 1) / kTile;
   const int n_tiles = (d->row_end - d->row_begin) * tile_w;
@@ -415,37 +489,42 @@ extern "C" int bds_bin_sort(const bds_render_desc* d, int64_t n_isect, int32_t n
   }
   BDS_REQUIRE(sorted_splats, "bin_sort: null sorted_splats");
   char* ws = static_cast<char*>(workspace);
-  SortWorkspace w = carve_sort(n_isect);
-  uint64_t* keys[2] = {reinterpret_cast<uint64_t*>(ws + w.keys_a), reinterpret_cast<uint64_t*>(ws + w.keys_b)};
+  int64_t ns_cap = (int64_t)d->n_gauss * d->n_cams;
+  if (ns_cap > n_isect) ns_cap = n_isect;
+  SortWorkspace w = carve_sort(n_isect, ns_cap);
+  uint32_t* keys[2] = {reinterpret_cast<uint32_t*>(ws + w.keys_a), reinterpret_cast<uint32_t*>(ws + w.keys_b)};
   uint32_t* vals[2] = {reinterpret_cast<uint32_t*>(ws + w.vals_a), reinterpret_cast<uint32_t*>(ws + w.vals_b)};
+  uint32_t* s1k[2] = {reinterpret_cast<uint32_t*>(ws + w.s1k_a), reinterpret_cast<uint32_t*>(ws + w.s1k_b)};
+  uint32_t* s1v[2] = {reinterpret_cast<uint32_t*>(ws + w.s1v_a), reinterpret_cast<uint32_t*>(ws + w.s1v_b)};
+  int32_t* tiles_sorted = reinterpret_cast<int32_t*>(ws + w.tiles_sorted);
+  int64_t* offs2 = reinterpret_cast<int64_t*>(ws + w.offs2);
   uint32_t* hist = reinterpret_cast<uint32_t*>(ws + w.hist);
   void* scan_ws = ws + w.scan;
 
+  // stage 1: visible splats by (depth bits, Gaussian id)
+  stage1_fill_kernel<<<ceil_div(n_slots, 256), 256, 0, stream>>>(splats, n_slots, isect_offsets, s1k[0], s1v[0]);
+  BDS_CHECK_LAUNCH();
+  int b1 = 0;
+  if (int rc = radix_sort_pairs<uint32_t>(s1k, s1v, n_slots, 32, hist, scan_ws, stream, &b1)) return rc;
+  // stage 2: emit in that order, stable sort on the band tile index
+  gather_tiles_kernel<<<ceil_div(n_slots, 256), 256, 0, stream>>>(splats, s1v[b1], n_slots, tiles_touched, tiles_sorted);
+  BDS_CHECK_LAUNCH();
+  if (int rc = exclusive_scan<int32_t, int64_t>(tiles_sorted, offs2, n_slots, nullptr, scan_ws, stream)) return rc;
   EmitParams ep;
-  ep.d = *d; ep.tile_w = tile_w; ep.tile_h = tile_h; ep.radii = radii; ep.tiles_touched = tiles_touched; ep.n_tiles = n_tiles; ep.n_slots = n_slots; ep.offsets = isect_offsets;
-  ep.splats = splats; ep.keys = keys[0]; ep.vals = vals[0];
+  ep.d = *d; ep.tile_w = tile_w; ep.tile_h = tile_h; ep.radii = radii; ep.tiles_sorted = tiles_sorted; ep.offsets = offs2;
+  ep.sorted_slots = s1v[b1]; ep.n_tiles = n_tiles; ep.n_slots = n_slots; ep.splats = splats; ep.keys = keys[0];
+  ep.vals = vals[0];
   emit_keys_kernel<<<ceil_div(n_slots, 256), 256, 0, stream>>>(ep);
   BDS_CHECK_LAUNCH();
-
-  const int nblocks = ceil_div(n_isect, kRsTile);
-  const int end_bit = 32 + tile_bits_for(n_tiles + 1);  // +1: the sentinel tile
-  int cur = 0;
-  for (int shift = 0; shift < end_bit; shift += 8) {
-    rs_hist_kernel<<<nblocks, kRsThreads, 0, stream>>>(keys[cur], n_isect, shift, nblocks, hist);
-    BDS_CHECK_LAUNCH();
-    if (int rc = exclusive_scan<uint32_t, uint32_t>(hist, hist, (int64_t)256 * nblocks, nullptr, scan_ws, stream)) return rc;
-    rs_scatter_kernel<<<nblocks, kRsThreads, 0, stream>>>(keys[cur], vals[cur], n_isect, shift, nblocks, hist,
-                                                          keys[cur ^ 1], vals[cur ^ 1]);
-    BDS_CHECK_LAUNCH();
-    cur ^= 1;
-  }
-  tile_offsets_kernel<<<ceil_div(n_isect, 256), 256, 0, stream>>>(keys[cur], n_isect, n_tiles, tile_offsets);
+  int b2 = 0;
+  if (int rc = radix_sort_pairs<uint32_t>(keys, vals, n_isect, tile_bits_for(n_tiles + 1), hist, scan_ws, stream, &b2)) return rc;
+  tile_offsets_kernel<<<ceil_div(n_isect, 256), 256, 0, stream>>>(keys[b2], n_isect, n_tiles, tile_offsets);
   BDS_CHECK_LAUNCH();
-  gather_records_kernel<<<ceil_div(n_isect * 3, 256), 256, 0, stream>>>(vals[cur], n_isect,
+  gather_records_kernel<<<ceil_div(n_isect * 3, 256), 256, 0, stream>>>(vals[b2], n_isect,
                                                                        reinterpret_cast<const float4*>(splats),
                                                                        reinterpret_cast<float4*>(sorted_splats));
   BDS_CHECK_LAUNCH();
   if (sorted_slots)
-    BDS_CHECK_CUDA(cudaMemcpyAsync(sorted_slots, vals[cur], (size_t)n_isect * 4, cudaMemcpyDeviceToDevice, stream));
+    BDS_CHECK_CUDA(cudaMemcpyAsync(sorted_slots, vals[b2], (size_t)n_isect * 4, cudaMemcpyDeviceToDevice, stream));
   return 0;
 }

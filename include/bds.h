@@ -134,10 +134,12 @@ int bds_project_fwd(const bds_render_desc* d, const float* means, const float* q
                     float* compensations, int32_t* tiles_touched, float* splats, int32_t splat_cap,
                     int32_t* slot_of, int32_t* counters, bds_stream_t stream);
 
-/* Binning: exclusive scan of tiles_touched -> isect offsets, emission of (tile|depth) keys,
- * stable LSD radix sort, per-tile start offsets, and the gather of packed records in sorted order.
+/* Binning: scan of tiles_touched, depth sort of the visible splats, emission of (tile, slot) records in
+ * (depth, id) order, stable radix sort on the tile, per-tile start offsets, gather of the packed records.
  * Two steps because the intersection count is data dependent:
- *   bds_bin_count   -> writes offsets [C*N] (exclusive scan) and total (device int64 at n_isect_dev)
+ *   bds_bin_count   -> isect_offsets [C*N] int64 = exclusive scan of a packed count: bits 40.. hold the
+ *                      id-ordered rank among splats with tiles_touched > 0, bits 0..39 the record prefix;
+ *                      n_isect_dev (device int64) = total number of records
  *   (caller reads n_isect, allocates)   bds_bin_sort -> sorted records + tile_offsets. */
 size_t bds_bin_count_workspace_bytes(int64_t n_elems);
 int bds_bin_count(const bds_render_desc* d, const int32_t* tiles_touched, int64_t* isect_offsets /*[C*N]*/,
