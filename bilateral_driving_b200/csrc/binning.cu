@@ -282,6 +282,7 @@ struct EmitParams {
   const uint32_t* sorted_slots;  // [n_slots] slots in (depth, id) order
   int n_tiles;
   int n_slots;
+  uint32_t perm_mul;             // multiplier coprime with n_slots
   const float* splats;
   uint32_t* keys;
   uint32_t* vals;
@@ -293,8 +294,12 @@ constexpr int kCoopTiles = 32;  // work-split threshold only (same value as proj
 __global__ void __launch_bounds__(256) emit_keys_kernel(EmitParams p) {
   const int N = p.d.n_gauss;
   const int lane = threadIdx.x & 31;
-  const int r = blockIdx.x * blockDim.x + threadIdx.x;
-  const bool active = r < p.n_slots;
+  // Depth order puts the largest (nearest) splats side by side; a multiplicative permutation of the
+  // thread -> rank map spreads them over the grid (output positions come from offsets[r], so the
+  // emitted order is unchanged).
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool active = t < p.n_slots;
+  const int r = active ? (int)(((uint64_t)t * p.perm_mul) % (uint64_t)p.n_slots) : 0;
   const int slot = active ? (int)p.sorted_slots[r] : 0;
   float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0, r2 = r0;
   TileRect tr = {0, 0, 0, 0};
@@ -514,6 +519,12 @@ extern "C" int bds_bin_sort(const bds_render_desc* d, int64_t n_isect, int32_t n
   ep.d = *d; ep.tile_w = tile_w; ep.tile_h = tile_h; ep.radii = radii; ep.tiles_sorted = tiles_sorted; ep.offsets = offs2;
   ep.sorted_slots = s1v[b1]; ep.n_tiles = n_tiles; ep.n_slots = n_slots; ep.splats = splats; ep.keys = keys[0];
   ep.vals = vals[0];
+  {
+    static const uint32_t primes[] = {2654435761u, 2246822519u, 3266489917u, 668265263u, 374761393u};
+    ep.perm_mul = 1;
+    for (uint32_t pr : primes)
+      if ((uint64_t)n_slots % pr != 0) { ep.perm_mul = pr; break; }  // prime not dividing n => bijection mod n
+  }
   emit_keys_kernel<<<ceil_div(n_slots, 256), 256, 0, stream>>>(ep);
   BDS_CHECK_LAUNCH();
   int b2 = 0;

@@ -50,39 +50,50 @@ BDS_HD void band_rows(const bds_render_desc& d, int tile_h, int c, int& ty0, int
 
 constexpr int kCoopTiles = 32;  // splats with more candidate tiles than this are enumerated by the whole warp
 
+// One thread per GAUSSIAN; the cameras of the band are walked in a loop so that the parameter loads,
+// the activations and the world covariance are paid once per Gaussian (a Gaussian is visible in ~1 of
+// the 6 rig cameras) and every lane of a warp has work.
 __global__ void __launch_bounds__(256) project_fwd_kernel(ProjParams p) {
   const int N = p.d.n_gauss;
   const int lane = threadIdx.x & 31;
-  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  bool in_range = idx < (int64_t)N * p.d.n_cams;
-  int c = in_range ? (int)(idx / N) : 0;
-  int n = in_range ? (int)(idx - (int64_t)c * N) : 0;
-  int n_tiles = 0, radius_i = 0;
-  // ---- phase 1: projection and candidate rectangle ------------------------------------------------
-  bool cand = false;
-  float mx = 0.f, my = 0.f, qa = 0.f, qb = 0.f, qc = 0.f, op = 0.f, sigma_cut = 0.f, depth = 0.f;
-  float mu[3] = {0.f, 0.f, 0.f};
-  TileRect tr = {0, 0, 0, 0};
-  CamIntr cam;
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool in_range = n < N;
+  float mu[3] = {0.f, 0.f, 0.f}, cov[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  float smax = 0.f, op_base = 0.f;
   if (in_range) {
+    mu[0] = p.means[3 * (size_t)n]; mu[1] = p.means[3 * (size_t)n + 1]; mu[2] = p.means[3 * (size_t)n + 2];
+    float q[4] = {p.quats[4 * (size_t)n], p.quats[4 * (size_t)n + 1], p.quats[4 * (size_t)n + 2], p.quats[4 * (size_t)n + 3]};
+    float s[3] = {p.scales[3 * (size_t)n], p.scales[3 * (size_t)n + 1], p.scales[3 * (size_t)n + 2]};
+    if (p.d.raw_params) { s[0] = __expf(s[0]); s[1] = __expf(s[1]); s[2] = __expf(s[2]); }
+    float Rq[9];
+    quat_to_rotmat(q, Rq);
+    covar_world(Rq, s, cov);
+    smax = fmaxf(s[0], fmaxf(s[1], s[2]));
+    op_base = p.opacities[n];
+    if (p.d.raw_params) op_base = sigmoidf(op_base);
+  }
+  for (int c = 0; c < p.d.n_cams; ++c) {
     int ty0, ty1;
     band_rows(p.d, p.tile_h, c, ty0, ty1);
-    if (ty1 > ty0) {
-      load_cam(p.viewmats, p.Ks, c, cam);
-      mu[0] = p.means[3 * (size_t)n]; mu[1] = p.means[3 * (size_t)n + 1]; mu[2] = p.means[3 * (size_t)n + 2];
-      float q[4] = {p.quats[4 * (size_t)n], p.quats[4 * (size_t)n + 1], p.quats[4 * (size_t)n + 2], p.quats[4 * (size_t)n + 3]};
-      float s[3] = {p.scales[3 * (size_t)n], p.scales[3 * (size_t)n + 1], p.scales[3 * (size_t)n + 2]};
-      if (p.d.raw_params) { s[0] = __expf(s[0]); s[1] = __expf(s[1]); s[2] = __expf(s[2]); }
+    if (ty1 <= ty0) continue;  // camera outside the band (uniform)
+    const int64_t idx = (int64_t)c * N + n;
+    int n_tiles = 0, radius_i = 0;
+    // ---- phase 1: projection and candidate rectangle ----------------------------------------------
+    bool cand = false;
+    float mx = 0.f, my = 0.f, qa = 0.f, qb = 0.f, qc = 0.f, op = 0.f, sigma_cut = 0.f, depth = 0.f;
+    TileRect tr = {0, 0, 0, 0};
+    CamIntr cam;
+    load_cam(p.viewmats, p.Ks, c, cam);
+    if (in_range) {
       Proj o;
-      if (project_gaussian(mu, q, s, cam, p.d.width, p.d.height, p.d.eps2d, p.d.near_plane, p.d.far_plane,
-                           p.d.radius_clip, o)) {
+      if (project_gaussian_cov(mu, cov, smax, cam, p.d.width, p.d.height, p.d.eps2d, p.d.near_plane, p.d.far_plane,
+                               p.d.radius_clip, o)) {
         radius_i = (int)o.radius;
         if (p.means2d) { p.means2d[2 * idx] = o.mx; p.means2d[2 * idx + 1] = o.my; }
         if (p.depths) p.depths[idx] = o.z;
         if (p.conics) { p.conics[3 * idx] = o.a; p.conics[3 * idx + 1] = o.b; p.conics[3 * idx + 2] = o.c; }
         if (p.compensations) p.compensations[idx] = o.comp;
-        op = p.opacities[n];
-        if (p.d.raw_params) op = sigmoidf(op);
+        op = op_base;
         if (p.d.antialiased) op *= o.comp;
         mx = o.mx; my = o.my; depth = o.z;
         qa = 0.5f * kLog2e * o.a; qb = kLog2e * o.b; qc = 0.5f * kLog2e * o.c;
@@ -93,96 +104,96 @@ __global__ void __launch_bounds__(256) project_fwd_kernel(ProjParams p) {
         }
       }
     }
-  }
-  // ---- phase 2: exact tile count; big rectangles are enumerated by the whole warp ----------------
-  const int ncand = cand ? (tr.x1 - tr.x0) * (tr.y1 - tr.y0) : 0;
-  if (cand && ncand <= kCoopTiles) {
-    for (int ty = tr.y0; ty < tr.y1; ++ty)
-      for (int tx = tr.x0; tx < tr.x1; ++tx)
-        n_tiles += tile_hit(mx, my, qa, qb, qc, sigma_cut, tx, ty, p.d.width, p.d.height) ? 1 : 0;
-  }
-  unsigned big = __ballot_sync(0xffffffffu, ncand > kCoopTiles);
-  while (big) {
-    const int src = __ffs(big) - 1;
-    big &= big - 1;
-    const int bx0 = __shfl_sync(0xffffffffu, tr.x0, src), bx1 = __shfl_sync(0xffffffffu, tr.x1, src);
-    const int by0 = __shfl_sync(0xffffffffu, tr.y0, src), by1 = __shfl_sync(0xffffffffu, tr.y1, src);
-    const float gx = __shfl_sync(0xffffffffu, mx, src), gy = __shfl_sync(0xffffffffu, my, src);
-    const float ga = __shfl_sync(0xffffffffu, qa, src), gb = __shfl_sync(0xffffffffu, qb, src);
-    const float gc = __shfl_sync(0xffffffffu, qc, src), gcut = __shfl_sync(0xffffffffu, sigma_cut, src);
-    const int w = bx1 - bx0, total = w * (by1 - by0);
-    int cnt = 0;
-    for (int base = 0; base < total; base += 32) {
-      int i = base + lane;
-      bool hit = false;
-      if (i < total) {
-        int ty = by0 + i / w, tx = bx0 + i - (i / w) * w;
-        hit = tile_hit(gx, gy, ga, gb, gc, gcut, tx, ty, p.d.width, p.d.height);
-      }
-      cnt += __popc(__ballot_sync(0xffffffffu, hit));
+    // ---- phase 2: exact tile count; big rectangles are enumerated by the whole warp --------------
+    const int ncand = cand ? (tr.x1 - tr.x0) * (tr.y1 - tr.y0) : 0;
+    if (cand && ncand <= kCoopTiles) {
+      for (int ty = tr.y0; ty < tr.y1; ++ty)
+        for (int tx = tr.x0; tx < tr.x1; ++tx)
+          n_tiles += tile_hit(mx, my, qa, qb, qc, sigma_cut, tx, ty, p.d.width, p.d.height) ? 1 : 0;
     }
-    if (lane == src) n_tiles = cnt;
-  }
-  // ---- phase 3: packed record (SH colour only for splats that reach some tile) ---------------------
-  const bool emit = n_tiles > 0;
-  float rec[12];
-  if (emit) {
-    rec[0] = mx; rec[1] = my; rec[2] = qa; rec[3] = qb; rec[4] = qc; rec[5] = op;
-    if (p.d.sh_degree >= 0) {
-      // view direction = mean - camera position, camera position = -R^T t  (vanilla.py:384-385)
-      float cp[3] = {-(cam.R[0] * cam.t[0] + cam.R[3] * cam.t[1] + cam.R[6] * cam.t[2]),
-                     -(cam.R[1] * cam.t[0] + cam.R[4] * cam.t[1] + cam.R[7] * cam.t[2]),
-                     -(cam.R[2] * cam.t[0] + cam.R[5] * cam.t[1] + cam.R[8] * cam.t[2])};
-      float dx = mu[0] - cp[0], dy = mu[1] - cp[1], dz = mu[2] - cp[2];
-      float inv = rsqrtf(dx * dx + dy * dy + dz * dz);
-      float b[16];
-      sh_basis(p.d.sh_degree, dx * inv, dy * inv, dz * inv, b);
-      int nb = (p.d.sh_degree + 1) * (p.d.sh_degree + 1);
-      if (nb > p.d.sh_K) nb = p.d.sh_K;
-      float col[3];
-#pragma unroll
-      for (int ch = 0; ch < 3; ++ch) col[ch] = b[0] * __ldg(p.fdc + 3 * (size_t)n + ch);
-      const float* fr = p.frest + (size_t)n * (p.d.sh_K - 1) * 3;
-      for (int k = 1; k < nb; ++k) {
-#pragma unroll
-        for (int ch = 0; ch < 3; ++ch) col[ch] = fmaf(b[k], __ldg(fr + (k - 1) * 3 + ch), col[ch]);
+    unsigned big = __ballot_sync(0xffffffffu, ncand > kCoopTiles);
+    while (big) {
+      const int src = __ffs(big) - 1;
+      big &= big - 1;
+      const int bx0 = __shfl_sync(0xffffffffu, tr.x0, src), bx1 = __shfl_sync(0xffffffffu, tr.x1, src);
+      const int by0 = __shfl_sync(0xffffffffu, tr.y0, src), by1 = __shfl_sync(0xffffffffu, tr.y1, src);
+      const float gx = __shfl_sync(0xffffffffu, mx, src), gy = __shfl_sync(0xffffffffu, my, src);
+      const float ga = __shfl_sync(0xffffffffu, qa, src), gb = __shfl_sync(0xffffffffu, qb, src);
+      const float gc = __shfl_sync(0xffffffffu, qc, src), gcut = __shfl_sync(0xffffffffu, sigma_cut, src);
+      const int w = bx1 - bx0, total = w * (by1 - by0);
+      int cnt = 0;
+      for (int base = 0; base < total; base += 32) {
+        int i = base + lane;
+        bool hit = false;
+        if (i < total) {
+          int ty = by0 + i / w, tx = bx0 + i - (i / w) * w;
+          hit = tile_hit(gx, gy, ga, gb, gc, gcut, tx, ty, p.d.width, p.d.height);
+        }
+        cnt += __popc(__ballot_sync(0xffffffffu, hit));
       }
-#pragma unroll
-      for (int ch = 0; ch < 3; ++ch) rec[6 + ch] = fminf(fmaxf(col[ch] + 0.5f, 0.f), 1.f);
-    } else {
-      const float* cp = p.colors + (p.colors_per_cam ? 3 * (size_t)idx : 3 * (size_t)n);
-      rec[6] = cp[0]; rec[7] = cp[1]; rec[8] = cp[2];
+      if (lane == src) n_tiles = cnt;
     }
-    rec[9] = depth;
-    rec[10] = __int_as_float((int)idx);
-    rec[11] = sigma_cut;
-  }
-  // warp-aggregated compaction: one atomic per warp
-  unsigned ballot = __ballot_sync(0xffffffffu, emit);
-  int slot = -1;
-  if (ballot) {
-    int leader = __ffs(ballot) - 1;
-    int base = 0;
-    if (lane == leader) base = atomicAdd(p.counters, __popc(ballot));
-    base = __shfl_sync(0xffffffffu, base, leader);
+    // ---- phase 3: packed record (SH colour only for splats that reach some tile) -------------------
+    const bool emit = n_tiles > 0;
+    float rec[12];
     if (emit) {
-      slot = base + __popc(ballot & ((1u << lane) - 1u));
-      if (slot >= p.splat_cap) {  // capacity overflow: flag, drop the record
-        p.counters[1] = 1;
-        slot = -1;
-        n_tiles = 0;
+      rec[0] = mx; rec[1] = my; rec[2] = qa; rec[3] = qb; rec[4] = qc; rec[5] = op;
+      if (p.d.sh_degree >= 0) {
+        // view direction = mean - camera position, camera position = -R^T t  (vanilla.py:384-385)
+        float cp[3] = {-(cam.R[0] * cam.t[0] + cam.R[3] * cam.t[1] + cam.R[6] * cam.t[2]),
+                       -(cam.R[1] * cam.t[0] + cam.R[4] * cam.t[1] + cam.R[7] * cam.t[2]),
+                       -(cam.R[2] * cam.t[0] + cam.R[5] * cam.t[1] + cam.R[8] * cam.t[2])};
+        float dx = mu[0] - cp[0], dy = mu[1] - cp[1], dz = mu[2] - cp[2];
+        float inv = rsqrtf(dx * dx + dy * dy + dz * dz);
+        float b[16];
+        sh_basis(p.d.sh_degree, dx * inv, dy * inv, dz * inv, b);
+        int nb = (p.d.sh_degree + 1) * (p.d.sh_degree + 1);
+        if (nb > p.d.sh_K) nb = p.d.sh_K;
+        float col[3];
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) col[ch] = b[0] * __ldg(p.fdc + 3 * (size_t)n + ch);
+        const float* fr = p.frest + (size_t)n * (p.d.sh_K - 1) * 3;
+        for (int k = 1; k < nb; ++k) {
+#pragma unroll
+          for (int ch = 0; ch < 3; ++ch) col[ch] = fmaf(b[k], __ldg(fr + (k - 1) * 3 + ch), col[ch]);
+        }
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) rec[6 + ch] = fminf(fmaxf(col[ch] + 0.5f, 0.f), 1.f);
+      } else {
+        const float* cp = p.colors + (p.colors_per_cam ? 3 * (size_t)idx : 3 * (size_t)n);
+        rec[6] = cp[0]; rec[7] = cp[1]; rec[8] = cp[2];
+      }
+      rec[9] = depth;
+      rec[10] = __int_as_float((int)idx);
+      rec[11] = sigma_cut;
+    }
+    // warp-aggregated compaction: one atomic per warp
+    unsigned ballot = __ballot_sync(0xffffffffu, emit);
+    int slot = -1;
+    if (ballot) {
+      int leader = __ffs(ballot) - 1;
+      int base = 0;
+      if (lane == leader) base = atomicAdd(p.counters, __popc(ballot));
+      base = __shfl_sync(0xffffffffu, base, leader);
+      if (emit) {
+        slot = base + __popc(ballot & ((1u << lane) - 1u));
+        if (slot >= p.splat_cap) {  // capacity overflow: flag, drop the record
+          p.counters[1] = 1;
+          slot = -1;
+          n_tiles = 0;
+        }
       }
     }
-  }
-  if (in_range) {
-    if (p.radii) p.radii[idx] = radius_i;
-    p.tiles_touched[idx] = n_tiles;
-    if (p.slot_of) p.slot_of[idx] = slot;
-    if (slot >= 0) {
-      float4* dst = reinterpret_cast<float4*>(p.splats + (size_t)slot * 12);
-      dst[0] = make_float4(rec[0], rec[1], rec[2], rec[3]);
-      dst[1] = make_float4(rec[4], rec[5], rec[6], rec[7]);
-      dst[2] = make_float4(rec[8], rec[9], rec[10], rec[11]);
+    if (in_range) {
+      if (p.radii) p.radii[idx] = radius_i;
+      p.tiles_touched[idx] = n_tiles;
+      if (p.slot_of) p.slot_of[idx] = slot;
+      if (slot >= 0) {
+        float4* dst = reinterpret_cast<float4*>(p.splats + (size_t)slot * 12);
+        dst[0] = make_float4(rec[0], rec[1], rec[2], rec[3]);
+        dst[1] = make_float4(rec[4], rec[5], rec[6], rec[7]);
+        dst[2] = make_float4(rec[8], rec[9], rec[10], rec[11]);
+      }
     }
   }
 }
@@ -396,7 +407,9 @@ extern "C" int bds_project_fwd(const bds_render_desc* d, const float* means, con
   p.fdc = features_dc; p.frest = features_rest; p.viewmats = viewmats; p.Ks = Ks; p.colors_per_cam = colors_per_cam;
   p.radii = radii; p.means2d = means2d; p.depths = depths; p.conics = conics; p.compensations = compensations;
   p.tiles_touched = tiles_touched; p.splats = splats; p.splat_cap = splat_cap; p.slot_of = slot_of; p.counters = counters;
-  project_fwd_kernel<<<ceil_div(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  // tiles_touched of cameras outside the band must read 0 for the scan: the caller's buffer may be fresh
+  BDS_CHECK_CUDA(cudaMemsetAsync(tiles_touched, 0, (size_t)total * sizeof(int32_t), static_cast<cudaStream_t>(stream)));
+  project_fwd_kernel<<<ceil_div(d->n_gauss, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
   BDS_CHECK_LAUNCH();
   return 0;
 }

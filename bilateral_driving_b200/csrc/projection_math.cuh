@@ -88,10 +88,11 @@ BDS_HD void covar_cam(const float R[9], const float S[6], float Sc[9]) {
     for (int j = 0; j < 3; ++j) Sc[i * 3 + j] = RS[i * 3] * R[j * 3] + RS[i * 3 + 1] * R[j * 3 + 1] + RS[i * 3 + 2] * R[j * 3 + 2];
 }
 
-// Returns false when culled (radius = 0).
-BDS_HD bool project_gaussian(const float mu[3], const float q[4], const float s[3], const CamIntr& cam, int width,
-                             int height, float eps2d, float near_plane, float far_plane, float radius_clip,
-                             Proj& o) {
+// Projection of one Gaussian whose world covariance (symmetric 6) is already known; smax = largest
+// scale.  Returns false when culled (radius = 0).
+BDS_HD bool project_gaussian_cov(const float mu[3], const float cov[6], float smax, const CamIntr& cam, int width,
+                                 int height, float eps2d, float near_plane, float far_plane, float radius_clip,
+                                 Proj& o) {
   o.radius = 0.f;
   o.x = cam.R[0] * mu[0] + cam.R[1] * mu[1] + cam.R[2] * mu[2] + cam.t[0];
   o.y = cam.R[3] * mu[0] + cam.R[4] * mu[1] + cam.R[5] * mu[2] + cam.t[1];
@@ -102,7 +103,6 @@ BDS_HD bool project_gaussian(const float mu[3], const float q[4], const float s[
     // outside any one camera): radius <= 3 sqrt(lambda_max) + 1 and lambda_max <= ||J||_F^2 smax^2 + 0.7
     // (trace bound incl. the eps2d blur and the 0.01 floor), so a splat whose mean is further than that
     // bound outside the image is culled by gsplat's own test as well.
-    float smax = fmaxf(s[0], fmaxf(s[1], s[2]));
     float lx = 1.3f * (0.5f * (float)width / cam.fx), ly = 1.3f * (0.5f * (float)height / cam.fy);
     float rzq = 1.0f / o.z;
     float jf2 = (cam.fx * cam.fx * (1.f + lx * lx) + cam.fy * cam.fy * (1.f + ly * ly)) * rzq * rzq;
@@ -110,9 +110,7 @@ BDS_HD bool project_gaussian(const float mu[3], const float q[4], const float s[
     float px = cam.fx * o.x * rzq + cam.cx, py = cam.fy * o.y * rzq + cam.cy;
     if (px + rb <= 0.f || px - rb >= (float)width || py + rb <= 0.f || py - rb >= (float)height) return false;
   }
-  float Rq[9], cov[6], Sc[9];
-  quat_to_rotmat(q, Rq);
-  covar_world(Rq, s, cov);
+  float Sc[9];
   covar_cam(cam.R, cov, Sc);
   float limx = 1.3f * (0.5f * (float)width / cam.fx), limy = 1.3f * (0.5f * (float)height / cam.fy);
   float rz = 1.0f / o.z, rz2 = rz * rz;
@@ -145,6 +143,17 @@ BDS_HD bool project_gaussian(const float mu[3], const float q[4], const float s[
     return false;
   o.radius = radius;
   return true;
+}
+
+// Returns false when culled (radius = 0).
+BDS_HD bool project_gaussian(const float mu[3], const float q[4], const float s[3], const CamIntr& cam, int width,
+                             int height, float eps2d, float near_plane, float far_plane, float radius_clip,
+                             Proj& o) {
+  float Rq[9], cov[6];
+  quat_to_rotmat(q, Rq);
+  covar_world(Rq, s, cov);
+  return project_gaussian_cov(mu, cov, fmaxf(s[0], fmaxf(s[1], s[2])), cam, width, height, eps2d, near_plane,
+                              far_plane, radius_clip, o);
 }
 
 // VJP.  Inputs: cotangents of means2d (vmx, vmy), depth (vz), conic (va, vb, vc) and (antialiased
