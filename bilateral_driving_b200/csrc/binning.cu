@@ -288,10 +288,9 @@ struct EmitParams {
   uint32_t* vals;
 };
 
-constexpr int kCoopTiles = 32;  // work-split threshold only (same value as projection.cu); not a result
-
 // one thread per splat in (depth, id) order: emits (band tile, slot) for every tile it reaches
 __global__ void __launch_bounds__(256) emit_keys_kernel(EmitParams p) {
+  __shared__ int s_run[8][32];
   const int N = p.d.n_gauss;
   const int lane = threadIdx.x & 31;
   // Depth order puts the largest (nearest) splats side by side; a multiplicative permutation of the
@@ -317,51 +316,51 @@ __global__ void __launch_bounds__(256) emit_keys_kernel(EmitParams p) {
     o = p.offsets[r];
     o_end = o + p.tiles_sorted[r];
   }
-  const int ncand = active ? (tr.x1 - tr.x0) * (tr.y1 - tr.y0) : 0;
-  // The o_end guard and the sentinel padding (a key that sorts behind every real tile) only make a
-  // count / emission disagreement memory-safe should a toolchain ever break the shared-body contract.
-  if (active && ncand <= kCoopTiles) {
-    for (int ty = tr.y0; ty < tr.y1; ++ty) {
-      for (int tx = tr.x0; tx < tr.x1; ++tx) {
-        if (tile_hit(r0.x, r0.y, r0.z, r0.w, r1.x, r2.w, tx, ty, p.d.width, p.d.height) && o < o_end) {
-          p.keys[o] = (uint32_t)((c * p.tile_h + ty - p.d.row_begin) * p.tile_w + tx);
-          p.vals[o] = (uint32_t)slot;
-          ++o;
-        }
-      }
-    }
-  }
-  unsigned big = __ballot_sync(0xffffffffu, ncand > kCoopTiles);
-  while (big) {
-    const int src = __ffs(big) - 1;
-    big &= big - 1;
-    const int bx0 = __shfl_sync(0xffffffffu, tr.x0, src), bx1 = __shfl_sync(0xffffffffu, tr.x1, src);
-    const int by0 = __shfl_sync(0xffffffffu, tr.y0, src), by1 = __shfl_sync(0xffffffffu, tr.y1, src);
-    const float gx = __shfl_sync(0xffffffffu, r0.x, src), gy = __shfl_sync(0xffffffffu, r0.y, src);
-    const float ga = __shfl_sync(0xffffffffu, r0.z, src), gb = __shfl_sync(0xffffffffu, r0.w, src);
-    const float gc = __shfl_sync(0xffffffffu, r1.x, src), gcut = __shfl_sync(0xffffffffu, r2.w, src);
-    const int gcam = __shfl_sync(0xffffffffu, c, src), gslot = __shfl_sync(0xffffffffu, slot, src);
-    long long go = __shfl_sync(0xffffffffu, o, src);
-    const long long gend = __shfl_sync(0xffffffffu, o_end, src);
-    const int w = bx1 - bx0, total = w * (by1 - by0);
+  // Same flat warp-cooperative enumeration as the counting pass.  The o_end guard and the sentinel
+  // padding (a key that sorts behind every real tile) only make a count / emission disagreement
+  // memory-safe should a toolchain ever break the shared-body contract.
+  {
+    const int ncand = active ? (tr.x1 - tr.x0) * (tr.y1 - tr.y0) : 0;
+    const int incl = warp_inclusive_scan_i32(ncand);
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    const int excl = incl - ncand;
+    const int rw = tr.x1 - tr.x0;
+    int* run = s_run[threadIdx.x >> 5];
+    run[lane] = 0;
+    __syncwarp();
     for (int base = 0; base < total; base += 32) {
-      int i = base + lane;
+      const int wi = min(base + lane, total - 1);
+      const int owner = warp_find_owner(excl, wi);
+      const int local = wi - __shfl_sync(0xffffffffu, excl, owner);
+      const int ow = __shfl_sync(0xffffffffu, rw, owner);
+      const int ox0 = __shfl_sync(0xffffffffu, tr.x0, owner), oy0 = __shfl_sync(0xffffffffu, tr.y0, owner);
+      const float gx = __shfl_sync(0xffffffffu, r0.x, owner), gy = __shfl_sync(0xffffffffu, r0.y, owner);
+      const float ga = __shfl_sync(0xffffffffu, r0.z, owner), gb = __shfl_sync(0xffffffffu, r0.w, owner);
+      const float gc = __shfl_sync(0xffffffffu, r1.x, owner), gcut = __shfl_sync(0xffffffffu, r2.w, owner);
+      const int gcam = __shfl_sync(0xffffffffu, c, owner), gslot = __shfl_sync(0xffffffffu, slot, owner);
+      const long long go = __shfl_sync(0xffffffffu, o, owner), gend = __shfl_sync(0xffffffffu, o_end, owner);
       bool hit = false;
       int tx = 0, ty = 0;
-      if (i < total) {
-        ty = by0 + i / w;
-        tx = bx0 + i - (i / w) * w;
+      if (base + lane < total) {
+        const int ry = local / ow;
+        tx = ox0 + local - ry * ow;
+        ty = oy0 + ry;
         hit = tile_hit(gx, gy, ga, gb, gc, gcut, tx, ty, p.d.width, p.d.height);
       }
-      unsigned hm = __ballot_sync(0xffffffffu, hit);
-      long long pos = go + __popc(hm & ((1u << lane) - 1u));
+      const unsigned hm = __ballot_sync(0xffffffffu, hit);
+      const unsigned grp = __match_any_sync(0xffffffffu, owner);
+      const int before = run[owner];
+      __syncwarp();
+      const long long pos = go + before + __popc(hm & grp & ((1u << lane) - 1u));
       if (hit && pos < gend) {
         p.keys[pos] = (uint32_t)((gcam * p.tile_h + ty - p.d.row_begin) * p.tile_w + tx);
         p.vals[pos] = (uint32_t)gslot;
       }
-      go += __popc(hm);
+      if (lane == __ffs(grp) - 1) run[owner] = before + __popc(hm & grp);
+      __syncwarp();
     }
-    if (lane == src) o = go < o_end ? go : o_end;
+    o += run[lane];
+    if (o > o_end) o = o_end;
   }
   for (; o < o_end; ++o) {
     p.keys[o] = (uint32_t)p.n_tiles;

@@ -48,12 +48,11 @@ BDS_HD void band_rows(const bds_render_desc& d, int tile_h, int c, int& ty0, int
   ty1 = hi - g0;
 }
 
-constexpr int kCoopTiles = 32;  // splats with more candidate tiles than this are enumerated by the whole warp
-
 // One thread per GAUSSIAN; the cameras of the band are walked in a loop so that the parameter loads,
 // the activations and the world covariance are paid once per Gaussian (a Gaussian is visible in ~1 of
 // the 6 rig cameras) and every lane of a warp has work.
 __global__ void __launch_bounds__(256) project_fwd_kernel(ProjParams p) {
+  __shared__ int s_run[8][32];
   const int N = p.d.n_gauss;
   const int lane = threadIdx.x & 31;
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
@@ -104,34 +103,38 @@ __global__ void __launch_bounds__(256) project_fwd_kernel(ProjParams p) {
         }
       }
     }
-    // ---- phase 2: exact tile count; big rectangles are enumerated by the whole warp --------------
-    const int ncand = cand ? (tr.x1 - tr.x0) * (tr.y1 - tr.y0) : 0;
-    if (cand && ncand <= kCoopTiles) {
-      for (int ty = tr.y0; ty < tr.y1; ++ty)
-        for (int tx = tr.x0; tx < tr.x1; ++tx)
-          n_tiles += tile_hit(mx, my, qa, qb, qc, sigma_cut, tx, ty, p.d.width, p.d.height) ? 1 : 0;
-    }
-    unsigned big = __ballot_sync(0xffffffffu, ncand > kCoopTiles);
-    while (big) {
-      const int src = __ffs(big) - 1;
-      big &= big - 1;
-      const int bx0 = __shfl_sync(0xffffffffu, tr.x0, src), bx1 = __shfl_sync(0xffffffffu, tr.x1, src);
-      const int by0 = __shfl_sync(0xffffffffu, tr.y0, src), by1 = __shfl_sync(0xffffffffu, tr.y1, src);
-      const float gx = __shfl_sync(0xffffffffu, mx, src), gy = __shfl_sync(0xffffffffu, my, src);
-      const float ga = __shfl_sync(0xffffffffu, qa, src), gb = __shfl_sync(0xffffffffu, qb, src);
-      const float gc = __shfl_sync(0xffffffffu, qc, src), gcut = __shfl_sync(0xffffffffu, sigma_cut, src);
-      const int w = bx1 - bx0, total = w * (by1 - by0);
-      int cnt = 0;
+    // ---- phase 2: exact tile count.  The candidates of the warp's splats form one flat list that the
+    // 32 lanes test 32 at a time (few lanes are visible in any one camera, so per-lane loops would idle).
+    {
+      const int ncand = cand ? (tr.x1 - tr.x0) * (tr.y1 - tr.y0) : 0;
+      const int incl = warp_inclusive_scan_i32(ncand);
+      const int total = __shfl_sync(0xffffffffu, incl, 31);
+      const int excl = incl - ncand;
+      const int rw = tr.x1 - tr.x0;
+      int* run = s_run[threadIdx.x >> 5];
+      run[lane] = 0;
+      __syncwarp();
       for (int base = 0; base < total; base += 32) {
-        int i = base + lane;
+        const int wi = min(base + lane, total - 1);
+        const int owner = warp_find_owner(excl, wi);
+        const int local = wi - __shfl_sync(0xffffffffu, excl, owner);
+        const int ow = __shfl_sync(0xffffffffu, rw, owner);
+        const int ox0 = __shfl_sync(0xffffffffu, tr.x0, owner), oy0 = __shfl_sync(0xffffffffu, tr.y0, owner);
+        const float gx = __shfl_sync(0xffffffffu, mx, owner), gy = __shfl_sync(0xffffffffu, my, owner);
+        const float ga = __shfl_sync(0xffffffffu, qa, owner), gb = __shfl_sync(0xffffffffu, qb, owner);
+        const float gc = __shfl_sync(0xffffffffu, qc, owner), gcut = __shfl_sync(0xffffffffu, sigma_cut, owner);
         bool hit = false;
-        if (i < total) {
-          int ty = by0 + i / w, tx = bx0 + i - (i / w) * w;
-          hit = tile_hit(gx, gy, ga, gb, gc, gcut, tx, ty, p.d.width, p.d.height);
+        if (base + lane < total) {
+          const int ry = local / ow;
+          hit = tile_hit(gx, gy, ga, gb, gc, gcut, ox0 + local - ry * ow, oy0 + ry, p.d.width, p.d.height);
         }
-        cnt += __popc(__ballot_sync(0xffffffffu, hit));
+        const unsigned hm = __ballot_sync(0xffffffffu, hit);
+        const unsigned grp = __match_any_sync(0xffffffffu, owner);
+        if (lane == __ffs(grp) - 1) run[owner] += __popc(hm & grp);  // one leader per owner: no atomics
+        __syncwarp();
       }
-      if (lane == src) n_tiles = cnt;
+      n_tiles = run[lane];
+      __syncwarp();
     }
     // ---- phase 3: packed record (SH colour only for splats that reach some tile) -------------------
     const bool emit = n_tiles > 0;

@@ -376,4 +376,30 @@ TileRect candidate_rect(float mx, float my, float radius, float qa, float qb, fl
   return r;
 }
 
+
+#ifdef __CUDACC__
+// Flat warp-cooperative enumeration of candidate tiles: lane j owns ncand_j candidates; work item w of the
+// concatenated list belongs to the largest lane whose exclusive prefix is <= w (zero-count lanes share
+// their successor's prefix, so they are never picked for w below the total).
+BDS_D int warp_inclusive_scan_i32(int v) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int t = __shfl_up_sync(0xffffffffu, v, o);
+    if (lane >= o) v += t;
+  }
+  return v;
+}
+BDS_D int warp_find_owner(int excl, int w) {
+  int owner = 0;
+#pragma unroll
+  for (int step = 16; step > 0; step >>= 1) {
+    const int cl = owner + step;
+    const int e = __shfl_sync(0xffffffffu, excl, cl & 31);
+    if (cl < 32 && e <= w) owner = cl;
+  }
+  return owner;
+}
+#endif
+
 }  // namespace bds
