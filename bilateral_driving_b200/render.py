@@ -404,18 +404,23 @@ def render_fused(params: Dict[str, torch.Tensor], viewmats, Ks, width: int, heig
                  grid_slots: Optional[Sequence[Sequence[torch.Tensor]]] = None, bil_sizes=(), sh_degree: int = 3,
                  near_plane: float = 0.1, far_plane: float = 1e10, radius_clip: float = 0.0, absgrad: bool = True,
                  row_begin: int = 0, row_end: int = -1, activated: bool = False, dense_info: bool = False,
-                 antialiased: bool = False):
+                 antialiased: bool = False, guidance_factor=None):
     """One fused pass of the hot path for C cameras.
 
     ``params``: ``_means [N,3], _scales (log) [N,3], _quats [N,4], _opacities (logit) [N] or [N,1],
     _features_dc [N,3], _features_rest [N,K-1,3]`` (``activated=True``: scales/opacities already
     activated and ``_rgbs [N,3]`` given instead of SH features).
-    ``grid_slots[c][l]`` = camera c's grid slot ``[12,L,GY,GX]`` of level l (mode 2), or None for
-    mode 1 (reference glue only; run the low-res-guidance bilateral afterwards).
+    ``grid_slots[c][l]`` = camera c's grid slot ``[12,L,GY,GX]`` of level l, or None (reference glue only).
+    ``guidance_factor=None``: full-resolution guidance, the bilateral chain runs INSIDE the composite kernel
+    (epilogue mode 2).  ``guidance_factor=[4,4,2]`` (the reference's default, modules.py:505): the composite
+    kernel stops after the glue (mode 1) and the low-resolution-guidance kernels of ``bilateral.py`` finish the
+    chain per camera (the low-res guidance of a pixel needs neighbours outside its tile).  Requires whole
+    cameras in the band.
     Returns dict(rgb, rgb_gaussians, depth, opacity [band pixels ...], radii, info).
     """
     Cn = viewmats.shape[0]
-    mode = 2 if grid_slots is not None else 1
+    lowres = grid_slots is not None and guidance_factor is not None
+    mode = 2 if (grid_slots is not None and not lowres) else 1
     cfg = RenderCfg(width=width, height=height, near_plane=near_plane, far_plane=far_plane, radius_clip=radius_clip,
                     antialiased=antialiased, row_begin=row_begin, row_end=row_end, raw_params=not activated,
                     sh_degree=-1 if activated else sh_degree, mode=mode, channels=4, expected_depth=True,
@@ -435,6 +440,15 @@ def render_fused(params: Dict[str, torch.Tensor], viewmats, Ks, width: int, heig
     out_rgb, out_rgbg, out_depth, out_alpha, means2d, radii, holder = out
     r0, r1 = band_pixel_rows(cfg, Cn)
     rows = r1 - r0
+    if lowres:
+        from .bilateral import multiscale_bilateral
+
+        if r0 % height or r1 % height:
+            raise NotImplementedError("low-resolution guidance needs whole cameras in the band (no halo exchange built)")
+        pre = out_rgb.view(rows // height, height, width, 3)
+        c0 = r0 // height
+        out_rgb = torch.cat([multiscale_bilateral(pre[i], grid_slots[c0 + i], bil_sizes, guidance_factor)
+                             for i in range(pre.shape[0])]).reshape(-1, 3)
     return dict(rgb=out_rgb.view(rows, width, 3), rgb_gaussians=out_rgbg.view(rows, width, 3),
                 depth=out_depth.view(rows, width, 1), opacity=out_alpha.view(rows, width, 1), radii=radii,
                 means2d=means2d, info=holder, pixel_rows=(r0, r1))
@@ -445,7 +459,7 @@ class _PhotoLossFn(torch.autograd.Function):
     writes the cotangents (the benchmark step's loss)."""
 
     @staticmethod
-    def forward(ctx, rgb, gt, depth, alpha, lambda_d, lambda_a, count):
+    def forward(ctx, rgb, gt, depth, alpha, lambda_d, lambda_a, count, unit_cotangent):
         require_cuda(rgb, gt, depth, alpha)
         rgb_c, gt_c = rgb.contiguous(), gt.contiguous()
         depth_c = None if depth is None else depth.contiguous()
@@ -459,16 +473,23 @@ class _PhotoLossFn(torch.autograd.Function):
                                    C.c_float(lambda_a), C.c_float(1.0 / count), ptr(loss), ptr(v_rgb), ptr(v_d), ptr(v_a),
                                    stream_ptr()), "bds_loss_fwd_bwd")
         ctx.save_for_backward(v_rgb, v_d, v_a)
+        ctx.unit = unit_cotangent
         return loss
 
     @staticmethod
     def backward(ctx, v_loss):
         v_rgb, v_d, v_a = ctx.saved_tensors
+        if ctx.unit:  # the loss enters the objective with weight 1: the stored cotangents are final
+            return v_rgb, None, v_d, v_a, None, None, None, None
         s = v_loss
-        return v_rgb * s, None, (None if v_d is None else v_d * s), (None if v_a is None else v_a * s), None, None, None
+        return v_rgb * s, None, (None if v_d is None else v_d * s), (None if v_a is None else v_a * s), None, None, None, None
 
 
-def photometric_loss(rgb, gt, depth=None, alpha=None, lambda_d=0.0, lambda_a=0.0, count=None):
-    """``count`` = number of pixels of the WHOLE job (so that band-sharded ranks sum to the global mean)."""
+def photometric_loss(rgb, gt, depth=None, alpha=None, lambda_d=0.0, lambda_a=0.0, count=None, unit_cotangent=False):
+    """``count`` = number of pixels of the WHOLE job (so that band-sharded ranks sum to the global mean).
+    ``unit_cotangent=True`` promises that the returned loss is added to the objective with weight 1 (scale it
+    through the lambdas instead); the backward then returns the cotangents the kernel already wrote instead of
+    re-scaling three full images."""
     n = rgb.numel() // 3
-    return _PhotoLossFn.apply(rgb, gt, depth, alpha, float(lambda_d), float(lambda_a), float(count or n))
+    return _PhotoLossFn.apply(rgb, gt, depth, alpha, float(lambda_d), float(lambda_a), float(count or n),
+                              bool(unit_cotangent))

@@ -135,6 +135,38 @@ def test_render_fused_vs_oracle(with_bilateral):
             assert _rel(a.grad.cpu(), b.grad.float()) < 1e-3
 
 
+def test_render_fused_lowres_guidance_vs_oracle():
+    """Reference default guidance_factor=[4,4,2]: composite mode 1 + stand-alone low-res bilateral kernels."""
+    from bilateral_driving_b200.render import render_fused
+    from oracle.path_ref import render_path
+
+    p, vm, Ks, W, H, grids, sky = _fused_inputs()
+    Cn = vm.shape[0]
+    gf = (4, 4, 2)
+    o_p = {k: v.double().requires_grad_(True) for k, v in p.items()}
+    o_g = [g.double().requires_grad_(True) for g in grids]
+    o = render_path(o_p, vm.double(), Ks.double(), W, H, sky=sky.double(), grid_slots=[[g[c] for g in o_g] for c in range(Cn)],
+                    guidance_factor=gf)
+    keep = (~o["ambiguous"])[..., None]
+    gen = torch.Generator(); gen.manual_seed(9)
+    G = torch.randn(o["rgb"].shape, generator=gen, dtype=torch.float64) * keep
+    (o["rgb"] * G).sum().backward()
+    c_p = {k: v.cuda().requires_grad_(True) for k, v in p.items()}
+    c_g = [g.cuda().requires_grad_(True) for g in grids]
+    out = render_fused(c_p, vm.cuda(), Ks.cuda(), W, H, sky=sky.cuda().view(Cn * H, W, 3),
+                       grid_slots=[[g[c] for g in c_g] for c in range(Cn)], bil_sizes=SIZES, near_plane=0.1,
+                       guidance_factor=gf)
+    ours = out["rgb"].view(Cn, H, W, 3)
+    # non-integer resampling ratios (56/4, 88/4 are integer; 56/2, 88/2 too) -> 1e-5 applies
+    assert ((ours - o["rgb"].float().cuda()).abs() * keep.cuda()).max() < 2e-5
+    (ours * G.float().cuda()).sum().backward()
+    for k in c_p:
+        r = _rel(c_p[k].grad.cpu(), o_p[k].grad.float())
+        assert r < 2e-3, (k, r)
+    for a, b in zip(c_g, o_g):
+        assert _rel(a.grad.cpu(), b.grad.float()) < 1e-3
+
+
 def test_band_split_equals_full():
     """Tile-row bands (multi-GPU sharding unit) reproduce the full render bit for bit and
     their gradients add up to the full gradient."""
