@@ -7,12 +7,13 @@
 //   repack_grid_kernel       [12,L,GY,GX] -> [L,GY,GX,12]                       (tiny)
 //   lowres_slice_fwd_kernel  per low-res pixel: bilinear-down guidance -> luma -> trilerp -> A_low
 //   apply_fwd_kernel         per pixel: A_l = up(A_low) or direct trilerp; x <- A_l x
-//   apply_bwd_kernel         per pixel: recompute chain; g_l; vA_l -> v_A_low (transposed up-sample)
-//                            or direct trilerp scatter (+ guidance gradient)
-//   lowres_slice_bwd_kernel  per low-res pixel: v_A_low -> v_grid, guidance gradient -> transposed
-//                            down-sample into v_rgb_in
+//   apply_bwd_tiled_kernel   per 16x16 tile: recompute chain; g_l; vA_l -> v_A_low by a shared-memory
+//                            gather over the tile's low-res footprint, or (full-res level) the
+//                            block-cooperative grid-node accumulation + guidance gradient
+//   lowres_slice_bwd_tiled_kernel  per 16x16 low-res tile: v_A_low -> v_grid (block-cooperative),
+//                            guidance gradient -> transposed down-sample into v_rgb_in
 //   unpack_add_grid_kernel   v_grid_cl [L,GY,GX,12] += into the parameter-layout gradient slot
-#include "bilateral_math.cuh"
+#include "bilateral_accum.cuh"
 
 namespace bds {
 
@@ -104,61 +105,123 @@ __global__ void __launch_bounds__(256) apply_fwd_kernel(const float* __restrict_
   rgb_out[(size_t)idx * 3 + 2] = b;
 }
 
-__global__ void __launch_bounds__(256) apply_bwd_kernel(const float* __restrict__ rgb_in,
-                                                        const float* __restrict__ v_rgb_out,
-                                                        float* __restrict__ v_rgb_in, BilChain ch) {
-  int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= ch.H * ch.W) return;
-  int i = idx / ch.W, j = idx - i * ch.W;
-  float r0 = rgb_in[(size_t)idx * 3], g0 = rgb_in[(size_t)idx * 3 + 1], b0 = rgb_in[(size_t)idx * 3 + 2];
-  float lum = luma_of(r0, g0, b0);
-  float A[BDS_MAX_LEVELS][12];
+// ---------------------------------------------------------------------------------------------
+// Tiled backward (16x16 pixel tiles, 256 threads): no per-pixel global atomics.
+//   apply_bwd_tiled_kernel        full-res tile: chain backward per pixel; for a low-res level the 12
+//                                 cotangents of the tile are staged in shared memory and every low-res
+//                                 pixel of the tile's footprint GATHERS its transposed-bilinear sum
+//                                 (one global reduction per (low-res pixel, channel) per tile instead of
+//                                 48 per pixel); full-res levels use level_grad_accumulate.
+//   lowres_slice_bwd_tiled_kernel low-res tile: grid-node gradients through level_grad_accumulate,
+//                                 guidance gradient through the transposed down-sample (12 reductions
+//                                 per low-res pixel).
+// ---------------------------------------------------------------------------------------------
+constexpr int kMaxFoot = 18;  // low-res rows/cols a 16-pixel tile edge can touch (factor >= 2 -> <= 10)
+
+__global__ void __launch_bounds__(256) apply_bwd_tiled_kernel(const float* __restrict__ rgb_in,
+                                                              const float* __restrict__ v_rgb_out,
+                                                              float* __restrict__ v_rgb_in, BilChain ch) {
+  __shared__ __align__(16) float smem[kBwdSmemBil / sizeof(float)];
+  __shared__ float wy_tab[kMaxFoot][16], wx_tab[kMaxFoot][16];
+  __shared__ int foot[4];  // qy0, nly, qx0, nlx
+  const int tiles_x = (ch.W + 15) / 16;
+  const int tile_x0 = (blockIdx.x % tiles_x) * 16, tile_y0 = (blockIdx.x / tiles_x) * 16;
+  const int lx = threadIdx.x & 15, ly = threadIdx.x >> 4;
+  const int j = tile_x0 + lx, i = tile_y0 + ly;
+  const bool inside = j < ch.W && i < ch.H;
+  const int jc = min(j, ch.W - 1), ic = min(i, ch.H - 1);
+  const size_t idx = (size_t)ic * ch.W + jc;
+  float r0 = 0.f, g0 = 0.f, b0 = 0.f, gr = 0.f, gg = 0.f, gb = 0.f;
+  if (inside) {
+    r0 = rgb_in[idx * 3]; g0 = rgb_in[idx * 3 + 1]; b0 = rgb_in[idx * 3 + 2];
+    gr = v_rgb_out[idx * 3]; gg = v_rgb_out[idx * 3 + 1]; gb = v_rgb_out[idx * 3 + 2];
+  }
+  const float lum = luma_of(r0, g0, b0);
   float xs[BDS_MAX_LEVELS][3];
-  float r = r0, g = g0, b = b0;
+  {
+    float r = r0, g = g0, b = b0;
 #pragma unroll
-  for (int l = 0; l < BDS_MAX_LEVELS; ++l) {
-    if (l < ch.n_levels) {
-      xs[l][0] = r; xs[l][1] = g; xs[l][2] = b;
-      level_affine_fwd(ch.lv[l], ch.H, ch.W, i, j, lum, A[l]);
-      affine_apply(A[l], r, g, b);
+    for (int l = 0; l < BDS_MAX_LEVELS; ++l) {
+      if (l < ch.n_levels) {
+        xs[l][0] = r; xs[l][1] = g; xs[l][2] = b;
+        float A[12];
+        level_affine_fwd(ch.lv[l], ch.H, ch.W, ic, jc, lum, A);
+        affine_apply(A, r, g, b);
+      }
     }
   }
-  float gr = v_rgb_out[(size_t)idx * 3], gg = v_rgb_out[(size_t)idx * 3 + 1], gb = v_rgb_out[(size_t)idx * 3 + 2];
   float v_lum = 0.f;
 #pragma unroll
   for (int l = BDS_MAX_LEVELS - 1; l >= 0; --l) {
     if (l < ch.n_levels) {
       const BilLevel& lv = ch.lv[l];
-      float vA[12];
-      if (lv.v_affine) {
-        load12(lv.v_affine + (size_t)idx * 12, vA);
+      float A[12], vA[12];
+      level_affine_fwd(lv, ch.H, ch.W, ic, jc, lum, A);
+      if (lv.v_affine && inside) {
+        load12(lv.v_affine + idx * 12, vA);
       } else {
 #pragma unroll
         for (int k = 0; k < 12; ++k) vA[k] = 0.f;
       }
       float nr, ng, nb;
-      affine_apply_bwd(A[l], xs[l][0], xs[l][1], xs[l][2], gr, gg, gb, vA, nr, ng, nb);
+      affine_apply_bwd(A, xs[l][0], xs[l][1], xs[l][2], gr, gg, gb, vA, nr, ng, nb);
       gr = nr; gg = ng; gb = nb;
       if (lv.factor > 1) {
-        // transposed bilinear up-sample: 4 taps x 12 channels
-        LinTap ty = lin_src(i, lv.Hd, ch.H), tx = lin_src(j, lv.Wd, ch.W);
-        float w0 = 1.f - tx.t, w1 = tx.t, h0 = 1.f - ty.t, h1 = ty.t;
-        float* p00 = lv.v_a_low + ((size_t)ty.i0 * lv.Wd + tx.i0) * 12;
-        float* p01 = lv.v_a_low + ((size_t)ty.i0 * lv.Wd + tx.i1) * 12;
-        float* p10 = lv.v_a_low + ((size_t)ty.i1 * lv.Wd + tx.i0) * 12;
-        float* p11 = lv.v_a_low + ((size_t)ty.i1 * lv.Wd + tx.i1) * 12;
-#pragma unroll
-        for (int k = 0; k < 12; ++k) {
-          red_add(p00 + k, h0 * w0 * vA[k]);
-          red_add(p01 + k, h0 * w1 * vA[k]);
-          red_add(p10 + k, h1 * w0 * vA[k]);
-          red_add(p11 + k, h1 * w1 * vA[k]);
+        // ---- transposed bilinear up-sample as a gather over the tile's low-res footprint
+        float* sva = smem;  // [256][12]
+        {
+          float4* sp = reinterpret_cast<float4*>(sva + threadIdx.x * 12);
+          const float m = inside ? 1.f : 0.f;
+          sp[0] = make_float4(vA[0] * m, vA[1] * m, vA[2] * m, vA[3] * m);
+          sp[1] = make_float4(vA[4] * m, vA[5] * m, vA[6] * m, vA[7] * m);
+          sp[2] = make_float4(vA[8] * m, vA[9] * m, vA[10] * m, vA[11] * m);
         }
+        if (threadIdx.x == 0) {
+          LinTap a = lin_src(tile_y0, lv.Hd, ch.H), b = lin_src(min(tile_y0 + 15, ch.H - 1), lv.Hd, ch.H);
+          LinTap c = lin_src(tile_x0, lv.Wd, ch.W), d = lin_src(min(tile_x0 + 15, ch.W - 1), lv.Wd, ch.W);
+          foot[0] = a.i0; foot[1] = min(b.i1 - a.i0 + 1, kMaxFoot);
+          foot[2] = c.i0; foot[3] = min(d.i1 - c.i0 + 1, kMaxFoot);
+        }
+        __syncthreads();
+        const int qy0 = foot[0], nly = foot[1], qx0 = foot[2], nlx = foot[3];
+        // weight tables: contribution of tile row/col t onto low-res row/col q
+        for (int e = threadIdx.x; e < kMaxFoot * 16; e += 256) {
+          const int q = e >> 4, t = e & 15;
+          float wy = 0.f, wx = 0.f;
+          if (q < nly && tile_y0 + t < ch.H) {
+            LinTap tp = lin_src(tile_y0 + t, lv.Hd, ch.H);
+            if (tp.i0 == qy0 + q) wy += 1.f - tp.t;
+            if (tp.i1 == qy0 + q) wy += tp.t;
+          }
+          if (q < nlx && tile_x0 + t < ch.W) {
+            LinTap tp = lin_src(tile_x0 + t, lv.Wd, ch.W);
+            if (tp.i0 == qx0 + q) wx += 1.f - tp.t;
+            if (tp.i1 == qx0 + q) wx += tp.t;
+          }
+          wy_tab[q][t] = wy;
+          wx_tab[q][t] = wx;
+        }
+        __syncthreads();
+        for (int item = threadIdx.x; item < nly * nlx * 12; item += 256) {
+          const int c = item % 12, q = item / 12;
+          const int qx = q % nlx, qy = q / nlx;
+          float acc = 0.f;
+          for (int ty = 0; ty < 16; ++ty) {
+            const float wy = wy_tab[qy][ty];
+            if (wy == 0.f) continue;
+            float row = 0.f;
+#pragma unroll
+            for (int tx = 0; tx < 16; ++tx) row = fmaf(wx_tab[qx][tx], sva[(ty * 16 + tx) * 12 + c], row);
+            acc = fmaf(wy, row, acc);
+          }
+          if (acc != 0.f) red_add(lv.v_a_low + ((size_t)(qy0 + qy) * lv.Wd + qx0 + qx) * 12 + c, acc);
+        }
+        __syncthreads();
+        // a tile wider than kMaxFoot low-res pixels cannot happen for factor >= 2 (<= 10)
       } else {
-        Tri t = tri_setup(lattice_coord(j, ch.W, lv.GX), lattice_coord(i, ch.H, lv.GY), luma_coord(lum, lv.L),
-                          lv.L, lv.GY, lv.GX);
-        tri_scatter(lv.v_grid_cl, t, vA);
-        if (t.z_inside) {
+        Tri t = tri_setup(lattice_coord(jc, ch.W, lv.GX), lattice_coord(ic, ch.H, lv.GY), luma_coord(lum, lv.L), lv.L,
+                          lv.GY, lv.GX);
+        if (t.z_inside && inside) {
           float Ad[12], dAdz[12];
           tri_fetch<true>(lv.grid_cl, t, Ad, dAdz);
           float s = 0.f;
@@ -166,35 +229,45 @@ __global__ void __launch_bounds__(256) apply_bwd_kernel(const float* __restrict_
           for (int k = 0; k < 12; ++k) s = fmaf(vA[k], dAdz[k], s);
           v_lum += s * (float)(lv.L - 1);
         }
+        level_grad_accumulate(smem, t, vA, inside, tile_x0, tile_y0, ch.W, ch.H, lv.L, lv.GY, lv.GX, lv.v_grid_cl);
       }
     }
   }
-  v_rgb_in[(size_t)idx * 3] = gr + v_lum * kLumaR;
-  v_rgb_in[(size_t)idx * 3 + 1] = gg + v_lum * kLumaG;
-  v_rgb_in[(size_t)idx * 3 + 2] = gb + v_lum * kLumaB;
+  if (inside) {
+    v_rgb_in[idx * 3] = gr + v_lum * kLumaR;
+    v_rgb_in[idx * 3 + 1] = gg + v_lum * kLumaG;
+    v_rgb_in[idx * 3 + 2] = gb + v_lum * kLumaB;
+  }
 }
 
-__global__ void __launch_bounds__(256) lowres_slice_bwd_kernel(const float* __restrict__ rgb, int H, int W,
-                                                               BilLevel lv, float* __restrict__ v_rgb_in) {
-  int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= lv.Hd * lv.Wd) return;
-  int h = idx / lv.Wd, w = idx - h * lv.Wd;
-  LinTap ty = lin_src(h, H, lv.Hd), tx = lin_src(w, W, lv.Wd);
+__global__ void __launch_bounds__(256) lowres_slice_bwd_tiled_kernel(const float* __restrict__ rgb, int H, int W,
+                                                                     BilLevel lv, float* __restrict__ v_rgb_in) {
+  __shared__ __align__(16) float smem[kBwdSmemBil / sizeof(float)];
+  const int tiles_x = (lv.Wd + 15) / 16;
+  const int tile_x0 = (blockIdx.x % tiles_x) * 16, tile_y0 = (blockIdx.x / tiles_x) * 16;
+  const int w = tile_x0 + (threadIdx.x & 15), h = tile_y0 + (threadIdx.x >> 4);
+  const bool inside = w < lv.Wd && h < lv.Hd;
+  const int wc = min(w, lv.Wd - 1), hc = min(h, lv.Hd - 1);
+  LinTap ty = lin_src(hc, H, lv.Hd), tx = lin_src(wc, W, lv.Wd);
   float r, g, b;
   downsample_rgb(rgb, H, W, ty, tx, r, g, b);
-  Tri t = tri_setup(lattice_coord(w, lv.Wd, lv.GX), lattice_coord(h, lv.Hd, lv.GY),
+  Tri t = tri_setup(lattice_coord(wc, lv.Wd, lv.GX), lattice_coord(hc, lv.Hd, lv.GY),
                     luma_coord(luma_of(r, g, b), lv.L), lv.L, lv.GY, lv.GX);
   float vA[12];
-  load12(lv.v_a_low + (size_t)idx * 12, vA);
-  tri_scatter(lv.v_grid_cl, t, vA);
-  if (t.z_inside) {
+  if (inside) {
+    load12(lv.v_a_low + ((size_t)hc * lv.Wd + wc) * 12, vA);
+  } else {
+#pragma unroll
+    for (int k = 0; k < 12; ++k) vA[k] = 0.f;
+  }
+  if (inside && t.z_inside) {
     float Ad[12], dAdz[12];
     tri_fetch<true>(lv.grid_cl, t, Ad, dAdz);
     float s = 0.f;
 #pragma unroll
     for (int k = 0; k < 12; ++k) s = fmaf(vA[k], dAdz[k], s);
-    float v_lum = s * (float)(lv.L - 1);
-    float w0 = 1.f - tx.t, w1 = tx.t, h0 = 1.f - ty.t, h1 = ty.t;
+    const float v_lum = s * (float)(lv.L - 1);
+    const float w0 = 1.f - tx.t, w1 = tx.t, h0 = 1.f - ty.t, h1 = ty.t;
     const float lw[3] = {kLumaR, kLumaG, kLumaB};
     float* p00 = v_rgb_in + ((size_t)ty.i0 * W + tx.i0) * 3;
     float* p01 = v_rgb_in + ((size_t)ty.i0 * W + tx.i1) * 3;
@@ -202,13 +275,14 @@ __global__ void __launch_bounds__(256) lowres_slice_bwd_kernel(const float* __re
     float* p11 = v_rgb_in + ((size_t)ty.i1 * W + tx.i1) * 3;
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-      float v = v_lum * lw[c];
+      const float v = v_lum * lw[c];
       red_add(p00 + c, h0 * w0 * v);
       red_add(p01 + c, h0 * w1 * v);
       red_add(p10 + c, h1 * w0 * v);
       red_add(p11 + c, h1 * w1 * v);
     }
   }
+  level_grad_accumulate(smem, t, vA, inside, tile_x0, tile_y0, lv.Wd, lv.Hd, lv.L, lv.GY, lv.GX, lv.v_grid_cl);
 }
 
 // generic per-sample slice on the channel-first parameter layout (BilateralGrid.forward) ----------
@@ -425,11 +499,11 @@ extern "C" int bds_bilateral_bwd(const bds_bilateral_desc* d, int H, int W, cons
     }
     if (host_v_affine) ch.lv[l].v_affine = host_v_affine[l];
   }
-  apply_bwd_kernel<<<ceil_div((int64_t)H * W, 256), 256, 0, stream>>>(rgb_in, v_rgb_out, v_rgb_in, ch);
+  apply_bwd_tiled_kernel<<<((W + 15) / 16) * ((H + 15) / 16), 256, 0, stream>>>(rgb_in, v_rgb_out, v_rgb_in, ch);
   BDS_CHECK_LAUNCH();
   for (int l = 0; l < d->n_levels; ++l) {
     if (ch.lv[l].factor > 1) {
-      lowres_slice_bwd_kernel<<<ceil_div((int64_t)ch.lv[l].Hd * ch.lv[l].Wd, 256), 256, 0, stream>>>(
+      lowres_slice_bwd_tiled_kernel<<<((ch.lv[l].Wd + 15) / 16) * ((ch.lv[l].Hd + 15) / 16), 256, 0, stream>>>(
           rgb_in, H, W, ch.lv[l], v_rgb_in);
       BDS_CHECK_LAUNCH();
     }
