@@ -241,7 +241,7 @@ def main():
             for lvl, g in enumerate(grids):
                 loss = loss + total_variation_loss(g, TV_W * 0.5 * (sizes[lvl][0] * sizes[lvl][1] * sizes[lvl][2]) ** 0.5)
         loss.backward()
-        allreduce_grads([t.grad for t in leaves])
+        allreduce_grads([t.grad for t in leaves], flat=out["info"].get("grad_flat"))
         info_box.update(n_isect=out["info"]["n_isect"], n_visible=out["info"]["n_visible"])
         return loss
 

@@ -508,17 +508,40 @@ __global__ void __launch_bounds__(256, 4) composite_bwd_kernel(CompParams p) {
   }
 }
 
-__global__ void repack_grids_kernel(const float* __restrict__ cf, float* __restrict__ cl, int nodes) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= nodes * 12) return;
-  int node = i / 12, ch = i - node * 12;
-  cl[i] = cf[(size_t)ch * nodes + node];
+// channel-first parameter slots <-> channel-last workspace, all (camera, level) pairs in ONE launch
+constexpr int kMaxRepackJobs = 48;
+struct RepackJobs {
+  const float* src[kMaxRepackJobs];
+  float* dst[kMaxRepackJobs];
+  int nodes[kMaxRepackJobs];
+  int n;
+};
+template <bool UNPACK_ADD>
+__global__ void repack_jobs_kernel(RepackJobs jobs) {
+  const int job = blockIdx.y;
+  const int nodes = jobs.nodes[job];
+  const float* __restrict__ src = jobs.src[job];
+  float* __restrict__ dst = jobs.dst[job];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nodes * 12; i += gridDim.x * blockDim.x) {
+    if (UNPACK_ADD) {  // dst [12][nodes] += src [nodes][12]
+      int ch = i / nodes, node = i - ch * nodes;
+      dst[i] += src[(size_t)node * 12 + ch];
+    } else {           // dst [nodes][12] = src [12][nodes]
+      int node = i / 12, ch = i - node * 12;
+      dst[i] = src[(size_t)ch * nodes + node];
+    }
+  }
 }
-__global__ void unpack_add_grids_kernel(const float* __restrict__ cl, float* __restrict__ cf, int nodes) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= nodes * 12) return;
-  int ch = i / nodes, node = i - ch * nodes;
-  cf[i] += cl[(size_t)node * 12 + ch];
+template <bool UNPACK_ADD>
+static int launch_repack(RepackJobs& jobs, cudaStream_t stream) {
+  if (jobs.n == 0) return 0;
+  int max_nodes = 0;
+  for (int k = 0; k < jobs.n; ++k) max_nodes = jobs.nodes[k] > max_nodes ? jobs.nodes[k] : max_nodes;
+  dim3 grid(ceil_div((int64_t)max_nodes * 12, 256), jobs.n);
+  repack_jobs_kernel<UNPACK_ADD><<<grid, 256, 0, stream>>>(jobs);
+  BDS_CHECK_LAUNCH();
+  jobs.n = 0;
+  return 0;
 }
 
 struct CompWorkspace {
@@ -593,6 +616,8 @@ extern "C" int bds_composite_fwd(const bds_render_desc* d, const bds_epilogue_de
     BDS_REQUIRE(host_grids && workspace, "composite_fwd: mode 2 needs grids and workspace");
     CompWorkspace w = carve_comp(d, e);
     p.bil.n_levels = e->bil.n_levels;
+    RepackJobs jobs;
+    jobs.n = 0;
     for (int l = 0; l < e->bil.n_levels; ++l) {
       int nodes = e->bil.L[l] * e->bil.GY[l] * e->bil.GX[l];
       float* base = reinterpret_cast<float*>(static_cast<char*>(workspace) + w.grid_cl[l]);
@@ -601,10 +626,12 @@ extern "C" int bds_composite_fwd(const bds_render_desc* d, const bds_epilogue_de
       for (int c = 0; c < d->n_cams; ++c) {
         const float* src = host_grids[c * e->bil.n_levels + l];
         if (!src) continue;  // camera outside the band
-        repack_grids_kernel<<<ceil_div(nodes * 12, 256), 256, 0, stream>>>(src, base + (size_t)c * nodes * 12, nodes);
-        BDS_CHECK_LAUNCH();
+        jobs.src[jobs.n] = src; jobs.dst[jobs.n] = base + (size_t)c * nodes * 12; jobs.nodes[jobs.n] = nodes;
+        if (++jobs.n == kMaxRepackJobs)
+          if (int rc = launch_repack<false>(jobs, stream)) return rc;
       }
     }
+    if (int rc = launch_repack<false>(jobs, stream)) return rc;
   }
   switch (e->mode) {
     case 0: composite_fwd_kernel<0><<<n_tiles, 256, 0, stream>>>(p); break;
@@ -644,19 +671,27 @@ extern "C" int bds_composite_bwd(const bds_render_desc* d, const bds_epilogue_de
   if (e->mode == 2) {
     BDS_REQUIRE(host_grids && host_v_grids && workspace, "composite_bwd: mode 2 needs grids, v_grids and workspace");
     p.bil.n_levels = e->bil.n_levels;
+    RepackJobs jobs;
+    jobs.n = 0;
     for (int l = 0; l < e->bil.n_levels; ++l) {
       int nodes = e->bil.L[l] * e->bil.GY[l] * e->bil.GX[l];
       float* base = reinterpret_cast<float*>(static_cast<char*>(workspace) + w.grid_cl[l]);
       float* vbase = reinterpret_cast<float*>(static_cast<char*>(workspace) + w.v_grid_cl[l]);
       p.bil.grid_cl[l] = base; p.bil.v_grid_cl[l] = vbase;
       p.bil.L[l] = e->bil.L[l]; p.bil.GY[l] = e->bil.GY[l]; p.bil.GX[l] = e->bil.GX[l];
-      BDS_CHECK_CUDA(cudaMemsetAsync(vbase, 0, (size_t)d->n_cams * nodes * 12 * sizeof(float), stream));
       for (int c = 0; c < d->n_cams; ++c) {
         const float* src = host_grids[c * e->bil.n_levels + l];
         if (!src) continue;
-        repack_grids_kernel<<<ceil_div(nodes * 12, 256), 256, 0, stream>>>(src, base + (size_t)c * nodes * 12, nodes);
-        BDS_CHECK_LAUNCH();
+        jobs.src[jobs.n] = src; jobs.dst[jobs.n] = base + (size_t)c * nodes * 12; jobs.nodes[jobs.n] = nodes;
+        if (++jobs.n == kMaxRepackJobs)
+          if (int rc = launch_repack<false>(jobs, stream)) return rc;
       }
+    }
+    if (int rc = launch_repack<false>(jobs, stream)) return rc;
+    // the gradient halves of the workspace are contiguous per level pair (grid_cl | v_grid_cl): zero them
+    for (int l = 0; l < e->bil.n_levels; ++l) {
+      int nodes = e->bil.L[l] * e->bil.GY[l] * e->bil.GX[l];
+      BDS_CHECK_CUDA(cudaMemsetAsync(p.bil.v_grid_cl[l], 0, (size_t)d->n_cams * nodes * 12 * sizeof(float), stream));
     }
   }
   switch (e->mode) {
@@ -670,16 +705,19 @@ extern "C" int bds_composite_bwd(const bds_render_desc* d, const bds_epilogue_de
   }
   BDS_CHECK_LAUNCH();
   if (e->mode == 2) {
+    RepackJobs jobs;
+    jobs.n = 0;
     for (int l = 0; l < e->bil.n_levels; ++l) {
       int nodes = e->bil.L[l] * e->bil.GY[l] * e->bil.GX[l];
       for (int c = 0; c < d->n_cams; ++c) {
         float* dst = host_v_grids[c * e->bil.n_levels + l];
         if (!dst) continue;
-        unpack_add_grids_kernel<<<ceil_div(nodes * 12, 256), 256, 0, stream>>>(p.bil.v_grid_cl[l] + (size_t)c * nodes * 12, dst,
-                                                                                nodes);
-        BDS_CHECK_LAUNCH();
+        jobs.src[jobs.n] = p.bil.v_grid_cl[l] + (size_t)c * nodes * 12; jobs.dst[jobs.n] = dst; jobs.nodes[jobs.n] = nodes;
+        if (++jobs.n == kMaxRepackJobs)
+          if (int rc = launch_repack<true>(jobs, stream)) return rc;
       }
     }
+    if (int rc = launch_repack<true>(jobs, stream)) return rc;
   }
   return 0;
 }

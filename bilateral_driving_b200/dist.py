@@ -36,7 +36,12 @@ def cameras_in_band(rb: int, re: int, height: int) -> List[int]:
     return list(range(rb // tile_h, (re - 1) // tile_h + 1))
 
 
-def allreduce_grads(tensors: Sequence[torch.Tensor], group=None) -> None:
+def _covered_by(flat: torch.Tensor, t: torch.Tensor) -> bool:
+    lo, hi = flat.data_ptr(), flat.data_ptr() + flat.numel() * flat.element_size()
+    return t.is_contiguous() and lo <= t.data_ptr() and t.data_ptr() + t.numel() * t.element_size() <= hi
+
+
+def allreduce_grads(tensors: Sequence[torch.Tensor], group=None, flat: torch.Tensor = None) -> None:
     """One all-reduce (SUM) of every gradient: a single coalesced NCCL group launch in place on GPUs, a
     single flat buffer elsewhere (gloo).  No-op for a single process."""
     import torch.distributed as dist
@@ -44,6 +49,11 @@ def allreduce_grads(tensors: Sequence[torch.Tensor], group=None) -> None:
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return
     grads = [t for t in tensors if t is not None]
+    if flat is not None:
+        # the render backward wrote the Gaussian gradients as views of ONE flat buffer: reduce it in place
+        rest = [g for g in grads if not _covered_by(flat, g)]
+        if len(rest) < len(grads):
+            grads = [flat] + rest
     backend = dist.get_backend(group)
     if backend == "nccl" and hasattr(dist, "_coalescing_manager"):
         # one fused NCCL launch (ncclGroupStart/End) over the gradient tensors in place: no staging copy

@@ -237,13 +237,23 @@ class _RenderFn(torch.autograd.Function):
                                         ptr(v_depth_in), ptr(v_alpha), ptr(v_splats), ptr(v_sky),
                                         ptr_array(v_grids) if grids else NULL, ptr(v_bg), ptr(ws2), st),
                   "bds_composite_bwd")
-        v_means = torch.zeros_like(means)
-        v_quats = torch.zeros_like(quats)
-        v_scales = torch.zeros_like(scales)
-        v_opac = torch.zeros_like(opacities)
-        v_colors = torch.zeros_like(colors) if colors is not None else None
-        v_fdc = torch.zeros_like(fdc) if fdc is not None else None
-        v_frest = torch.zeros_like(frest) if frest is not None else None
+        # every Gaussian-parameter gradient lives in ONE flat zero-filled buffer (one fill, and the
+        # multi-GPU step all-reduces it in place: dist.allreduce_grads)
+        parts = [("means", means), ("quats", quats), ("scales", scales), ("opac", opacities)]
+        if colors is not None:
+            parts.append(("colors", colors))
+        if fdc is not None:
+            parts.append(("fdc", fdc))
+        if frest is not None:
+            parts.append(("frest", frest))
+        flat = torch.zeros(sum(t.numel() for _, t in parts), **f32)
+        views, off = {}, 0
+        for name, t in parts:
+            views[name] = flat[off:off + t.numel()].view(t.shape)
+            off += t.numel()
+        v_means, v_quats, v_scales, v_opac = views["means"], views["quats"], views["scales"], views["opac"]
+        v_colors, v_fdc, v_frest = views.get("colors"), views.get("fdc"), views.get("frest")
+        ctx.holder["grad_flat"] = flat
         v_view = torch.zeros_like(viewmats) if need[9] else None
         want_taps = cfg.dense_info
         v_m2d = torch.zeros(Cn, N, 2, **f32) if want_taps else None
