@@ -49,6 +49,7 @@ constexpr float kAlphaMax = 0.999f;
 constexpr float kTStop = 1e-4f;
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
+constexpr float kLog2_255 = 7.994353436858858f;   // alpha >= 1/255  <=>  log2(alpha) >= -kLog2_255
 
 #ifdef __CUDACC__
 // warp helpers ---------------------------------------------------------------------------------

@@ -312,7 +312,7 @@ __global__ void __launch_bounds__(256) emit_keys_kernel(EmitParams p) {
     int ty0, ty1;
     band_rows2(p.d, p.tile_h, c, ty0, ty1);
     // same candidate rectangle + same hit test (both non-inlined bodies) as the counting pass
-    tr = candidate_rect(r0.x, r0.y, (float)p.radii[idx], r0.z, r0.w, r1.x, r2.w, p.tile_w, p.tile_h, ty0, ty1);
+    tr = candidate_rect(r0.x, r0.y, (float)p.radii[idx], r0.z, r0.w, r1.x, r2.w + kLog2_255, p.tile_w, p.tile_h, ty0, ty1);
     o = p.offsets[r];
     o_end = o + p.tiles_sorted[r];
   }
@@ -336,7 +336,7 @@ __global__ void __launch_bounds__(256) emit_keys_kernel(EmitParams p) {
       const int ox0 = __shfl_sync(0xffffffffu, tr.x0, owner), oy0 = __shfl_sync(0xffffffffu, tr.y0, owner);
       const float gx = __shfl_sync(0xffffffffu, r0.x, owner), gy = __shfl_sync(0xffffffffu, r0.y, owner);
       const float ga = __shfl_sync(0xffffffffu, r0.z, owner), gb = __shfl_sync(0xffffffffu, r0.w, owner);
-      const float gc = __shfl_sync(0xffffffffu, r1.x, owner), gcut = __shfl_sync(0xffffffffu, r2.w, owner);
+      const float gc = __shfl_sync(0xffffffffu, r1.x, owner), gcut = __shfl_sync(0xffffffffu, r2.w, owner) + kLog2_255;
       const int gcam = __shfl_sync(0xffffffffu, c, owner), gslot = __shfl_sync(0xffffffffu, slot, owner);
       const long long go = __shfl_sync(0xffffffffu, o, owner), gend = __shfl_sync(0xffffffffu, o_end, owner);
       bool hit = false;

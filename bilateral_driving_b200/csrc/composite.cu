@@ -129,7 +129,7 @@ BDS_D void fused_chain_fwd(const FusedBil& b, int cam, int H, int W, int i, int 
 // forward
 // =================================================================================================
 template <int MODE>
-__global__ void __launch_bounds__(256) composite_fwd_kernel(CompParams p) {
+__global__ void __launch_bounds__(256, 5) composite_fwd_kernel(CompParams p) {
   __shared__ __align__(128) float4 srec[kStages][kChunk * 3];
   __shared__ __align__(8) uint64_t bars[kStages];
 
@@ -174,7 +174,7 @@ __global__ void __launch_bounds__(256) composite_fwd_kernel(CompParams p) {
         if (j < cnt) {
           float4 r0 = sr[j * 3], r1 = sr[j * 3 + 1], r2 = sr[j * 3 + 2];
           float s = min_sigma_rect(r0.x, r0.y, r0.z, r0.w, r1.x, rxmin, rxmax, rymin, rymax);
-          hit = !(s > r2.w + kCullMargin);
+          hit = !(s > r2.w + (kLog2_255 + kCullMargin));
         }
         unsigned m = __ballot_sync(kFull, hit);
         while (m) {
@@ -182,9 +182,11 @@ __global__ void __launch_bounds__(256) composite_fwd_kernel(CompParams p) {
           m &= m - 1;
           float4 r0 = sr[jj * 3], r1 = sr[jj * 3 + 1], r2 = sr[jj * 3 + 2];
           float dx = r0.x - pxf, dy = r0.y - pyf;
-          float s = r0.z * dx * dx + r0.w * dx * dy + r1.x * dy * dy;  // sigma * log2(e)
-          float alpha = fminf(kAlphaMax, r1.y * exp2f(-s));
-          if (!done && s >= 0.f && alpha >= kAlphaMin) {
+          // e = log2(opacity) - sigma', sigma' = a' dx^2 + b' dx dy + c' dy^2  (alpha = 2^e)
+          float e = fmaf(-dx, fmaf(r0.w, dy, r0.z * dx), r2.w);
+          e = fmaf(-(r1.x * dy), dy, e);
+          float alpha = fminf(kAlphaMax, exp2f(e));
+          if (!done && e <= r2.w && e >= -kLog2_255) {  // sigma' >= 0 and alpha >= 1/255
             float nT = T * (1.f - alpha);
             if (nT <= kTStop) {
               done = true;
@@ -436,7 +438,7 @@ __global__ void __launch_bounds__(256, 4) composite_bwd_kernel(CompParams p) {
         if (j < cnt) {
           float4 r0 = sr[j * 3], r1 = sr[j * 3 + 1], r2 = sr[j * 3 + 2];
           float s = min_sigma_rect(r0.x, r0.y, r0.z, r0.w, r1.x, rxmin, rxmax, rymin, rymax);
-          hit = !(s > r2.w + kCullMargin);
+          hit = !(s > r2.w + (kLog2_255 + kCullMargin));
         }
         unsigned m = __ballot_sync(kFull, hit);
         while (m) {
@@ -446,11 +448,11 @@ __global__ void __launch_bounds__(256, 4) composite_bwd_kernel(CompParams p) {
           int gidx = chunk0 + jj;
           float4 r0 = sr[jj * 3], r1 = sr[jj * 3 + 1], r2 = sr[jj * 3 + 2];
           float dx = r0.x - pxf, dy = r0.y - pyf;
-          float s = r0.z * dx * dx + r0.w * dx * dy + r1.x * dy * dy;
-          float vis = exp2f(-s);
-          float araw = r1.y * vis;
+          float e = fmaf(-dx, fmaf(r0.w, dy, r0.z * dx), r2.w);
+          e = fmaf(-(r1.x * dy), dy, e);
+          float araw = exp2f(e);                       // opacity * exp(-sigma)
           float alpha = fminf(kAlphaMax, araw);
-          bool valid = g.inside && gidx <= last && s >= 0.f && alpha >= kAlphaMin;
+          bool valid = g.inside && gidx <= last && e <= r2.w && e >= -kLog2_255;
           if (!__any_sync(kFull, valid)) continue;
           float v[16];
 #pragma unroll
@@ -477,11 +479,12 @@ __global__ void __launch_bounds__(256, 4) composite_bwd_kernel(CompParams p) {
               float vy = v_s * (r0.w * dx + 2.f * r1.x * dy);
               v[0] = vx; v[1] = vy;
               v[10] = fabsf(vx); v[11] = fabsf(vy);
-              v[5] = vis * v_alpha;
+              v[5] = araw * v_alpha;                   // x 1/opacity after the reduction (linear)
             }
           }
           float tot = warp_transpose_reduce16(v);
           int comp = lane >> 1;
+          if (comp == 5) tot = __fdividef(tot, r1.y);   // v_opacity = sum(vis * v_alpha), vis = araw / opacity
           if ((lane & 1) == 0 && comp < 12 && tot != 0.f) {
             int slot = __float_as_int(r2.z);
             red_add(p.v_splats + (size_t)slot * 12 + comp, tot);

@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(256) project_fwd_kernel(ProjParams p) {
     int n_tiles = 0, radius_i = 0;
     // ---- phase 1: projection and candidate rectangle ----------------------------------------------
     bool cand = false;
-    float mx = 0.f, my = 0.f, qa = 0.f, qb = 0.f, qc = 0.f, op = 0.f, sigma_cut = 0.f, depth = 0.f;
+    float mx = 0.f, my = 0.f, qa = 0.f, qb = 0.f, qc = 0.f, op = 0.f, sigma_cut = 0.f, lop = 0.f, depth = 0.f;
     TileRect tr = {0, 0, 0, 0};
     CamIntr cam;
     load_cam(p.viewmats, p.Ks, c, cam);
@@ -96,7 +96,8 @@ __global__ void __launch_bounds__(256) project_fwd_kernel(ProjParams p) {
         if (p.d.antialiased) op *= o.comp;
         mx = o.mx; my = o.my; depth = o.z;
         qa = 0.5f * kLog2e * o.a; qb = kLog2e * o.b; qc = 0.5f * kLog2e * o.c;
-        sigma_cut = __log2f(255.0f * op);  // alpha >= 1/255  <=>  sigma' <= log2(255 o)
+        lop = __log2f(op);
+        sigma_cut = lop + kLog2_255;  // alpha >= 1/255  <=>  sigma' <= log2(255 o)
         if (op >= kAlphaMin) {
           tr = candidate_rect(mx, my, o.radius, qa, qb, qc, sigma_cut, p.tile_w, p.tile_h, ty0, ty1);
           cand = (tr.x1 > tr.x0) && (tr.y1 > tr.y0);
@@ -168,7 +169,7 @@ __global__ void __launch_bounds__(256) project_fwd_kernel(ProjParams p) {
       }
       rec[9] = depth;
       rec[10] = __int_as_float((int)idx);
-      rec[11] = sigma_cut;
+      rec[11] = lop;  // log2(opacity): alpha = exp2(rec[11] - sigma')
     }
     // warp-aggregated compaction: one atomic per warp
     unsigned ballot = __ballot_sync(0xffffffffu, emit);

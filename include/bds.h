@@ -121,8 +121,8 @@ typedef struct {
  * radii [C,N] int32, means2d [C,N,2], depths [C,N], conics [C,N,3], (compensations [C,N] or NULL),
  * tiles_touched [C,N] int32 (exact number of (tile) records the Gaussian will emit inside the
  * band), and compacts the visible splats into packed 48-byte records:
- *   splats [cap,12] = {x, y, a', b', c', opacity, r, g, b, depth, bits(flat id c*N+n), sigma_cut}
- * with (a',b',c') = log2(e) * (a/2, b, c/2) of the conic and sigma_cut = log2(255*opacity);
+ *   splats [cap,12] = {x, y, a', b', c', opacity, r, g, b, depth, bits(flat id c*N+n), log2(opacity)}
+ * with (a',b',c') = log2(e) * (a/2, b, c/2) of the conic (alpha = exp2(log2(opacity) - sigma'));
  * slot_of [C,N] int32 = record index or -1 (optional, may be NULL); counters[0] = number of records (device int32,
  * caller zero-fills counters[0..3]); counters[1] is set to 1 on capacity overflow.
  * camera position for the SH view direction is taken from viewmats. */
