@@ -109,6 +109,13 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def cpu_threads() -> int:
+    """Threads for the CPU legs: torch's indexing kernels peak at 32 threads on the 128-core hosts of this pool
+    (probe scripts/cpu_threads_probe.py: 8/16/32/64/128 threads -> 0.54/0.61/0.68/0.43/0.08 Mpix/s), so the
+    fastest setting is used and reported in ``cores``."""
+    return max(1, min(os.cpu_count() or 1, 32))
+
+
 def cpu_bilateral_baseline(rgb_in_cpu, grids_cpu, repeats=2):
     """The reference's pure-PyTorch bilateral path (oracle port of modules.py:505-584 +
     scene_graph.py:112-117, guidance_factor=None = the semantics the fused kernel implements), fwd+bwd
@@ -117,7 +124,7 @@ def cpu_bilateral_baseline(rgb_in_cpu, grids_cpu, repeats=2):
 
     from oracle import bilateral_ref as B
 
-    torch.set_num_threads(os.cpu_count() or 1)
+    torch.set_num_threads(cpu_threads())
     H, W, _ = rgb_in_cpu.shape
     g = torch.Generator(); g.manual_seed(2)
     G = torch.randn(H, W, 3, generator=g)
@@ -150,7 +157,7 @@ def run_reference(args):
     g = torch.Generator(); g.manual_seed(17)
     rgb_in = torch.rand(H, W, 3, generator=g)
     grids = [x[0] for x in S.make_grids(1)]
-    torch.set_num_threads(os.cpu_count() or 1)
+    torch.set_num_threads(cpu_threads())
     from oracle import bilateral_ref as B
 
     Gm = torch.randn(H, W, 3, generator=g)
