@@ -277,7 +277,12 @@ def main():
         sampler.start()
     render.KERNEL_EVENTS = {}
     launches0 = _lib.lib.bds_launch_count()
+    profile_range = os.environ.get("BDS_PROFILE_RANGE") == "1"  # ncu --profile-from-start off: the timed steps only
+    if profile_range:
+        torch.cuda.profiler.start()
     ms = timed(lambda: step(gt_dev, vm_d, Ks_d), args.steps)
+    if profile_range:
+        torch.cuda.profiler.stop()
     launches = (_lib.lib.bds_launch_count() - launches0) // args.steps
     ev = render.KERNEL_EVENTS
     render.KERNEL_EVENTS = None

@@ -17,18 +17,20 @@
 
 namespace bds {
 
-__global__ void repack_grid_kernel(const float* __restrict__ cf, float* __restrict__ cl, int nodes) {
+__global__ void repack_grid_kernel(const float* __restrict__ cf, float* __restrict__ cl, int L, int GY, int GX) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;  // over nodes*12, channel fastest
-  if (i >= nodes * 12) return;
+  if (i >= L * GY * GX * 12) return;
   int node = i / 12, ch = i - node * 12;
-  cl[i] = cf[(size_t)ch * nodes + node];
+  cl[i] = cf[bil_param_index(node, ch, L, GY, GX)];
 }
 
-__global__ void unpack_add_grid_kernel(const float* __restrict__ cl, float* __restrict__ cf, int nodes) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;  // over 12*nodes, node fastest (coalesced writes)
+__global__ void unpack_add_grid_kernel(const float* __restrict__ cl, float* __restrict__ cf, int L, int GY, int GX) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;  // over the parameter layout [12][L][GY][GX] (coalesced writes)
+  int nodes = L * GY * GX;
   if (i >= nodes * 12) return;
-  int ch = i / nodes, node = i - ch * nodes;
-  cf[i] += cl[(size_t)node * 12 + ch];
+  int ch = i / nodes, rem = i - ch * nodes;
+  int x = rem % GX, y = (rem / GX) % GY, z = rem / (GX * GY);
+  cf[i] += cl[(size_t)bil_node(x, y, z, L, GX) * 12 + ch];
 }
 
 // bilinear gather of the guidance RGB at low-res pixel (h, w)
@@ -296,12 +298,16 @@ __global__ void slice_generic_fwd_kernel(const float* __restrict__ grid, int L, 
   Tri t = tri_setup(fx, fy, fz, L, GY, GX);
   int nodes = L * GY * GX;
   float wx0 = 1.f - t.wx1, wy0 = 1.f - t.wy1, wz0 = 1.f - t.wz1;
+  // offsets in the PARAMETER layout [L][GY][GX] (this entry reads the grid in place)
+  const int x1 = t.n01 != t.n00 ? t.x0 + 1 : t.x0, y1 = t.n10 != t.n00 ? t.y0 + 1 : t.y0;
+  const int q00 = (t.z0 * GY + t.y0) * GX + t.x0, q01 = (t.z0 * GY + t.y0) * GX + x1;
+  const int q10 = (t.z0 * GY + y1) * GX + t.x0, q11 = (t.z0 * GY + y1) * GX + x1, qz = t.dz * GY * GX;
   for (int k = 0; k < 12; ++k) {
     const float* g = grid + (size_t)k * nodes;
-    float c0 = wy0 * (wx0 * __ldg(g + t.n00) + t.wx1 * __ldg(g + t.n01)) +
-               t.wy1 * (wx0 * __ldg(g + t.n10) + t.wx1 * __ldg(g + t.n11));
-    float c1 = wy0 * (wx0 * __ldg(g + t.n00 + t.dz) + t.wx1 * __ldg(g + t.n01 + t.dz)) +
-               t.wy1 * (wx0 * __ldg(g + t.n10 + t.dz) + t.wx1 * __ldg(g + t.n11 + t.dz));
+    float c0 = wy0 * (wx0 * __ldg(g + q00) + t.wx1 * __ldg(g + q01)) +
+               t.wy1 * (wx0 * __ldg(g + q10) + t.wx1 * __ldg(g + q11));
+    float c1 = wy0 * (wx0 * __ldg(g + q00 + qz) + t.wx1 * __ldg(g + q01 + qz)) +
+               t.wy1 * (wx0 * __ldg(g + q10 + qz) + t.wx1 * __ldg(g + q11 + qz));
     affine[(size_t)idx * 12 + k] = wz0 * c0 + t.wz1 * c1;
   }
 }
@@ -317,24 +323,27 @@ __global__ void slice_generic_bwd_kernel(const float* __restrict__ grid, int L, 
   Tri t = tri_setup(fx, fy, fz, L, GY, GX);
   int nodes = L * GY * GX;
   float wx0 = 1.f - t.wx1, wy0 = 1.f - t.wy1, wz0 = 1.f - t.wz1;
+  const int x1 = t.n01 != t.n00 ? t.x0 + 1 : t.x0, y1 = t.n10 != t.n00 ? t.y0 + 1 : t.y0;
+  const int q00 = (t.z0 * GY + t.y0) * GX + t.x0, q01 = (t.z0 * GY + t.y0) * GX + x1;
+  const int q10 = (t.z0 * GY + y1) * GX + t.x0, q11 = (t.z0 * GY + y1) * GX + x1, qz = t.dz * GY * GX;
   float s = 0.f;
   for (int k = 0; k < 12; ++k) {
     float va = v_affine[(size_t)idx * 12 + k];
     const float* g = grid + (size_t)k * nodes;
     float* vg = v_grid + (size_t)k * nodes;
-    float c0 = wy0 * (wx0 * __ldg(g + t.n00) + t.wx1 * __ldg(g + t.n01)) +
-               t.wy1 * (wx0 * __ldg(g + t.n10) + t.wx1 * __ldg(g + t.n11));
-    float c1 = wy0 * (wx0 * __ldg(g + t.n00 + t.dz) + t.wx1 * __ldg(g + t.n01 + t.dz)) +
-               t.wy1 * (wx0 * __ldg(g + t.n10 + t.dz) + t.wx1 * __ldg(g + t.n11 + t.dz));
+    float c0 = wy0 * (wx0 * __ldg(g + q00) + t.wx1 * __ldg(g + q01)) +
+               t.wy1 * (wx0 * __ldg(g + q10) + t.wx1 * __ldg(g + q11));
+    float c1 = wy0 * (wx0 * __ldg(g + q00 + qz) + t.wx1 * __ldg(g + q01 + qz)) +
+               t.wy1 * (wx0 * __ldg(g + q10 + qz) + t.wx1 * __ldg(g + q11 + qz));
     s = fmaf(va, c1 - c0, s);
-    red_add(vg + t.n00, va * wz0 * wy0 * wx0);
-    red_add(vg + t.n01, va * wz0 * wy0 * t.wx1);
-    red_add(vg + t.n10, va * wz0 * t.wy1 * wx0);
-    red_add(vg + t.n11, va * wz0 * t.wy1 * t.wx1);
-    red_add(vg + t.n00 + t.dz, va * t.wz1 * wy0 * wx0);
-    red_add(vg + t.n01 + t.dz, va * t.wz1 * wy0 * t.wx1);
-    red_add(vg + t.n10 + t.dz, va * t.wz1 * t.wy1 * wx0);
-    red_add(vg + t.n11 + t.dz, va * t.wz1 * t.wy1 * t.wx1);
+    red_add(vg + q00, va * wz0 * wy0 * wx0);
+    red_add(vg + q01, va * wz0 * wy0 * t.wx1);
+    red_add(vg + q10, va * wz0 * t.wy1 * wx0);
+    red_add(vg + q11, va * wz0 * t.wy1 * t.wx1);
+    red_add(vg + q00 + qz, va * t.wz1 * wy0 * wx0);
+    red_add(vg + q01 + qz, va * t.wz1 * wy0 * t.wx1);
+    red_add(vg + q10 + qz, va * t.wz1 * t.wy1 * wx0);
+    red_add(vg + q11 + qz, va * t.wz1 * t.wy1 * t.wx1);
   }
   float v_lum = t.z_inside ? s * (float)(L - 1) : 0.f;
   v_rgb[(size_t)idx * 3] = v_lum * kLumaR;
@@ -455,7 +464,7 @@ extern "C" int bds_bilateral_fwd(const bds_bilateral_desc* d, int H, int W, cons
   for (int l = 0; l < d->n_levels; ++l) {
     BDS_REQUIRE(host_grids[l], "bilateral_fwd: null grid at level %d", l);
     int nodes = d->L[l] * d->GY[l] * d->GX[l];
-    repack_grid_kernel<<<ceil_div(nodes * 12, 256), 256, 0, stream>>>(host_grids[l], const_cast<float*>(ch.lv[l].grid_cl), nodes);
+    repack_grid_kernel<<<ceil_div(nodes * 12, 256), 256, 0, stream>>>(host_grids[l], const_cast<float*>(ch.lv[l].grid_cl), d->L[l], d->GY[l], d->GX[l]);
     BDS_CHECK_LAUNCH();
     if (host_affine_out) ch.lv[l].affine_out = host_affine_out[l];
   }
@@ -487,7 +496,7 @@ extern "C" int bds_bilateral_bwd(const bds_bilateral_desc* d, int H, int W, cons
   for (int l = 0; l < d->n_levels; ++l) {
     BDS_REQUIRE(host_grids[l] && host_v_grids[l], "bilateral_bwd: null grid at level %d", l);
     int nodes = d->L[l] * d->GY[l] * d->GX[l];
-    repack_grid_kernel<<<ceil_div(nodes * 12, 256), 256, 0, stream>>>(host_grids[l], const_cast<float*>(ch.lv[l].grid_cl), nodes);
+    repack_grid_kernel<<<ceil_div(nodes * 12, 256), 256, 0, stream>>>(host_grids[l], const_cast<float*>(ch.lv[l].grid_cl), d->L[l], d->GY[l], d->GX[l]);
     BDS_CHECK_LAUNCH();
     BDS_CHECK_CUDA(cudaMemsetAsync(ch.lv[l].v_grid_cl, 0, (size_t)nodes * 12 * sizeof(float), stream));
     if (ch.lv[l].factor > 1) {
@@ -508,7 +517,7 @@ extern "C" int bds_bilateral_bwd(const bds_bilateral_desc* d, int H, int W, cons
       BDS_CHECK_LAUNCH();
     }
     int nodes = d->L[l] * d->GY[l] * d->GX[l];
-    unpack_add_grid_kernel<<<ceil_div(nodes * 12, 256), 256, 0, stream>>>(ch.lv[l].v_grid_cl, host_v_grids[l], nodes);
+    unpack_add_grid_kernel<<<ceil_div(nodes * 12, 256), 256, 0, stream>>>(ch.lv[l].v_grid_cl, host_v_grids[l], d->L[l], d->GY[l], d->GX[l]);
     BDS_CHECK_LAUNCH();
   }
   return 0;

@@ -136,7 +136,7 @@ BDS_D void level_grad_accumulate(float* smem, const Tri& t, const float vAff[12]
         const int nx = node % kWinNodes, ny = (node / kWinNodes) % kWinNodes, z = node / (kWinNodes * kWinNodes);
         const int gx = nx0 + nx, gy = ny0 + ny;
         if (gx < GX && gy < GY) {
-          float* dst = v_grid + ((size_t)(z * GY + gy) * GX + gx) * 12 + ch0;
+          float* dst = v_grid + (size_t)bil_node(gx, gy, z, L, GX) * 12 + ch0;
           if (v.x != 0.f) red_add(dst, v.x);
           if (v.y != 0.f) red_add(dst + 1, v.y);
           if (v.z != 0.f) red_add(dst + 2, v.z);

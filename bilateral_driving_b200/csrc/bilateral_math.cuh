@@ -8,8 +8,10 @@
 //   models/modules.py:494-504, 409-420  bilinear resize, align_corners=False (low-res guidance)
 //   models/trainers/scene_graph.py:112-117   x <- A[:, :3] x + A[:, 3], level after level
 //
-// Grids are read in a channel-LAST repack [L][GY][GX][12] (three float4 per lattice node) that the
-// host entry points build from the reference's channel-first [12][L][GY][GX] parameter slot.
+// Grids are read in a channel-LAST, guidance-contiguous repack [GY][GX][L][12] (three float4 per
+// lattice node; the L slabs of one xy node are 48*L contiguous bytes, so lanes of a warp that differ
+// only in their guidance cell touch a handful of cache lines) that the host entry points build from
+// the reference's channel-first [12][L][GY][GX] parameter slot.
 #pragma once
 #include "bds_common.cuh"
 
@@ -66,7 +68,16 @@ BDS_HD float luma_coord(float luma, int L) {
   return ((z + 1.0f) * 0.5f) * (float)(L - 1);
 }
 
-// Trilinear set-up with border clamping.  Offsets are in lattice NODES of the [L][GY][GX] repack.
+// node index of (x, y, z) in the [GY][GX][L] repack, and the inverse map used by the repack kernels
+BDS_HD int bil_node(int x, int y, int z, int L, int GX) { return (y * GX + x) * L + z; }
+// element i of the repack ([node][12]) <-> element of the parameter layout [12][L][GY][GX]
+BDS_HD size_t bil_param_index(int node, int ch, int L, int GY, int GX) {
+  int z = node % L, xy = node / L;
+  int x = xy % GX, y = xy / GX;
+  return (((size_t)ch * L + z) * GY + y) * GX + x;
+}
+
+// Trilinear set-up with border clamping.  Offsets are in lattice NODES of the [GY][GX][L] repack.
 struct Tri {
   int n00, n01, n10, n11;  // (y0,x0) (y0,x1) (y1,x0) (y1,x1) node offsets inside slab z0
   int dz;                  // node offset from slab z0 to slab z1 (0 when clamped)
@@ -88,12 +99,11 @@ BDS_HD Tri tri_setup(float fx, float fy, float fz, int L, int GY, int GX) {
   int y1 = y0 + 1 < GY ? y0 + 1 : y0;
   int z1 = z0 + 1 < L ? z0 + 1 : z0;
   t.x0 = x0; t.y0 = y0; t.z0 = z0;
-  int base = (z0 * GY) * GX;
-  t.n00 = base + y0 * GX + x0;
-  t.n01 = base + y0 * GX + x1;
-  t.n10 = base + y1 * GX + x0;
-  t.n11 = base + y1 * GX + x1;
-  t.dz = (z1 - z0) * GY * GX;
+  t.n00 = bil_node(x0, y0, z0, L, GX);
+  t.n01 = bil_node(x1, y0, z0, L, GX);
+  t.n10 = bil_node(x0, y1, z0, L, GX);
+  t.n11 = bil_node(x1, y1, z0, L, GX);
+  t.dz = z1 - z0;
   return t;
 }
 

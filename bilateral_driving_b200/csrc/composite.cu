@@ -516,22 +516,24 @@ constexpr int kMaxRepackJobs = 48;
 struct RepackJobs {
   const float* src[kMaxRepackJobs];
   float* dst[kMaxRepackJobs];
-  int nodes[kMaxRepackJobs];
+  int L[kMaxRepackJobs], GY[kMaxRepackJobs], GX[kMaxRepackJobs];
   int n;
 };
 template <bool UNPACK_ADD>
 __global__ void repack_jobs_kernel(RepackJobs jobs) {
   const int job = blockIdx.y;
-  const int nodes = jobs.nodes[job];
+  const int L = jobs.L[job], GY = jobs.GY[job], GX = jobs.GX[job];
+  const int nodes = L * GY * GX;
   const float* __restrict__ src = jobs.src[job];
   float* __restrict__ dst = jobs.dst[job];
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nodes * 12; i += gridDim.x * blockDim.x) {
-    if (UNPACK_ADD) {  // dst [12][nodes] += src [nodes][12]
-      int ch = i / nodes, node = i - ch * nodes;
-      dst[i] += src[(size_t)node * 12 + ch];
-    } else {           // dst [nodes][12] = src [12][nodes]
+    if (UNPACK_ADD) {  // dst = parameter layout [12][L][GY][GX] += src repack [GY][GX][L][12]
+      int ch = i / nodes, rem = i - ch * nodes;
+      int x = rem % GX, y = (rem / GX) % GY, z = rem / (GX * GY);
+      dst[i] += src[(size_t)bil_node(x, y, z, L, GX) * 12 + ch];
+    } else {           // dst = repack [GY][GX][L][12] = src parameter layout
       int node = i / 12, ch = i - node * 12;
-      dst[i] = src[(size_t)ch * nodes + node];
+      dst[i] = src[bil_param_index(node, ch, L, GY, GX)];
     }
   }
 }
@@ -539,7 +541,10 @@ template <bool UNPACK_ADD>
 static int launch_repack(RepackJobs& jobs, cudaStream_t stream) {
   if (jobs.n == 0) return 0;
   int max_nodes = 0;
-  for (int k = 0; k < jobs.n; ++k) max_nodes = jobs.nodes[k] > max_nodes ? jobs.nodes[k] : max_nodes;
+  for (int k = 0; k < jobs.n; ++k) {
+    int nk = jobs.L[k] * jobs.GY[k] * jobs.GX[k];
+    max_nodes = nk > max_nodes ? nk : max_nodes;
+  }
   dim3 grid(ceil_div((int64_t)max_nodes * 12, 256), jobs.n);
   repack_jobs_kernel<UNPACK_ADD><<<grid, 256, 0, stream>>>(jobs);
   BDS_CHECK_LAUNCH();
@@ -629,7 +634,8 @@ extern "C" int bds_composite_fwd(const bds_render_desc* d, const bds_epilogue_de
       for (int c = 0; c < d->n_cams; ++c) {
         const float* src = host_grids[c * e->bil.n_levels + l];
         if (!src) continue;  // camera outside the band
-        jobs.src[jobs.n] = src; jobs.dst[jobs.n] = base + (size_t)c * nodes * 12; jobs.nodes[jobs.n] = nodes;
+        jobs.src[jobs.n] = src; jobs.dst[jobs.n] = base + (size_t)c * nodes * 12;
+        jobs.L[jobs.n] = e->bil.L[l]; jobs.GY[jobs.n] = e->bil.GY[l]; jobs.GX[jobs.n] = e->bil.GX[l];
         if (++jobs.n == kMaxRepackJobs)
           if (int rc = launch_repack<false>(jobs, stream)) return rc;
       }
@@ -685,7 +691,8 @@ extern "C" int bds_composite_bwd(const bds_render_desc* d, const bds_epilogue_de
       for (int c = 0; c < d->n_cams; ++c) {
         const float* src = host_grids[c * e->bil.n_levels + l];
         if (!src) continue;
-        jobs.src[jobs.n] = src; jobs.dst[jobs.n] = base + (size_t)c * nodes * 12; jobs.nodes[jobs.n] = nodes;
+        jobs.src[jobs.n] = src; jobs.dst[jobs.n] = base + (size_t)c * nodes * 12;
+        jobs.L[jobs.n] = e->bil.L[l]; jobs.GY[jobs.n] = e->bil.GY[l]; jobs.GX[jobs.n] = e->bil.GX[l];
         if (++jobs.n == kMaxRepackJobs)
           if (int rc = launch_repack<false>(jobs, stream)) return rc;
       }
@@ -715,7 +722,8 @@ extern "C" int bds_composite_bwd(const bds_render_desc* d, const bds_epilogue_de
       for (int c = 0; c < d->n_cams; ++c) {
         float* dst = host_v_grids[c * e->bil.n_levels + l];
         if (!dst) continue;
-        jobs.src[jobs.n] = p.bil.v_grid_cl[l] + (size_t)c * nodes * 12; jobs.dst[jobs.n] = dst; jobs.nodes[jobs.n] = nodes;
+        jobs.src[jobs.n] = p.bil.v_grid_cl[l] + (size_t)c * nodes * 12; jobs.dst[jobs.n] = dst;
+        jobs.L[jobs.n] = e->bil.L[l]; jobs.GY[jobs.n] = e->bil.GY[l]; jobs.GX[jobs.n] = e->bil.GX[l];
         if (++jobs.n == kMaxRepackJobs)
           if (int rc = launch_repack<true>(jobs, stream)) return rc;
       }

@@ -136,3 +136,37 @@ def test_tv_loss_matches_oracle():
     tv.backward()
     assert abs(float(tv) - float(B.total_variation_loss(go))) < 1e-5 * float(B.total_variation_loss(go))
     assert _rel(gc.grad.cpu(), go.grad.float()) < 1e-4
+
+
+def test_generic_slice_arbitrary_xy():
+    """BilateralGrid.forward / slice() with arbitrary xy samples (lib_bilagrid.py:171-230, 317-368)."""
+    from bilateral_driving_b200.bilateral import BilateralGrid, slice as bil_slice
+    from oracle import bilateral_ref as B
+
+    torch.manual_seed(3)
+    bg = BilateralGrid(num=3, grid_X=6, grid_Y=5, grid_W=4).cuda()
+    with torch.no_grad():
+        bg.grids.add_(0.1 * torch.randn_like(bg.grids))
+    n = 500
+    xy = torch.rand(n, 2) * 1.2 - 0.1          # some outside [0,1]: border padding
+    rgb = torch.rand(n, 3) * 1.4 - 0.2
+    idx = torch.full((n, 1), 2, dtype=torch.long)
+    c_rgb = rgb.cuda().requires_grad_(True)
+    out = bil_slice(bg, xy.cuda(), c_rgb, idx.cuda())
+    G = torch.randn(n, 3, 4)
+    (out["rgb_affine_mats"] * G.cuda()).sum().backward()
+    # oracle
+    g = bg.grids[2].detach().cpu().double().requires_grad_(True)
+    o_rgb = rgb.double().requires_grad_(True)
+    fx = xy[:, 0].double() * 5
+    fy = xy[:, 1].double() * 4
+    fz = B.luma_of(o_rgb) * 3
+    ref = B.trilerp(g, fx, fy, fz).reshape(n, 3, 4)
+    (ref * G.double()).sum().backward()
+    assert (out["rgb_affine_mats"].detach().cpu() - ref.detach().float()).abs().max() < 1e-5
+    ref_rgb = (ref[..., :3] @ o_rgb[..., None])[..., 0] + ref[..., 3]
+    assert (out["rgb"].detach().cpu() - ref_rgb.detach().float()).abs().max() < 1e-5
+    assert _rel(bg.grids.grad[2].cpu(), g.grad.float()) < 1e-3
+    amb = ((fz.detach() - fz.detach().round()).abs() < 1e-4)
+    keep = (~amb)[:, None].float()
+    assert _rel(c_rgb.grad.cpu() * keep, o_rgb.grad.float() * keep) < 1e-3

@@ -167,7 +167,7 @@ def test_resize_taps_and_trilinear_stencil(hc):
     for (fx, fy, fz) in ((2.3, 1.7, 0.4), (-1.0, 9.0, 3.0), (5.0, 4.0, 2.999), (0.0, 0.0, -0.5)):
         nodes = (C.c_int * 8)(); w = (C.c_float * 8)()
         inside = hc.hc_tri(C.c_float(fx), C.c_float(fy), C.c_float(fz), 4, 5, 6, nodes, w)
-        flat = g.reshape(12, -1)
+        flat = g.permute(0, 2, 3, 1).reshape(12, -1)  # product repack order [GY][GX][L]
         ours = sum(flat[:, nodes[k]] * w[k] for k in range(8))
         ref = B.trilerp(g, torch.tensor(fx).double(), torch.tensor(fy).double(), torch.tensor(fz).double())
         assert (ours - ref).abs().max() < 1e-5
