@@ -7,47 +7,57 @@ namespace bds {
 
 constexpr unsigned kFull = 0xffffffffu;
 
-// Grid-node gradients of one tile land in a handful of lattice cells (a 16x16 tile spans a fraction
-// of a grid cell at 1080p).  Instead of 96 global reductions per pixel per level:
+// Grid-node gradients of one tile land in a handful of lattice nodes (a 16x16 tile spans a fraction
+// of a grid cell at 1080p).  They are accumulated in shared memory and leave as one global reduction
+// per touched (node, channel) per tile instead of 96 per pixel per level:
 //   1. every thread stages its pixel (vA[12], 4 xy-corner weights, 2 z weights) at a position given by
-//      a counting sort on its cell key (z0, oy, ox) relative to the tile's first cell (integer shared
-//      atomics are native; pixels whose cell is more than one cell away from it - tiny images / huge
-//      grids - scatter straight to global memory instead);
+//      a counting sort on its cell key (z0, oy, ox) inside a 3x3x(L+1)-node window (integer shared
+//      atomics are native; pixels whose cell falls outside the window - tiny images / huge grids -
+//      scatter straight to global memory instead);
 //   2. the 16 half-warps take equal slices of the sorted list; 12 lanes (4 xy-corners x 3 channel
-//      quads) accumulate runs of equal key in REGISTERS and flush each run with 8 fire-and-forget
-//      global reductions of 12 lanes (48 contiguous bytes) - ~(16 + #cells) flushes per tile and level.
-// No shared-memory fp32 atomics (CAS loops), no window to zero or drain, deterministic work split.
-constexpr int kWinNodes = 3;                   // cells considered: offsets 0..1 from the tile's first cell
+//      quads) accumulate runs of equal key in REGISTERS and flush a run with a few shared atomic adds
+//      (fp32 shared atomics are CAS loops, so they are kept to run boundaries: <= ~2 per half-warp);
+//   3. the window is flushed to global memory with one reduction per touched (node, channel).
+constexpr int kWinNodes = 3;                   // window is kWinNodes x kWinNodes lattice nodes in xy
 constexpr int kWinMaxL = 16;
-constexpr int kStageFloats = 20;               // per pixel: vA[12] | wxy[4] | wz0, wz1, key, pad
-constexpr int kWinKeys = 2 * 2 * kWinMaxL;     // (oy, ox, z0) cell keys
-constexpr size_t kBwdSmemBil = (size_t)(256 * kStageFloats) * sizeof(float) + 2 * 96 * sizeof(int);
+constexpr int kStageFloats = 20;               // per pixel: vA[12] | wxy[4] | wz0, wz1, base, pad
+constexpr int kWinFloats = kWinNodes * kWinNodes * (kWinMaxL + 1) * 12;
+constexpr int kWinKeys = kWinNodes * kWinNodes * kWinMaxL;         // 144 cell keys
+constexpr size_t kBwdSmemBil = (size_t)(256 * kStageFloats + kWinFloats) * sizeof(float) + 2 * 160 * sizeof(int);
 
 BDS_D void level_grad_accumulate(float* smem, const Tri& t, const float vAff[12], bool valid, int tile_x0,
                                  int tile_y0, int W, int H, int L, int GY, int GX, float* __restrict__ v_grid) {
   float* stage = smem;
-  int* hist = reinterpret_cast<int*>(smem + 256 * kStageFloats);  // [96] counts -> start offsets
-  int* misc = hist + 96;                                          // [0] = number of staged pixels
-  // first cell of the tile (uniform over the block)
+  float* win = smem + 256 * kStageFloats;
+  int* hist = reinterpret_cast<int*>(win + kWinFloats);  // [160] counts -> start offsets
+  int* misc = hist + 160;                                // [0] = number of staged pixels
+  // window origin = cell of the tile's first pixel (uniform over the block)
   const float fx0 = fminf(fmaxf(lattice_coord(tile_x0, W, GX), 0.f), (float)(GX - 1));
   const float fy0 = fminf(fmaxf(lattice_coord(tile_y0, H, GY), 0.f), (float)(GY - 1));
   const int nx0 = (int)floorf(fx0), ny0 = (int)floorf(fy0);
+  const bool use_win = L <= kWinMaxL;
+  const int slab = kWinNodes * kWinNodes * 12;           // floats per z slab
+  const int per_win = slab * (L + 1);                    // + one dummy slab so z0 + 1 is always in range
   const int ox = t.x0 - nx0, oy = t.y0 - ny0;
-  const bool in_win = L <= kWinMaxL && ox >= 0 && ox < 2 && oy >= 0 && oy < 2;
+  const bool in_win = use_win && ox >= 0 && ox + 1 < kWinNodes && oy >= 0 && oy + 1 < kWinNodes;
   if (valid && !in_win) tri_scatter(v_grid, t, vAff);    // rare: straight to global memory
-  if (L > kWinMaxL) return;                              // uniform over the block
-  if (threadIdx.x < 96) hist[threadIdx.x] = 0;
+  if (!use_win) return;                                  // uniform over the block
+  {
+    float4* w4 = reinterpret_cast<float4*>(win);
+    for (int i = threadIdx.x; i < per_win / 4; i += 256) w4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (threadIdx.x < 160) hist[threadIdx.x] = 0;
+  }
   __syncthreads();
   // ---- counting sort by cell key
   const bool staged = valid && in_win;
-  const int key = staged ? (t.z0 * 2 + oy) * 2 + ox : 0;
+  const int key = staged ? (t.z0 * kWinNodes + oy) * kWinNodes + ox : 0;
   int rank = 0;
   if (staged) rank = atomicAdd(&hist[key], 1);
   __syncthreads();
-  if (threadIdx.x < 32) {  // exclusive scan of 96 counters: 3 per lane
-    int v[3], s = 0;
+  if (threadIdx.x < 32) {  // exclusive scan of 160 counters: 5 per lane
+    int v[5], s = 0;
 #pragma unroll
-    for (int k = 0; k < 3; ++k) { v[k] = hist[threadIdx.x * 3 + k]; s += v[k]; }
+    for (int k = 0; k < 5; ++k) { v[k] = hist[threadIdx.x * 5 + k]; s += v[k]; }
     int inc = s;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -56,7 +66,7 @@ BDS_D void level_grad_accumulate(float* smem, const Tri& t, const float vAff[12]
     }
     int ex = inc - s;
 #pragma unroll
-    for (int k = 0; k < 3; ++k) { hist[threadIdx.x * 3 + k] = ex; ex += v[k]; }
+    for (int k = 0; k < 5; ++k) { hist[threadIdx.x * 5 + k] = ex; ex += v[k]; }
     if (threadIdx.x == 31) misc[0] = inc;
   }
   __syncthreads();
@@ -67,7 +77,7 @@ BDS_D void level_grad_accumulate(float* smem, const Tri& t, const float vAff[12]
     sp[1] = make_float4(vAff[4], vAff[5], vAff[6], vAff[7]);
     sp[2] = make_float4(vAff[8], vAff[9], vAff[10], vAff[11]);
     sp[3] = make_float4(wx0 * wy0, t.wx1 * wy0, wx0 * t.wy1, t.wx1 * t.wy1);
-    sp[4] = make_float4(1.f - t.wz1, t.dz != 0 ? t.wz1 : 0.f, __int_as_float(key), 0.f);
+    sp[4] = make_float4(1.f - t.wz1, t.dz != 0 ? t.wz1 : 0.f, __int_as_float(key * 12), 0.f);
   }
   __syncthreads();
   {
@@ -76,42 +86,38 @@ BDS_D void level_grad_accumulate(float* smem, const Tri& t, const float vAff[12]
     const int hw = threadIdx.x >> 4, l16 = threadIdx.x & 15;
     const int per = (n_staged + 15) >> 4;
     const int p0 = hw * per, p1 = min(n_staged, p0 + per);
+    const bool worker = l16 < 12;
     const int corner = l16 / 3, quad = l16 - corner * 3;
-    const int dx = corner & 1, dy = corner >> 1;
+    const int coff = ((corner >> 1) * kWinNodes + (corner & 1)) * 12 + quad * 4;  // (dy, dx) node + channel quad
     float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
     int cur = -1;
-    if (l16 < 12) {
+    if (worker) {
       for (int px = p0; px <= p1; ++px) {
-        int k = -2;
+        int base = -2;
         float4 va = make_float4(0.f, 0.f, 0.f, 0.f), m = va;
         float wc = 0.f;
         if (px < p1) {
           const float4* sp = reinterpret_cast<const float4*>(stage + px * kStageFloats);
           m = sp[4];
-          k = __float_as_int(m.z);
+          base = __float_as_int(m.z);
           va = sp[quad];
           wc = stage[px * kStageFloats + 12 + corner];
         }
-        if (k != cur) {  // run boundary (or end of slice): flush the registers
+        if (base != cur) {  // run boundary (or end of slice): flush the registers
           if (cur >= 0) {
-            const int z0 = cur >> 2, gy = ny0 + ((cur >> 1) & 1) + dy, gx = nx0 + (cur & 1) + dx;
-            if (gx < GX && gy < GY) {  // a clamped corner carries weight exactly 0
-              float* c0 = v_grid + (size_t)bil_node(gx, gy, z0, L, GX) * 12 + quad * 4;
-              if (a0.x != 0.f) red_add(c0, a0.x);
-              if (a0.y != 0.f) red_add(c0 + 1, a0.y);
-              if (a0.z != 0.f) red_add(c0 + 2, a0.z);
-              if (a0.w != 0.f) red_add(c0 + 3, a0.w);
-              if (z0 + 1 < L) {
-                if (a1.x != 0.f) red_add(c0 + 12, a1.x);
-                if (a1.y != 0.f) red_add(c0 + 13, a1.y);
-                if (a1.z != 0.f) red_add(c0 + 14, a1.z);
-                if (a1.w != 0.f) red_add(c0 + 15, a1.w);
-              }
-            }
+            float* c0 = win + cur + coff;
+            if (a0.x != 0.f) atomicAdd(c0, a0.x);
+            if (a0.y != 0.f) atomicAdd(c0 + 1, a0.y);
+            if (a0.z != 0.f) atomicAdd(c0 + 2, a0.z);
+            if (a0.w != 0.f) atomicAdd(c0 + 3, a0.w);
+            if (a1.x != 0.f) atomicAdd(c0 + slab, a1.x);
+            if (a1.y != 0.f) atomicAdd(c0 + slab + 1, a1.y);
+            if (a1.z != 0.f) atomicAdd(c0 + slab + 2, a1.z);
+            if (a1.w != 0.f) atomicAdd(c0 + slab + 3, a1.w);
           }
           a0 = make_float4(0.f, 0.f, 0.f, 0.f);
           a1 = a0;
-          cur = k;
+          cur = base;
         }
         const float w0 = wc * m.x, w1 = wc * m.y;
         a0.x = fmaf(w0, va.x, a0.x); a0.y = fmaf(w0, va.y, a0.y); a0.z = fmaf(w0, va.z, a0.z); a0.w = fmaf(w0, va.w, a0.w);
@@ -120,6 +126,27 @@ BDS_D void level_grad_accumulate(float* smem, const Tri& t, const float vAff[12]
     }
   }
   __syncthreads();
+  {
+    const int n_out4 = slab * L / 4;  // float4 entries; a float4 never straddles a node (12 floats per node)
+    const float4* win4 = reinterpret_cast<const float4*>(win);
+    for (int e = threadIdx.x; e < n_out4; e += 256) {
+      const float4 v = win4[e];
+      if (v.x != 0.f || v.y != 0.f || v.z != 0.f || v.w != 0.f) {
+        const int node = e / 3, ch0 = (e - node * 3) * 4;
+        const int nx = node % kWinNodes, ny = (node / kWinNodes) % kWinNodes, z = node / (kWinNodes * kWinNodes);
+        const int gx = nx0 + nx, gy = ny0 + ny;
+        if (gx < GX && gy < GY) {
+          float* dst = v_grid + (size_t)bil_node(gx, gy, z, L, GX) * 12 + ch0;
+          if (v.x != 0.f) red_add(dst, v.x);
+          if (v.y != 0.f) red_add(dst + 1, v.y);
+          if (v.z != 0.f) red_add(dst + 2, v.z);
+          if (v.w != 0.f) red_add(dst + 3, v.w);
+        }
+      }
+    }
+  }
+  __syncthreads();
 }
+
 
 }  // namespace bds
