@@ -25,28 +25,8 @@ constexpr int kWinFloats = kWinNodes * kWinNodes * (kWinMaxL + 1) * 12;
 constexpr int kWinKeys = kWinNodes * kWinNodes * kWinMaxL;         // 144 cell keys
 constexpr size_t kBwdSmemBil = (size_t)(256 * kStageFloats + kWinFloats) * sizeof(float) + 2 * 160 * sizeof(int);
 
-// shared-memory add of 4 floats (16-byte aligned) as two 64-bit CAS loops (fp32 shared atomics are CAS
-// loops anyway; pairing halves their number)
-BDS_D void smem_add_f2(float* addr, float x, float y) {
-  if (x == 0.f && y == 0.f) return;
-  unsigned long long* p = reinterpret_cast<unsigned long long*>(addr);
-  unsigned long long old = *p, assumed;
-  do {
-    assumed = old;
-    float lo = __uint_as_float((unsigned)(assumed & 0xffffffffull)) + x;
-    float hi = __uint_as_float((unsigned)(assumed >> 32)) + y;
-    unsigned long long desired = ((unsigned long long)__float_as_uint(hi) << 32) | (unsigned long long)__float_as_uint(lo);
-    old = atomicCAS(p, assumed, desired);
-  } while (old != assumed);
-}
-BDS_D void smem_add_f4(float* addr, const float4& v) {
-  smem_add_f2(addr, v.x, v.y);
-  smem_add_f2(addr + 2, v.z, v.w);
-}
-
 BDS_D void level_grad_accumulate(float* smem, const Tri& t, const float vAff[12], bool valid, int tile_x0,
-                                 int tile_y0, int W, int H, int L, int GY, int GX, float* __restrict__ v_grid,
-                                 int debug = 0) {
+                                 int tile_y0, int W, int H, int L, int GY, int GX, float* __restrict__ v_grid) {
   float* stage = smem;
   float* win = smem + 256 * kStageFloats;
   int* hist = reinterpret_cast<int*>(win + kWinFloats);  // [160] counts -> start offsets
@@ -70,7 +50,7 @@ BDS_D void level_grad_accumulate(float* smem, const Tri& t, const float vAff[12]
   __syncthreads();
   // ---- counting sort by cell key
   const bool staged = valid && in_win;
-  const int key = staged ? (oy * 2 + ox) * L + t.z0 : 0;  // guidance cell fastest: consecutive runs share a slab
+  const int key = staged ? (t.z0 * kWinNodes + oy) * kWinNodes + ox : 0;
   int rank = 0;
   if (staged) rank = atomicAdd(&hist[key], 1);
   __syncthreads();
@@ -97,7 +77,7 @@ BDS_D void level_grad_accumulate(float* smem, const Tri& t, const float vAff[12]
     sp[1] = make_float4(vAff[4], vAff[5], vAff[6], vAff[7]);
     sp[2] = make_float4(vAff[8], vAff[9], vAff[10], vAff[11]);
     sp[3] = make_float4(wx0 * wy0, t.wx1 * wy0, wx0 * t.wy1, t.wx1 * t.wy1);
-    sp[4] = make_float4(1.f - t.wz1, t.dz != 0 ? t.wz1 : 0.f, __int_as_float(key), 0.f);
+    sp[4] = make_float4(1.f - t.wz1, t.dz != 0 ? t.wz1 : 0.f, __int_as_float(key * 12), 0.f);
   }
   __syncthreads();
   {
@@ -111,32 +91,33 @@ BDS_D void level_grad_accumulate(float* smem, const Tri& t, const float vAff[12]
     const int coff = ((corner >> 1) * kWinNodes + (corner & 1)) * 12 + quad * 4;  // (dy, dx) node + channel quad
     float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
     int cur = -1;
-    if (worker && !(debug & 8)) {
+    if (worker) {
       for (int px = p0; px <= p1; ++px) {
-        int k = -2;
+        int base = -2;
         float4 va = make_float4(0.f, 0.f, 0.f, 0.f), m = va;
         float wc = 0.f;
         if (px < p1) {
           const float4* sp = reinterpret_cast<const float4*>(stage + px * kStageFloats);
           m = sp[4];
-          k = __float_as_int(m.z);
+          base = __float_as_int(m.z);
           va = sp[quad];
           wc = stage[px * kStageFloats + 12 + corner];
         }
-        if (k != cur) {  // run boundary (or end of slice): flush the registers
-          bool carry = false;
+        if (base != cur) {  // run boundary (or end of slice): flush the registers
           if (cur >= 0) {
-            const int cls = cur / L, z0 = cur - cls * L;
-            float* c0 = win + ((z0 * kWinNodes + (cls >> 1)) * kWinNodes + (cls & 1)) * 12 + coff;
-            smem_add_f4(c0, a0);
-            // the next run is the next guidance cell of the same xy class: its lower slab is this run's
-            // upper slab, so the upper partial sums simply become its lower ones (no flush)
-            carry = (k == cur + 1) && (z0 + 1 < L);
-            if (!carry) smem_add_f4(c0 + slab, a1);
+            float* c0 = win + cur + coff;
+            if (a0.x != 0.f) atomicAdd(c0, a0.x);
+            if (a0.y != 0.f) atomicAdd(c0 + 1, a0.y);
+            if (a0.z != 0.f) atomicAdd(c0 + 2, a0.z);
+            if (a0.w != 0.f) atomicAdd(c0 + 3, a0.w);
+            if (a1.x != 0.f) atomicAdd(c0 + slab, a1.x);
+            if (a1.y != 0.f) atomicAdd(c0 + slab + 1, a1.y);
+            if (a1.z != 0.f) atomicAdd(c0 + slab + 2, a1.z);
+            if (a1.w != 0.f) atomicAdd(c0 + slab + 3, a1.w);
           }
-          a0 = carry ? a1 : make_float4(0.f, 0.f, 0.f, 0.f);
-          a1 = make_float4(0.f, 0.f, 0.f, 0.f);
-          cur = k;
+          a0 = make_float4(0.f, 0.f, 0.f, 0.f);
+          a1 = a0;
+          cur = base;
         }
         const float w0 = wc * m.x, w1 = wc * m.y;
         a0.x = fmaf(w0, va.x, a0.x); a0.y = fmaf(w0, va.y, a0.y); a0.z = fmaf(w0, va.z, a0.z); a0.w = fmaf(w0, va.w, a0.w);
@@ -146,7 +127,7 @@ BDS_D void level_grad_accumulate(float* smem, const Tri& t, const float vAff[12]
   }
   __syncthreads();
   {
-    const int n_out4 = (debug & 4) ? 0 : slab * L / 4;  // float4 entries; a float4 never straddles a node
+    const int n_out4 = slab * L / 4;  // float4 entries; a float4 never straddles a node (12 floats per node)
     const float4* win4 = reinterpret_cast<const float4*>(win);
     for (int e = threadIdx.x; e < n_out4; e += 256) {
       const float4 v = win4[e];

@@ -84,7 +84,6 @@ struct CompParams {
   // backward only
   const float *v_rgb, *v_rgbg, *v_depth, *v_alpha;
   float *v_splats, *v_sky, *v_backgrounds;
-  int debug;  // profiling aid (BDS_DEBUG_SKIP): bit0 skip grid-gradient accumulation, bit1 skip the walk
 };
 
 struct TileGeom {
@@ -360,9 +359,8 @@ __global__ void __launch_bounds__(256, 4) composite_bwd_kernel(CompParams p) {
           for (int k = 0; k < 12; ++k) sdot = fmaf(vAff[k], dAdz[k], sdot);
           v_lum += sdot * (float)(p.bil.L[l] - 1);
         }
-        if (!(p.debug & 1))
-          level_grad_accumulate(reinterpret_cast<float*>(dyn_smem), t, vAff, g.inside, tile_x0, tile_y0, p.W, p.H,
-                                p.bil.L[l], p.bil.GY[l], p.bil.GX[l], p.bil.v_grid_cl[l] + goff, p.debug);
+        level_grad_accumulate(reinterpret_cast<float*>(dyn_smem), t, vAff, g.inside, tile_x0, tile_y0, p.W, p.H,
+                              p.bil.L[l], p.bil.GY[l], p.bil.GX[l], p.bil.v_grid_cl[l] + goff);
       }
     }
     gr += v_lum * kLumaR; gg2 += v_lum * kLumaG; gb += v_lum * kLumaB;
@@ -402,7 +400,7 @@ __global__ void __launch_bounds__(256, 4) composite_bwd_kernel(CompParams p) {
   for (int w = 0; w < 8; ++w) block_last = max(block_last, s_last[w]);
   const int warp_last = wl;
 
-  const int n = (block_last < 0 || (p.debug & 2)) ? 0 : block_last - g.start + 1;
+  const int n = (block_last < 0) ? 0 : block_last - g.start + 1;
   const int nchunks = (n + kChunk - 1) / kChunk;
   // chunks are walked from the back: walk index q = 0.. corresponds to chunk k = nchunks-1-q
   int issued = 0;
@@ -680,7 +678,6 @@ extern "C" int bds_composite_bwd(const bds_render_desc* d, const bds_epilogue_de
   p.out_alpha = const_cast<float*>(out_alpha); p.last_ids = const_cast<int32_t*>(last_ids);
   p.v_rgb = v_rgb; p.v_rgbg = v_rgb_gauss; p.v_depth = v_depth; p.v_alpha = v_alpha;
   p.v_splats = v_splats; p.v_sky = v_sky; p.v_backgrounds = v_backgrounds;
-  { const char* dbg = getenv("BDS_DEBUG_SKIP"); p.debug = dbg ? atoi(dbg) : 0; }
   CompWorkspace w = carve_comp(d, e);
   if (e->mode == 2) {
     BDS_REQUIRE(host_grids && host_v_grids && workspace, "composite_bwd: mode 2 needs grids, v_grids and workspace");
