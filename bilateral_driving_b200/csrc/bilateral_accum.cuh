@@ -15,15 +15,19 @@ constexpr unsigned kFull = 0xffffffffu;
 //      atomics are native; pixels whose cell falls outside the window - tiny images / huge grids -
 //      scatter straight to global memory instead);
 //   2. the 16 half-warps take equal slices of the sorted list; 12 lanes (4 xy-corners x 3 channel
-//      quads) accumulate runs of equal key in REGISTERS and flush a run with a few shared atomic adds
-//      (fp32 shared atomics are CAS loops, so they are kept to run boundaries: <= ~2 per half-warp);
+//      quads) accumulate runs of equal key in REGISTERS.  A run that ends inside a slice goes to the
+//      window with shared atomic adds (fp32 shared atomics are CAS loops: kept rare); the LAST run of
+//      each slice - all slices end together, mostly on the same cells - is parked in a per-half-warp
+//      slot with plain stores and 192 threads merge equal-key neighbours into the window afterwards;
 //   3. the window is flushed to global memory with one reduction per touched (node, channel).
 constexpr int kWinNodes = 3;                   // window is kWinNodes x kWinNodes lattice nodes in xy
 constexpr int kWinMaxL = 16;
 constexpr int kStageFloats = 20;               // per pixel: vA[12] | wxy[4] | wz0, wz1, base, pad
 constexpr int kWinFloats = kWinNodes * kWinNodes * (kWinMaxL + 1) * 12;
 constexpr int kWinKeys = kWinNodes * kWinNodes * kWinMaxL;         // 144 cell keys
-constexpr size_t kBwdSmemBil = (size_t)(256 * kStageFloats + kWinFloats) * sizeof(float) + 2 * 160 * sizeof(int);
+constexpr int kSlotFloats = 16 * 96;  // last-run register sums of the 16 half-warps: 12 lanes x (a0 | a1)
+constexpr size_t kBwdSmemBil =
+    (size_t)(256 * kStageFloats + kWinFloats + kSlotFloats) * sizeof(float) + 2 * 160 * sizeof(int);
 
 BDS_D void level_grad_accumulate(float* smem, const Tri& t, const float vAff[12], bool valid, int tile_x0,
                                  int tile_y0, int W, int H, int L, int GY, int GX, float* __restrict__ v_grid) {
@@ -31,6 +35,8 @@ BDS_D void level_grad_accumulate(float* smem, const Tri& t, const float vAff[12]
   float* win = smem + 256 * kStageFloats;
   int* hist = reinterpret_cast<int*>(win + kWinFloats);  // [160] counts -> start offsets
   int* misc = hist + 160;                                // [0] = number of staged pixels
+  int* slot_key = misc + 8;                              // [16] window offset of each half-warp's last run (-1: none)
+  float* slot_val = reinterpret_cast<float*>(hist + 320);  // [16][12 lanes][a0 | a1]
   // window origin = cell of the tile's first pixel (uniform over the block)
   const float fx0 = fminf(fmaxf(lattice_coord(tile_x0, W, GX), 0.f), (float)(GX - 1));
   const float fy0 = fminf(fmaxf(lattice_coord(tile_y0, H, GY), 0.f), (float)(GY - 1));
@@ -92,18 +98,13 @@ BDS_D void level_grad_accumulate(float* smem, const Tri& t, const float vAff[12]
     float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
     int cur = -1;
     if (worker) {
-      for (int px = p0; px <= p1; ++px) {
-        int base = -2;
-        float4 va = make_float4(0.f, 0.f, 0.f, 0.f), m = va;
-        float wc = 0.f;
-        if (px < p1) {
-          const float4* sp = reinterpret_cast<const float4*>(stage + px * kStageFloats);
-          m = sp[4];
-          base = __float_as_int(m.z);
-          va = sp[quad];
-          wc = stage[px * kStageFloats + 12 + corner];
-        }
-        if (base != cur) {  // run boundary (or end of slice): flush the registers
+      for (int px = p0; px < p1; ++px) {
+        const float4* sp = reinterpret_cast<const float4*>(stage + px * kStageFloats);
+        const float4 m = sp[4];
+        const int base = __float_as_int(m.z);
+        const float4 va = sp[quad];
+        const float wc = stage[px * kStageFloats + 12 + corner];
+        if (base != cur) {  // run boundary inside the slice: flush the registers
           if (cur >= 0) {
             float* c0 = win + cur + coff;
             if (a0.x != 0.f) atomicAdd(c0, a0.x);
@@ -122,6 +123,33 @@ BDS_D void level_grad_accumulate(float* smem, const Tri& t, const float vAff[12]
         const float w0 = wc * m.x, w1 = wc * m.y;
         a0.x = fmaf(w0, va.x, a0.x); a0.y = fmaf(w0, va.y, a0.y); a0.z = fmaf(w0, va.z, a0.z); a0.w = fmaf(w0, va.w, a0.w);
         a1.x = fmaf(w1, va.x, a1.x); a1.y = fmaf(w1, va.y, a1.y); a1.z = fmaf(w1, va.z, a1.z); a1.w = fmaf(w1, va.w, a1.w);
+      }
+      // every slice ends at about the same time and mostly on the same few cells: instead of 16 x 96
+      // contended shared atomics the last runs are parked in per-half-warp slots ...
+      float4* sv = reinterpret_cast<float4*>(slot_val + (hw * 12 + l16) * 8);
+      sv[0] = a0;
+      sv[1] = a1;
+    }
+    if (l16 == 0) slot_key[hw] = cur;
+  }
+  __syncthreads();
+  if (threadIdx.x < 192) {
+    // ... and merged here: slices are contiguous pieces of a sorted list, so equal last keys sit in
+    // consecutive slots; thread (lane, value) sums each group and adds it to the window once
+    const int j = threadIdx.x % 96, h0 = (threadIdx.x / 96) * 8;
+    const int lane12 = j >> 3, v = j & 7;
+    const int corner = lane12 / 3, quad = lane12 - corner * 3;
+    const int off = ((corner >> 1) * kWinNodes + (corner & 1)) * 12 + quad * 4 + (v >> 2) * slab + (v & 3);
+    float sum = 0.f;
+    int kcur = slot_key[h0];
+#pragma unroll
+    for (int h = 0; h < 8; ++h) {
+      sum += slot_val[(h0 + h) * 96 + j];
+      const int knext = (h < 7) ? slot_key[h0 + h + 1] : -2;
+      if (knext != kcur) {
+        if (kcur >= 0 && sum != 0.f) atomicAdd(win + kcur + off, sum);
+        sum = 0.f;
+        kcur = knext;
       }
     }
   }
