@@ -23,6 +23,7 @@
 #include <stdlib.h>
 
 #include "bilateral_accum.cuh"
+#include "tma.cuh"
 #include "projection_math.cuh"
 
 namespace bds {
@@ -30,37 +31,6 @@ namespace bds {
 constexpr int kChunk = 128;                 // records per stage
 constexpr int kStages = 3;
 constexpr int kRecBytes = 48;
-
-// ---- mbarrier / TMA bulk copy (PTX) -----------------------------------------------------------
-BDS_D uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-BDS_D void mbar_init(uint64_t* bar, unsigned count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-BDS_D void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-BDS_D void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-BDS_D void bulk_g2s(void* dst, const void* src, unsigned bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   smem_u32(dst)),
-               "l"(src), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
-BDS_D bool mbar_try_wait(uint64_t* bar, unsigned parity) {
-  unsigned ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-BDS_D void mbar_wait(uint64_t* bar, unsigned parity) {
-  // bounded spin: a byte-count mismatch would otherwise hang the GPU; trap instead
-  for (unsigned it = 0; it < (1u << 24); ++it)
-    if (mbar_try_wait(bar, parity)) return;
-  __trap();
-}
 
 // ---- parameters ----------------------------------------------------------------------------------
 struct FusedBil {       // per-camera bilateral chain, full-resolution guidance
@@ -127,6 +97,9 @@ BDS_D void fused_chain_fwd(const FusedBil& b, int cam, int H, int W, int i, int 
   }
 }
 
+#ifdef BDS_STATS
+__device__ unsigned long long g_stats[16];
+#endif
 // =================================================================================================
 // forward
 // =================================================================================================
@@ -166,6 +139,9 @@ __global__ void __launch_bounds__(256, 5) composite_fwd_kernel(CompParams p) {
     const int st = k % kStages;
     mbar_wait(&bars[st], (k / kStages) & 1);
     waited = k + 1;
+#ifdef BDS_STATS
+    int st_cA = 0, st_cB = 0, st_q0 = 0, st_q1 = 0, st_q2 = 0, st_q3 = 0;
+#endif
     if (!warp_done) {
       const int cnt = min(kChunk, n - k * kChunk);
       const float4* sr = &srec[st][0];
@@ -179,6 +155,34 @@ __global__ void __launch_bounds__(256, 5) composite_fwd_kernel(CompParams p) {
           hit = !(s > r2.w + (kLog2_255 + kCullMargin));
         }
         unsigned m = __ballot_sync(kFull, hit);
+#ifdef BDS_STATS
+        {
+          unsigned q[4];
+          for (int qi = 0; qi < 4; ++qi) {
+            bool h = false;
+            if (j < cnt) {
+              float4 r0 = sr[j * 3], r1 = sr[j * 3 + 1], r2 = sr[j * 3 + 2];
+              float x0 = g.wx0 + (qi & 1) * 4 + 0.5f, y0 = g.wy0 + (qi >> 1) * 2 + 0.5f;
+              float s = min_sigma_rect(r0.x, r0.y, r0.z, r0.w, r1.x, x0, x0 + 3.f, y0, y0 + 1.f);
+              h = !(s > r2.w + (kLog2_255 + kCullMargin));
+            }
+            q[qi] = __ballot_sync(kFull, h);
+          }
+          unsigned mA = q[0] | q[2], mB = q[1] | q[3];
+          int pa = __popc(mA), pb = __popc(mB);
+          int p0 = __popc(q[0]), p1 = __popc(q[1]), p2 = __popc(q[2]), p3 = __popc(q[3]);
+          st_cA += pa; st_cB += pb; st_q0 += p0; st_q1 += p1; st_q2 += p2; st_q3 += p3;
+          if (lane == 0) {
+            atomicAdd(&g_stats[0], 1ull);
+            atomicAdd(&g_stats[1], (unsigned long long)__popc(m));
+            atomicAdd(&g_stats[2], (unsigned long long)max(pa, pb));
+            atomicAdd(&g_stats[4], (unsigned long long)max(max(p0, p1), max(p2, p3)));
+            atomicAdd(&g_stats[6], (unsigned long long)(pa + pb));
+            atomicAdd(&g_stats[7], (unsigned long long)(p0 + p1 + p2 + p3));
+            atomicAdd(&g_stats[9], (unsigned long long)__popc(mA | mB));
+          }
+        }
+#endif
         while (m) {
           int jj = base + __ffs(m) - 1;
           m &= m - 1;
@@ -188,6 +192,12 @@ __global__ void __launch_bounds__(256, 5) composite_fwd_kernel(CompParams p) {
           float e = fmaf(-dx, fmaf(r0.w, dy, r0.z * dx), r2.w);
           e = fmaf(-(r1.x * dy), dy, e);
           float alpha = fminf(kAlphaMax, exp2f(e));
+#ifdef BDS_STATS
+          {
+            unsigned vm = __ballot_sync(kFull, !done && e <= r2.w && e >= -kLog2_255);
+            if (lane == 0) atomicAdd(&g_stats[8], (unsigned long long)__popc(vm));
+          }
+#endif
           if (!done && e <= r2.w && e >= -kLog2_255) {  // sigma' >= 0 and alpha >= 1/255
             float nT = T * (1.f - alpha);
             if (nT <= kTStop) {
@@ -206,6 +216,12 @@ __global__ void __launch_bounds__(256, 5) composite_fwd_kernel(CompParams p) {
         warp_done = __all_sync(kFull, done);
       }
     }
+#ifdef BDS_STATS
+    if (lane == 0) {
+      atomicAdd(&g_stats[3], (unsigned long long)max(st_cA, st_cB));
+      atomicAdd(&g_stats[5], (unsigned long long)max(max(st_q0, st_q1), max(st_q2, st_q3)));
+    }
+#endif
     // every warp is past stage st: it may be refilled; also the block-wide early exit
     int all_done = __syncthreads_and(warp_done ? 1 : 0);
     if (all_done) break;
@@ -734,3 +750,15 @@ extern "C" int bds_composite_bwd(const bds_render_desc* d, const bds_epilogue_de
   }
   return 0;
 }
+
+#ifdef BDS_STATS
+extern "C" int bds_debug_stats(unsigned long long* out, int reset) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out, bds::g_stats, sizeof(unsigned long long) * 16);
+  if (reset) {
+    unsigned long long z[16] = {0};
+    cudaMemcpyToSymbol(bds::g_stats, z, sizeof(z));
+  }
+  return 0;
+}
+#endif

@@ -7,6 +7,7 @@
 // sites models/trainers/base.py:393-408 and models/gaussians/vanilla.py:383-395.
 #include "projection_math.cuh"
 #include "sh_math.cuh"
+#include "tma.cuh"
 
 namespace bds {
 
@@ -48,155 +49,269 @@ BDS_HD void band_rows(const bds_render_desc& d, int tile_h, int c, int& ty0, int
   ty1 = hi - g0;
 }
 
-// One thread per GAUSSIAN; the cameras of the band are walked in a loop so that the parameter loads,
-// the activations and the world covariance are paid once per Gaussian (a Gaussian is visible in ~1 of
-// the 6 rig cameras) and every lane of a warp has work.
-__global__ void __launch_bounds__(256) project_fwd_kernel(ProjParams p) {
-  __shared__ int s_run[8][32];
+// Two phases per block of 256 Gaussians.
+//  A. one thread per GAUSSIAN: parameters, activations and the world covariance are paid once; the
+//     cameras of the band are walked with only the cheap conservative cull (depth range + screen bound).
+//     A Gaussian is visible in ~1 of the 6 rig cameras, so the (Gaussian, camera) pairs that survive are
+//     pushed to a shared-memory queue instead of being processed by the few lanes that own them.
+//  B. one thread per QUEUE ENTRY: full EWA projection, exact tile count, SH colour, packed record.  Every
+//     lane has work; the SH coefficients of the block were staged in shared memory by coalesced loads.
+constexpr int kProjBlock = 256;
+constexpr int kProjCamsPerRound = 8;
+constexpr int kProjGaussFloats = 12;   // mu[3] cov[6] smax opacity pad
+constexpr int kProjCamFloats = 24;     // R[9] t[3] fx fy cx cy | camera position[3] | pad
+constexpr size_t kProjSmemBase = (size_t)kProjBlock * kProjGaussFloats * sizeof(float) +
+                                 (size_t)kProjCamsPerRound * kProjCamFloats * sizeof(float) +
+                                 (size_t)kProjBlock * kProjCamsPerRound * sizeof(uint16_t) + 8 * 32 * sizeof(int) + 32;
+BDS_HD size_t proj_smem_bytes(int sh_floats) { return kProjSmemBase + (size_t)kProjBlock * sh_floats * sizeof(float); }
+
+__global__ void __launch_bounds__(kProjBlock) project_fwd_kernel(ProjParams p, int sh_floats, int sh_bulk_ok) {
+  extern __shared__ __align__(128) unsigned char proj_smem[];
+  const int K3 = sh_floats;  // 3 * sh_K on the SH path, else 0
+  float* s_dc = reinterpret_cast<float*>(proj_smem);                              // [256][3]
+  float* s_rest = s_dc + (K3 > 0 ? kProjBlock * 3 : 0);                           // [256][3 (K - 1)]
+  float* s_gauss = s_rest + (K3 > 0 ? kProjBlock * (K3 - 3) : 0);                 // [256][12]
+  float* s_cam = s_gauss + kProjBlock * kProjGaussFloats;                         // [8][24]
+  int* s_run = reinterpret_cast<int*>(s_cam + kProjCamsPerRound * kProjCamFloats);  // [8 warps][32]
+  int* s_count = s_run + 8 * 32;                                                  // [4]
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_count + 4);                     // SH staging barrier
+  uint16_t* s_queue = reinterpret_cast<uint16_t*>(s_bar + 2);                     // [256 * 8]
+
   const int N = p.d.n_gauss;
   const int lane = threadIdx.x & 31;
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n0 = blockIdx.x * kProjBlock;
+  const int n = n0 + threadIdx.x;
   const bool in_range = n < N;
-  float mu[3] = {0.f, 0.f, 0.f}, cov[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  float smax = 0.f, op_base = 0.f;
+  const int per = K3 - 3;
+
+  // ---- stage the block's SH coefficients (contiguous in global memory) with two bulk copies that
+  // complete on an mbarrier while phase A runs; odd tails / unaligned bases use plain loads
+  const int cnt = min(kProjBlock, N - n0);
+  const bool bulk = K3 > 0 && sh_bulk_ok && (cnt & 3) == 0;
+  if (K3 > 0 && bulk) {
+    if (threadIdx.x == 0) {
+      mbar_init(s_bar, 1);
+      mbar_fence_init();
+      mbar_expect_tx(s_bar, (unsigned)(cnt * K3 * sizeof(float)));
+      bulk_g2s(s_dc, p.fdc + (size_t)n0 * 3, (unsigned)(cnt * 3 * sizeof(float)), s_bar);
+      if (per > 0) bulk_g2s(s_rest, p.frest + (size_t)n0 * per, (unsigned)(cnt * per * sizeof(float)), s_bar);
+    }
+  } else if (K3 > 0) {
+    const float* fdc = p.fdc + (size_t)n0 * 3;
+    for (int i = threadIdx.x; i < cnt * 3; i += kProjBlock) s_dc[i] = __ldg(fdc + i);
+    if (per > 0) {
+      const float* fr = p.frest + (size_t)n0 * per;
+      for (int i = threadIdx.x; i < cnt * per; i += kProjBlock) s_rest[i] = __ldg(fr + i);
+    }
+  }
+  // ---- per-Gaussian parameters
+  float mu[3] = {0.f, 0.f, 0.f}, smax = 0.f;
   if (in_range) {
     mu[0] = p.means[3 * (size_t)n]; mu[1] = p.means[3 * (size_t)n + 1]; mu[2] = p.means[3 * (size_t)n + 2];
     float q[4] = {p.quats[4 * (size_t)n], p.quats[4 * (size_t)n + 1], p.quats[4 * (size_t)n + 2], p.quats[4 * (size_t)n + 3]};
     float s[3] = {p.scales[3 * (size_t)n], p.scales[3 * (size_t)n + 1], p.scales[3 * (size_t)n + 2]};
     if (p.d.raw_params) { s[0] = __expf(s[0]); s[1] = __expf(s[1]); s[2] = __expf(s[2]); }
-    float Rq[9];
+    float Rq[9], cov[6];
     quat_to_rotmat(q, Rq);
     covar_world(Rq, s, cov);
     smax = fmaxf(s[0], fmaxf(s[1], s[2]));
-    op_base = p.opacities[n];
+    float op_base = p.opacities[n];
     if (p.d.raw_params) op_base = sigmoidf(op_base);
+    float4* sg = reinterpret_cast<float4*>(s_gauss + threadIdx.x * kProjGaussFloats);
+    sg[0] = make_float4(mu[0], mu[1], mu[2], cov[0]);
+    sg[1] = make_float4(cov[1], cov[2], cov[3], cov[4]);
+    sg[2] = make_float4(cov[5], smax, op_base, 0.f);
   }
-  for (int c = 0; c < p.d.n_cams; ++c) {
-    int ty0, ty1;
-    band_rows(p.d, p.tile_h, c, ty0, ty1);
-    if (ty1 <= ty0) continue;  // camera outside the band (uniform)
-    const int64_t idx = (int64_t)c * N + n;
-    int n_tiles = 0, radius_i = 0;
-    // ---- phase 1: projection and candidate rectangle ----------------------------------------------
-    bool cand = false;
-    float mx = 0.f, my = 0.f, qa = 0.f, qb = 0.f, qc = 0.f, op = 0.f, sigma_cut = 0.f, lop = 0.f, depth = 0.f;
-    TileRect tr = {0, 0, 0, 0};
-    CamIntr cam;
-    load_cam(p.viewmats, p.Ks, c, cam);
-    if (in_range) {
-      Proj o;
-      if (project_gaussian_cov(mu, cov, smax, cam, p.d.width, p.d.height, p.d.eps2d, p.d.near_plane, p.d.far_plane,
-                               p.d.radius_clip, o)) {
-        radius_i = (int)o.radius;
-        if (p.means2d) { p.means2d[2 * idx] = o.mx; p.means2d[2 * idx + 1] = o.my; }
-        if (p.depths) p.depths[idx] = o.z;
-        if (p.conics) { p.conics[3 * idx] = o.a; p.conics[3 * idx + 1] = o.b; p.conics[3 * idx + 2] = o.c; }
-        if (p.compensations) p.compensations[idx] = o.comp;
-        op = op_base;
-        if (p.d.antialiased) op *= o.comp;
-        mx = o.mx; my = o.my; depth = o.z;
-        qa = 0.5f * kLog2e * o.a; qb = kLog2e * o.b; qc = 0.5f * kLog2e * o.c;
-        lop = __log2f(op);
-        sigma_cut = lop + kLog2_255;  // alpha >= 1/255  <=>  sigma' <= log2(255 o)
-        if (op >= kAlphaMin) {
-          tr = candidate_rect(mx, my, o.radius, qa, qb, qc, sigma_cut, p.tile_w, p.tile_h, ty0, ty1);
-          cand = (tr.x1 > tr.x0) && (tr.y1 > tr.y0);
+
+  for (int c0 = 0; c0 < p.d.n_cams; c0 += kProjCamsPerRound) {
+    const int nc = min(kProjCamsPerRound, p.d.n_cams - c0);
+    __syncthreads();  // previous round's queue and cameras are consumed; (first round) staging is visible
+    if (threadIdx.x < nc) {
+      CamIntr cam;
+      load_cam(p.viewmats, p.Ks, c0 + threadIdx.x, cam);
+      float* sc = s_cam + threadIdx.x * kProjCamFloats;
+#pragma unroll
+      for (int i = 0; i < 9; ++i) sc[i] = cam.R[i];
+      sc[9] = cam.t[0]; sc[10] = cam.t[1]; sc[11] = cam.t[2];
+      sc[12] = cam.fx; sc[13] = cam.fy; sc[14] = cam.cx; sc[15] = cam.cy;
+      // camera position = -R^T t  (vanilla.py:384-385)
+      sc[16] = -(cam.R[0] * cam.t[0] + cam.R[3] * cam.t[1] + cam.R[6] * cam.t[2]);
+      sc[17] = -(cam.R[1] * cam.t[0] + cam.R[4] * cam.t[1] + cam.R[7] * cam.t[2]);
+      sc[18] = -(cam.R[2] * cam.t[0] + cam.R[5] * cam.t[1] + cam.R[8] * cam.t[2]);
+    }
+    if (threadIdx.x == 0) s_count[0] = 0;
+    __syncthreads();
+    // ---- phase A: cheap cull, defaults for the culled pairs, queue for the rest
+    for (int ci = 0; ci < nc; ++ci) {
+      const int c = c0 + ci;
+      int ty0, ty1;
+      band_rows(p.d, p.tile_h, c, ty0, ty1);
+      if (ty1 <= ty0) continue;  // camera outside the band (uniform)
+      const float* sc = s_cam + ci * kProjCamFloats;
+      bool keep = false;
+      if (in_range) {
+        const float x = sc[0] * mu[0] + sc[1] * mu[1] + sc[2] * mu[2] + sc[9];
+        const float y = sc[3] * mu[0] + sc[4] * mu[1] + sc[5] * mu[2] + sc[10];
+        const float z = sc[6] * mu[0] + sc[7] * mu[1] + sc[8] * mu[2] + sc[11];
+        keep = !(z < p.d.near_plane || z > p.d.far_plane) &&
+               !screen_cull(x, y, z, smax, sc[12], sc[13], sc[14], sc[15], p.d.width, p.d.height, p.d.eps2d);
+        if (!keep) {
+          const int64_t idx = (int64_t)c * N + n;
+          if (p.radii) p.radii[idx] = 0;
+          p.tiles_touched[idx] = 0;
+          if (p.slot_of) p.slot_of[idx] = -1;
         }
       }
+      const unsigned km = __ballot_sync(0xffffffffu, keep);
+      if (km) {
+        int base = 0;
+        const int leader = __ffs(km) - 1;
+        if (lane == leader) base = atomicAdd(&s_count[0], __popc(km));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (keep) s_queue[base + __popc(km & ((1u << lane) - 1u))] = (uint16_t)((ci << 8) | threadIdx.x);
+      }
     }
-    // ---- phase 2: exact tile count.  The candidates of the warp's splats form one flat list that the
-    // 32 lanes test 32 at a time (few lanes are visible in any one camera, so per-lane loops would idle).
-    {
-      const int ncand = cand ? (tr.x1 - tr.x0) * (tr.y1 - tr.y0) : 0;
-      const int incl = warp_inclusive_scan_i32(ncand);
-      const int total = __shfl_sync(0xffffffffu, incl, 31);
-      const int excl = incl - ncand;
-      const int rw = tr.x1 - tr.x0;
-      int* run = s_run[threadIdx.x >> 5];
-      run[lane] = 0;
-      __syncwarp();
-      for (int base = 0; base < total; base += 32) {
-        const int wi = min(base + lane, total - 1);
-        const int owner = warp_find_owner(excl, wi);
-        const int local = wi - __shfl_sync(0xffffffffu, excl, owner);
-        const int ow = __shfl_sync(0xffffffffu, rw, owner);
-        const int ox0 = __shfl_sync(0xffffffffu, tr.x0, owner), oy0 = __shfl_sync(0xffffffffu, tr.y0, owner);
-        const float gx = __shfl_sync(0xffffffffu, mx, owner), gy = __shfl_sync(0xffffffffu, my, owner);
-        const float ga = __shfl_sync(0xffffffffu, qa, owner), gb = __shfl_sync(0xffffffffu, qb, owner);
-        const float gc = __shfl_sync(0xffffffffu, qc, owner), gcut = __shfl_sync(0xffffffffu, sigma_cut, owner);
-        bool hit = false;
-        if (base + lane < total) {
-          const int ry = local / ow;
-          hit = tile_hit(gx, gy, ga, gb, gc, gcut, ox0 + local - ry * ow, oy0 + ry, p.d.width, p.d.height);
+    __syncthreads();
+    if (bulk && c0 == 0) mbar_wait(s_bar, 0);  // SH coefficients have landed (waiting again is harmless)
+    // ---- phase B: one queue entry per thread
+    const int n_queue = s_count[0];
+    for (int q0 = 0; q0 < n_queue; q0 += kProjBlock) {
+      const int qi = q0 + threadIdx.x;
+      const bool active = qi < n_queue;
+      const int ent = active ? (int)s_queue[qi] : 0;
+      const int ci = ent >> 8, ln = ent & 255;
+      const int c = c0 + ci, gn = n0 + ln;
+      const int64_t idx = (int64_t)c * N + gn;
+      int ty0, ty1;
+      band_rows(p.d, p.tile_h, c, ty0, ty1);
+      int n_tiles = 0, radius_i = 0;
+      bool cand = false;
+      float mx = 0.f, my = 0.f, qa = 0.f, qb = 0.f, qc = 0.f, op = 0.f, sigma_cut = 0.f, lop = 0.f, depth = 0.f;
+      TileRect tr = {0, 0, 0, 0};
+      if (active) {
+        const float4* sg = reinterpret_cast<const float4*>(s_gauss + ln * kProjGaussFloats);
+        const float4 g0 = sg[0], g1 = sg[1], g2 = sg[2];
+        const float gmu[3] = {g0.x, g0.y, g0.z};
+        const float cov[6] = {g0.w, g1.x, g1.y, g1.z, g1.w, g2.x};
+        const float* sc = s_cam + ci * kProjCamFloats;
+        CamIntr cam;
+#pragma unroll
+        for (int i = 0; i < 9; ++i) cam.R[i] = sc[i];
+        cam.t[0] = sc[9]; cam.t[1] = sc[10]; cam.t[2] = sc[11];
+        cam.fx = sc[12]; cam.fy = sc[13]; cam.cx = sc[14]; cam.cy = sc[15];
+        Proj o;
+        if (project_gaussian_cov(gmu, cov, g2.y, cam, p.d.width, p.d.height, p.d.eps2d, p.d.near_plane, p.d.far_plane,
+                                 p.d.radius_clip, o)) {
+          radius_i = (int)o.radius;
+          if (p.means2d) { p.means2d[2 * idx] = o.mx; p.means2d[2 * idx + 1] = o.my; }
+          if (p.depths) p.depths[idx] = o.z;
+          if (p.conics) { p.conics[3 * idx] = o.a; p.conics[3 * idx + 1] = o.b; p.conics[3 * idx + 2] = o.c; }
+          if (p.compensations) p.compensations[idx] = o.comp;
+          op = g2.z;
+          if (p.d.antialiased) op *= o.comp;
+          mx = o.mx; my = o.my; depth = o.z;
+          qa = 0.5f * kLog2e * o.a; qb = kLog2e * o.b; qc = 0.5f * kLog2e * o.c;
+          lop = __log2f(op);
+          sigma_cut = lop + kLog2_255;  // alpha >= 1/255  <=>  sigma' <= log2(255 o)
+          if (op >= kAlphaMin) {
+            tr = candidate_rect(mx, my, o.radius, qa, qb, qc, sigma_cut, p.tile_w, p.tile_h, ty0, ty1);
+            cand = (tr.x1 > tr.x0) && (tr.y1 > tr.y0);
+          }
         }
-        const unsigned hm = __ballot_sync(0xffffffffu, hit);
-        const unsigned grp = __match_any_sync(0xffffffffu, owner);
-        if (lane == __ffs(grp) - 1) run[owner] += __popc(hm & grp);  // one leader per owner: no atomics
+      }
+      // ---- exact tile count.  The candidates of the warp's splats form one flat list that the 32 lanes
+      // test 32 at a time (splat footprints differ by orders of magnitude: per-lane loops would idle).
+      {
+        const int ncand = cand ? (tr.x1 - tr.x0) * (tr.y1 - tr.y0) : 0;
+        const int incl = warp_inclusive_scan_i32(ncand);
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        const int excl = incl - ncand;
+        const int rw = tr.x1 - tr.x0;
+        int* run = s_run + (threadIdx.x >> 5) * 32;
+        run[lane] = 0;
+        __syncwarp();
+        for (int base = 0; base < total; base += 32) {
+          const int wi = min(base + lane, total - 1);
+          const int owner = warp_find_owner(excl, wi);
+          const int local = wi - __shfl_sync(0xffffffffu, excl, owner);
+          const int ow = __shfl_sync(0xffffffffu, rw, owner);
+          const int ox0 = __shfl_sync(0xffffffffu, tr.x0, owner), oy0 = __shfl_sync(0xffffffffu, tr.y0, owner);
+          const float gx = __shfl_sync(0xffffffffu, mx, owner), gy = __shfl_sync(0xffffffffu, my, owner);
+          const float ga = __shfl_sync(0xffffffffu, qa, owner), gb = __shfl_sync(0xffffffffu, qb, owner);
+          const float gc = __shfl_sync(0xffffffffu, qc, owner), gcut = __shfl_sync(0xffffffffu, sigma_cut, owner);
+          bool hit = false;
+          if (base + lane < total) {
+            const int ry = local / ow;
+            hit = tile_hit(gx, gy, ga, gb, gc, gcut, ox0 + local - ry * ow, oy0 + ry, p.d.width, p.d.height);
+          }
+          const unsigned hm = __ballot_sync(0xffffffffu, hit);
+          const unsigned grp = __match_any_sync(0xffffffffu, owner);
+          if (lane == __ffs(grp) - 1) run[owner] += __popc(hm & grp);  // one leader per owner: no atomics
+          __syncwarp();
+        }
+        n_tiles = run[lane];
         __syncwarp();
       }
-      n_tiles = run[lane];
-      __syncwarp();
-    }
-    // ---- phase 3: packed record (SH colour only for splats that reach some tile) -------------------
-    const bool emit = n_tiles > 0;
-    float rec[12];
-    if (emit) {
-      rec[0] = mx; rec[1] = my; rec[2] = qa; rec[3] = qb; rec[4] = qc; rec[5] = op;
-      if (p.d.sh_degree >= 0) {
-        // view direction = mean - camera position, camera position = -R^T t  (vanilla.py:384-385)
-        float cp[3] = {-(cam.R[0] * cam.t[0] + cam.R[3] * cam.t[1] + cam.R[6] * cam.t[2]),
-                       -(cam.R[1] * cam.t[0] + cam.R[4] * cam.t[1] + cam.R[7] * cam.t[2]),
-                       -(cam.R[2] * cam.t[0] + cam.R[5] * cam.t[1] + cam.R[8] * cam.t[2])};
-        float dx = mu[0] - cp[0], dy = mu[1] - cp[1], dz = mu[2] - cp[2];
-        float inv = rsqrtf(dx * dx + dy * dy + dz * dz);
-        float b[16];
-        sh_basis(p.d.sh_degree, dx * inv, dy * inv, dz * inv, b);
-        int nb = (p.d.sh_degree + 1) * (p.d.sh_degree + 1);
-        if (nb > p.d.sh_K) nb = p.d.sh_K;
-        float col[3];
-#pragma unroll
-        for (int ch = 0; ch < 3; ++ch) col[ch] = b[0] * __ldg(p.fdc + 3 * (size_t)n + ch);
-        const float* fr = p.frest + (size_t)n * (p.d.sh_K - 1) * 3;
-        for (int k = 1; k < nb; ++k) {
-#pragma unroll
-          for (int ch = 0; ch < 3; ++ch) col[ch] = fmaf(b[k], __ldg(fr + (k - 1) * 3 + ch), col[ch]);
-        }
-#pragma unroll
-        for (int ch = 0; ch < 3; ++ch) rec[6 + ch] = fminf(fmaxf(col[ch] + 0.5f, 0.f), 1.f);
-      } else {
-        const float* cp = p.colors + (p.colors_per_cam ? 3 * (size_t)idx : 3 * (size_t)n);
-        rec[6] = cp[0]; rec[7] = cp[1]; rec[8] = cp[2];
-      }
-      rec[9] = depth;
-      rec[10] = __int_as_float((int)idx);
-      rec[11] = lop;  // log2(opacity): alpha = exp2(rec[11] - sigma')
-    }
-    // warp-aggregated compaction: one atomic per warp
-    unsigned ballot = __ballot_sync(0xffffffffu, emit);
-    int slot = -1;
-    if (ballot) {
-      int leader = __ffs(ballot) - 1;
-      int base = 0;
-      if (lane == leader) base = atomicAdd(p.counters, __popc(ballot));
-      base = __shfl_sync(0xffffffffu, base, leader);
+      // ---- packed record (SH colour only for splats that reach some tile)
+      const bool emit = n_tiles > 0;
+      float rec[12];
       if (emit) {
-        slot = base + __popc(ballot & ((1u << lane) - 1u));
-        if (slot >= p.splat_cap) {  // capacity overflow: flag, drop the record
-          p.counters[1] = 1;
-          slot = -1;
-          n_tiles = 0;
+        rec[0] = mx; rec[1] = my; rec[2] = qa; rec[3] = qb; rec[4] = qc; rec[5] = op;
+        if (p.d.sh_degree >= 0) {
+          const float* sg = s_gauss + ln * kProjGaussFloats;
+          const float* sc = s_cam + ci * kProjCamFloats;
+          float dx = sg[0] - sc[16], dy = sg[1] - sc[17], dz = sg[2] - sc[18];  // mean - camera position
+          float inv = rsqrtf(dx * dx + dy * dy + dz * dz);
+          float b[16];
+          sh_basis(p.d.sh_degree, dx * inv, dy * inv, dz * inv, b);
+          int nb = (p.d.sh_degree + 1) * (p.d.sh_degree + 1);
+          if (nb > p.d.sh_K) nb = p.d.sh_K;
+          const float* dc = s_dc + ln * 3;
+          const float* rest = s_rest + ln * per - 3;  // rest[k * 3 + ch], k >= 1
+          float col[3];
+#pragma unroll
+          for (int ch = 0; ch < 3; ++ch) col[ch] = b[0] * dc[ch];
+          for (int k = 1; k < nb; ++k) {
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) col[ch] = fmaf(b[k], rest[k * 3 + ch], col[ch]);
+          }
+#pragma unroll
+          for (int ch = 0; ch < 3; ++ch) rec[6 + ch] = fminf(fmaxf(col[ch] + 0.5f, 0.f), 1.f);
+        } else {
+          const float* cp = p.colors + (p.colors_per_cam ? 3 * (size_t)idx : 3 * (size_t)gn);
+          rec[6] = cp[0]; rec[7] = cp[1]; rec[8] = cp[2];
+        }
+        rec[9] = depth;
+        rec[10] = __int_as_float((int)idx);
+        rec[11] = lop;  // log2(opacity): alpha = exp2(rec[11] - sigma')
+      }
+      // warp-aggregated compaction: one atomic per warp
+      unsigned ballot = __ballot_sync(0xffffffffu, emit);
+      int slot = -1;
+      if (ballot) {
+        int leader = __ffs(ballot) - 1;
+        int base = 0;
+        if (lane == leader) base = atomicAdd(p.counters, __popc(ballot));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (emit) {
+          slot = base + __popc(ballot & ((1u << lane) - 1u));
+          if (slot >= p.splat_cap) {  // capacity overflow: flag, drop the record
+            p.counters[1] = 1;
+            slot = -1;
+            n_tiles = 0;
+          }
         }
       }
-    }
-    if (in_range) {
-      if (p.radii) p.radii[idx] = radius_i;
-      p.tiles_touched[idx] = n_tiles;
-      if (p.slot_of) p.slot_of[idx] = slot;
-      if (slot >= 0) {
-        float4* dst = reinterpret_cast<float4*>(p.splats + (size_t)slot * 12);
-        dst[0] = make_float4(rec[0], rec[1], rec[2], rec[3]);
-        dst[1] = make_float4(rec[4], rec[5], rec[6], rec[7]);
-        dst[2] = make_float4(rec[8], rec[9], rec[10], rec[11]);
+      if (active) {
+        if (p.radii) p.radii[idx] = radius_i;
+        p.tiles_touched[idx] = n_tiles;
+        if (p.slot_of) p.slot_of[idx] = slot;
+        if (slot >= 0) {
+          float4* dst = reinterpret_cast<float4*>(p.splats + (size_t)slot * 12);
+          dst[0] = make_float4(rec[0], rec[1], rec[2], rec[3]);
+          dst[1] = make_float4(rec[4], rec[5], rec[6], rec[7]);
+          dst[2] = make_float4(rec[8], rec[9], rec[10], rec[11]);
+        }
       }
     }
   }
@@ -413,7 +528,13 @@ extern "C" int bds_project_fwd(const bds_render_desc* d, const float* means, con
   p.tiles_touched = tiles_touched; p.splats = splats; p.splat_cap = splat_cap; p.slot_of = slot_of; p.counters = counters;
   // tiles_touched of cameras outside the band must read 0 for the scan: the caller's buffer may be fresh
   BDS_CHECK_CUDA(cudaMemsetAsync(tiles_touched, 0, (size_t)total * sizeof(int32_t), static_cast<cudaStream_t>(stream)));
-  project_fwd_kernel<<<ceil_div(d->n_gauss, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  const int sh_floats = d->sh_degree >= 0 ? 3 * d->sh_K : 0;
+  const size_t smem = proj_smem_bytes(sh_floats);
+  BDS_CHECK_CUDA(cudaFuncSetAttribute(project_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int sh_bulk_ok = sh_floats > 0 && ((uintptr_t)features_dc % 16 == 0) &&
+                         (sh_floats == 3 || (uintptr_t)features_rest % 16 == 0);
+  project_fwd_kernel<<<ceil_div(d->n_gauss, kProjBlock), kProjBlock, smem, static_cast<cudaStream_t>(stream)>>>(
+      p, sh_floats, sh_bulk_ok);
   BDS_CHECK_LAUNCH();
   return 0;
 }

@@ -88,6 +88,20 @@ BDS_HD void covar_cam(const float R[9], const float S[6], float Sc[9]) {
     for (int j = 0; j < 3; ++j) Sc[i * 3 + j] = RS[i * 3] * R[j * 3] + RS[i * 3 + 1] * R[j * 3 + 1] + RS[i * 3 + 2] * R[j * 3 + 2];
 }
 
+// Cheap conservative screen cull before the covariance arithmetic (5/6 of a rig's Gaussians are outside
+// any one camera): radius <= 3 sqrt(lambda_max) + 1 and lambda_max <= ||J||_F^2 smax^2 + 0.7 (trace bound
+// incl. the eps2d blur and the 0.01 floor), so a splat whose mean (camera coordinates x, y, z) is further
+// than that bound outside the image is culled by gsplat's own test as well.  true = culled.
+BDS_HD bool screen_cull(float x, float y, float z, float smax, float fx, float fy, float cx, float cy, int width,
+                        int height, float eps2d) {
+  float lx = 1.3f * (0.5f * (float)width / fx), ly = 1.3f * (0.5f * (float)height / fy);
+  float rzq = 1.0f / z;
+  float jf2 = (fx * fx * (1.f + lx * lx) + fy * fy * (1.f + ly * ly)) * rzq * rzq;
+  float rb = 3.f * sqrtf(jf2 * smax * smax + 0.7f + eps2d) * 1.001f + 2.f;
+  float px = fx * x * rzq + cx, py = fy * y * rzq + cy;
+  return px + rb <= 0.f || px - rb >= (float)width || py + rb <= 0.f || py - rb >= (float)height;
+}
+
 // Projection of one Gaussian whose world covariance (symmetric 6) is already known; smax = largest
 // scale.  Returns false when culled (radius = 0).
 BDS_HD bool project_gaussian_cov(const float mu[3], const float cov[6], float smax, const CamIntr& cam, int width,
@@ -98,18 +112,7 @@ BDS_HD bool project_gaussian_cov(const float mu[3], const float cov[6], float sm
   o.y = cam.R[3] * mu[0] + cam.R[4] * mu[1] + cam.R[5] * mu[2] + cam.t[1];
   o.z = cam.R[6] * mu[0] + cam.R[7] * mu[1] + cam.R[8] * mu[2] + cam.t[2];
   if (o.z < near_plane || o.z > far_plane) return false;
-  {
-    // Cheap conservative screen cull before the covariance arithmetic (5/6 of a rig's Gaussians are
-    // outside any one camera): radius <= 3 sqrt(lambda_max) + 1 and lambda_max <= ||J||_F^2 smax^2 + 0.7
-    // (trace bound incl. the eps2d blur and the 0.01 floor), so a splat whose mean is further than that
-    // bound outside the image is culled by gsplat's own test as well.
-    float lx = 1.3f * (0.5f * (float)width / cam.fx), ly = 1.3f * (0.5f * (float)height / cam.fy);
-    float rzq = 1.0f / o.z;
-    float jf2 = (cam.fx * cam.fx * (1.f + lx * lx) + cam.fy * cam.fy * (1.f + ly * ly)) * rzq * rzq;
-    float rb = 3.f * sqrtf(jf2 * smax * smax + 0.7f + eps2d) * 1.001f + 2.f;
-    float px = cam.fx * o.x * rzq + cam.cx, py = cam.fy * o.y * rzq + cam.cy;
-    if (px + rb <= 0.f || px - rb >= (float)width || py + rb <= 0.f || py - rb >= (float)height) return false;
-  }
+  if (screen_cull(o.x, o.y, o.z, smax, cam.fx, cam.fy, cam.cx, cam.cy, width, height, eps2d)) return false;
   float Sc[9];
   covar_cam(cam.R, cov, Sc);
   float limx = 1.3f * (0.5f * (float)width / cam.fx), limy = 1.3f * (0.5f * (float)height / cam.fy);

@@ -1,0 +1,19 @@
+"""Profiling aid: sub-warp hit statistics of the composite walk (needs a -DBDS_STATS build of composite.cu)."""
+import ctypes as C, json, subprocess, sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from bilateral_driving_b200 import _lib
+import bench  # noqa: F401  (reuses the bench scene through its CLI below)
+
+if __name__ == "__main__":
+    lib = _lib.lib
+    out = (C.c_ulonglong * 16)()
+    lib.bds_debug_stats(out, 1)
+    sys.argv = ["bench.py", "--steps", "1", "--warmup", "3", "--no-cpu-baseline"]
+    bench.main()
+    lib.bds_debug_stats(out, 0)
+    v = [int(x) for x in out]
+    names = ["batches", "hits_8x4", "max2_batch", "max2_chunk", "max4_batch", "max4_chunk", "sum2", "sum4", "valid_lanes", "union2"]
+    d = dict(zip(names, v))
+    d["calls"] = 4 + 1 + 1  # warm-up(3 -> max(3)) + timed + e2e ... informational only
+    print(json.dumps(d))
