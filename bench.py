@@ -236,7 +236,8 @@ def main():
     def step(gt, vmx, Ksx, gt_ready=None):
         for t in leaves:
             t.grad = None
-        slots = [[g[c] for g in grids] if c in cams else None for c in range(Cn)]
+        per_cam = [g.unbind(0) for g in grids]  # one autograd node per level (backward = one stack), not C selects
+        slots = [[u[c] for u in per_cam] if c in cams else None for c in range(Cn)]
         out = render.render_fused(params, vmx, Ksx, W, H, sky=sky, grid_slots=slots, bil_sizes=sizes, sh_degree=3,
                                   near_plane=0.1, row_begin=rb, row_end=re, absgrad=True, dense_info=False,
                                   guidance_factor=(4, 4, 2) if args.guidance == "lowres" else None)

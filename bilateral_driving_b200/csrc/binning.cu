@@ -1,14 +1,19 @@
-// Tile binning: one scan of the per-(camera, Gaussian) tile counts (record total + id-ordered rank of
-// every emitting splat), a stable LSD radix sort written for this library (no CUB / thrust) used twice
-// - visible splats by fp32 depth bits, then the emitted (band tile, slot) records by tile -, per-tile
-// start offsets and the gather of the packed 48-byte splat records into sorted order so that the
-// composite kernels read contiguous chunks (TMA bulk copies).
+// Tile binning.  The projection kernel counted, per band tile, the splats that reach it; here
+//   bds_bin_count  scans those counts into per-tile start offsets (+ the record total), and
+//   bds_bin_sort   (1) emits every (tile, splat) pair into its tile's segment through a per-tile atomic
+//                  cursor (unordered inside the segment), (2) sorts each segment by (fp32 depth bits,
+//                  Gaussian id) with ONE CTA per tile - in shared memory for segments up to
+//                  kTileSortCap records, in place in global memory beyond - and gathers the packed
+//                  48-byte splat records into that order, so that the composite kernels read contiguous
+//                  chunks (TMA bulk copies).
+// No global sort: a record is written once as a 12-byte (key, slot) pair and once as its 48-byte record.
 //
 // Replaces gsplat's isect_tiles + torch.cumsum + cub::DeviceRadixSort + isect_offset_encode for the
-// reference call at models/trainers/base.py:393-408.  Ordering contract = gsplat's: ascending
-// (camera, tile, depth bits), ties in Gaussian-id order.
+// reference call at models/trainers/base.py:393-408.  Ordering contract = gsplat's: per (camera, tile)
+// ascending depth bits, ties in Gaussian-id order (what a stable sort over id-ordered emission gives).
 //
-// All kernels are HBM-bound integer / copy work: coalesced loads, grid sized to the data.
+// All kernels are HBM-bound integer / copy work: coalesced loads where the data allows, grid sized to
+// the data.
 #include "projection_math.cuh"
 
 namespace bds {
@@ -137,173 +142,29 @@ static int exclusive_scan(const TIn* in, TOut* out, int64_t n, int64_t* total_de
 }
 
 // ---------------------------------------------------------------------------------------------
-// LSD radix sort, 8-bit digits, (KeyT key, uint32 value), stable.  Per pass:
-//   rs_hist_kernel     per-block digit histogram -> hist[digit][block]
-//   exclusive_scan     over the digit-major array -> global base of every (digit, block)
-//   rs_scatter_kernel  stable in-block ranking (warp match_any + per-warp counters) and scatter
+// emission: one thread per visible splat (compaction order), (tile, splat) pairs through per-tile cursors
 // ---------------------------------------------------------------------------------------------
-constexpr int kRsThreads = 256;
-constexpr int kRsItems = 16;
-constexpr int kRsTile = kRsThreads * kRsItems;  // 4096 keys per block
-constexpr int kRsWarps = kRsThreads / 32;
-
-template <typename KeyT>
-__global__ void __launch_bounds__(kRsThreads) rs_hist_kernel(const KeyT* __restrict__ keys, int64_t n, int shift,
-                                                             int nblocks, uint32_t* __restrict__ hist) {
-  __shared__ uint32_t sh[256];
-  sh[threadIdx.x] = 0;
-  __syncthreads();
-  int64_t base = (int64_t)blockIdx.x * kRsTile;
-#pragma unroll
-  for (int k = 0; k < kRsItems; ++k) {
-    int64_t i = base + (int64_t)k * kRsThreads + threadIdx.x;
-    if (i < n) atomicAdd(&sh[(uint32_t)(keys[i] >> shift) & 255u], 1u);
-  }
-  __syncthreads();
-  hist[(size_t)threadIdx.x * nblocks + blockIdx.x] = sh[threadIdx.x];
-}
-
-template <typename KeyT>
-__global__ void __launch_bounds__(kRsThreads) rs_scatter_kernel(const KeyT* __restrict__ keys_in,
-                                                                const uint32_t* __restrict__ vals_in, int64_t n,
-                                                                int shift, int nblocks,
-                                                                const uint32_t* __restrict__ base,
-                                                                KeyT* __restrict__ keys_out,
-                                                                uint32_t* __restrict__ vals_out) {
-  __shared__ uint32_t warp_hist[kRsWarps][256];
-  __shared__ uint32_t gbase[256];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int i = threadIdx.x; i < kRsWarps * 256; i += kRsThreads) (&warp_hist[0][0])[i] = 0;
-  gbase[threadIdx.x] = base[(size_t)threadIdx.x * nblocks + blockIdx.x];
-  __syncthreads();
-  // warp w owns the contiguous segment [w*512, (w+1)*512) of the block tile, in rounds of 32
-  int64_t seg = (int64_t)blockIdx.x * kRsTile + (int64_t)warp * (32 * kRsItems);
-  KeyT key[kRsItems];
-  uint32_t rank[kRsItems];
-#pragma unroll
-  for (int r = 0; r < kRsItems; ++r) {
-    int64_t i = seg + r * 32 + lane;
-    bool valid = i < n;
-    key[r] = valid ? keys_in[i] : (KeyT)0;
-    uint32_t digit = valid ? ((uint32_t)(key[r] >> shift) & 255u) : 256u;  // 256 = "no element"
-    unsigned peers = __match_any_sync(0xffffffffu, digit);
-    uint32_t before = __popc(peers & ((1u << lane) - 1u));
-    int leader = __ffs(peers) - 1;
-    uint32_t old = 0;
-    if (valid && lane == leader) {
-      old = warp_hist[warp][digit];
-      warp_hist[warp][digit] = old + __popc(peers);
-    }
-    old = __shfl_sync(0xffffffffu, old, leader);
-    rank[r] = old + before;
-    __syncwarp();
-  }
-  __syncthreads();
-  {  // exclusive scan over warps, per digit
-    uint32_t run = 0;
-#pragma unroll
-    for (int w = 0; w < kRsWarps; ++w) {
-      uint32_t cnt = warp_hist[w][threadIdx.x];
-      warp_hist[w][threadIdx.x] = run;
-      run += cnt;
-    }
-  }
-  __syncthreads();
-#pragma unroll
-  for (int r = 0; r < kRsItems; ++r) {
-    int64_t i = seg + r * 32 + lane;
-    if (i < n) {
-      uint32_t digit = (uint32_t)(key[r] >> shift) & 255u;
-      uint32_t pos = gbase[digit] + warp_hist[warp][digit] + rank[r];
-      keys_out[pos] = key[r];
-      vals_out[pos] = vals_in[i];
-    }
-  }
-}
-
-// sorts (keys[0], vals[0]) over bits [0, end_bit); returns the index (0/1) of the buffer holding the result
-template <typename KeyT>
-static int radix_sort_pairs(KeyT* keys[2], uint32_t* vals[2], int64_t n, int end_bit, uint32_t* hist, void* scan_ws,
-                            cudaStream_t stream, int* result_buf) {
-  const int nblocks = ceil_div(n, kRsTile);
-  int cur = 0;
-  for (int shift = 0; shift < end_bit; shift += 8) {
-    rs_hist_kernel<KeyT><<<nblocks, kRsThreads, 0, stream>>>(keys[cur], n, shift, nblocks, hist);
-    BDS_CHECK_LAUNCH();
-    if (int rc = exclusive_scan<uint32_t, uint32_t>(hist, hist, (int64_t)256 * nblocks, nullptr, scan_ws, stream)) return rc;
-    rs_scatter_kernel<KeyT><<<nblocks, kRsThreads, 0, stream>>>(keys[cur], vals[cur], n, shift, nblocks, hist,
-                                                                keys[cur ^ 1], vals[cur ^ 1]);
-    BDS_CHECK_LAUNCH();
-    cur ^= 1;
-  }
-  *result_buf = cur;
-  return 0;
-}
-
-// ---------------------------------------------------------------------------------------------
-// Two-stage ordering.  gsplat sorts every (tile, splat) record by a 64-bit (tile | depth) key; here the
-// visible splats (n_slots, ~7x fewer than records) are first sorted by (depth bits, Gaussian id), the
-// records are then emitted in that order and only need a STABLE sort on the tile index
-// (17 bits -> 3 passes of 20 B/record instead of 6 passes of 32 B/record).  Result: per tile ascending
-// (depth bits, id) - exactly the order of gsplat's stable 64-bit sort over id-ordered emission.
-// ---------------------------------------------------------------------------------------------
-constexpr int kRankShift = 40;  // bds_bin_count packs (rank of emitting splats << 40) | tile prefix
-
-// stage-1 input in Gaussian-id order: key = depth bits, value = slot (one thread per compact slot)
-__global__ void __launch_bounds__(256) stage1_fill_kernel(const float* __restrict__ splats, int n_slots,
-                                                          const int64_t* __restrict__ packed_prefix,
-                                                          uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
-  int slot = blockIdx.x * blockDim.x + threadIdx.x;
-  if (slot >= n_slots) return;
-  const float* rec = splats + (size_t)slot * 12;
-  int64_t idx = (int64_t)__float_as_int(__ldg(rec + 10));
-  int64_t rank = packed_prefix[idx] >> kRankShift;
-  keys[rank] = (uint32_t)__float_as_int(__ldg(rec + 9));  // positive floats order like their bit patterns
-  vals[rank] = (uint32_t)slot;
-}
-
-// tiles_touched in depth-sorted order (input of the second scan)
-__global__ void __launch_bounds__(256) gather_tiles_kernel(const float* __restrict__ splats,
-                                                           const uint32_t* __restrict__ sorted_slots, int n_slots,
-                                                           const int32_t* __restrict__ tiles_touched,
-                                                           int32_t* __restrict__ out) {
-  int r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= n_slots) return;
-  int64_t idx = (int64_t)__float_as_int(__ldg(splats + (size_t)sorted_slots[r] * 12 + 10));
-  out[r] = tiles_touched[idx];
-}
-
 struct EmitParams {
   bds_render_desc d;
   int tile_w, tile_h;
   const int32_t* radii;
-  const int32_t* tiles_sorted;   // [n_slots] tile counts in depth order
-  const int64_t* offsets;        // [n_slots] exclusive prefix of tiles_sorted
-  const uint32_t* sorted_slots;  // [n_slots] slots in (depth, id) order
-  int n_tiles;
+  const int32_t* tile_offsets;  // [n_tiles + 1]
+  int32_t* cursors;             // [n_tiles], zero on entry
   int n_slots;
-  uint32_t perm_mul;             // multiplier coprime with n_slots
   const float* splats;
-  uint32_t* keys;
-  uint32_t* vals;
+  uint64_t* keys;               // [n_isect] (depth bits << 32) | Gaussian id
+  uint32_t* slots;              // [n_isect]
 };
 
-// one thread per splat in (depth, id) order: emits (band tile, slot) for every tile it reaches
-__global__ void __launch_bounds__(256) emit_keys_kernel(EmitParams p) {
-  __shared__ int s_run[8][32];
+__global__ void __launch_bounds__(256) emit_pairs_kernel(EmitParams p) {
   const int N = p.d.n_gauss;
   const int lane = threadIdx.x & 31;
-  // Depth order puts the largest (nearest) splats side by side; a multiplicative permutation of the
-  // thread -> rank map spreads them over the grid (output positions come from offsets[r], so the
-  // emitted order is unchanged).
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  const bool active = t < p.n_slots;
-  const int r = active ? (int)(((uint64_t)t * p.perm_mul) % (uint64_t)p.n_slots) : 0;
-  const int slot = active ? (int)p.sorted_slots[r] : 0;
+  const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool active = slot < p.n_slots;
   float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0, r2 = r0;
   TileRect tr = {0, 0, 0, 0};
-  long long o = 0, o_end = 0;
   int c = 0;
+  uint64_t key = 0;
   if (active) {
     const float4* rp = reinterpret_cast<const float4*>(p.splats + (size_t)slot * 12);
     r0 = __ldg(rp); r1 = __ldg(rp + 1); r2 = __ldg(rp + 2);
@@ -313,132 +174,139 @@ __global__ void __launch_bounds__(256) emit_keys_kernel(EmitParams p) {
     band_rows2(p.d, p.tile_h, c, ty0, ty1);
     // same candidate rectangle + same hit test (both non-inlined bodies) as the counting pass
     tr = candidate_rect(r0.x, r0.y, (float)p.radii[idx], r0.z, r0.w, r1.x, r2.w + kLog2_255, p.tile_w, p.tile_h, ty0, ty1);
-    o = p.offsets[r];
-    o_end = o + p.tiles_sorted[r];
+    // positive floats order like their bit patterns; ties by Gaussian id (the camera is implied by the tile)
+    key = ((uint64_t)(uint32_t)__float_as_int(r2.y) << 32) | (uint64_t)(uint32_t)(idx - (int64_t)c * N);
   }
-  // Same flat warp-cooperative enumeration as the counting pass.  The o_end guard and the sentinel
-  // padding (a key that sorts behind every real tile) only make a count / emission disagreement
-  // memory-safe should a toolchain ever break the shared-body contract.
-  {
-    const int ncand = active ? (tr.x1 - tr.x0) * (tr.y1 - tr.y0) : 0;
-    const int incl = warp_inclusive_scan_i32(ncand);
-    const int total = __shfl_sync(0xffffffffu, incl, 31);
-    const int excl = incl - ncand;
-    const int rw = tr.x1 - tr.x0;
-    int* run = s_run[threadIdx.x >> 5];
-    run[lane] = 0;
-    __syncwarp();
-    for (int base = 0; base < total; base += 32) {
-      const int wi = min(base + lane, total - 1);
-      const int owner = warp_find_owner(excl, wi);
-      const int local = wi - __shfl_sync(0xffffffffu, excl, owner);
-      const int ow = __shfl_sync(0xffffffffu, rw, owner);
-      const int ox0 = __shfl_sync(0xffffffffu, tr.x0, owner), oy0 = __shfl_sync(0xffffffffu, tr.y0, owner);
-      const float gx = __shfl_sync(0xffffffffu, r0.x, owner), gy = __shfl_sync(0xffffffffu, r0.y, owner);
-      const float ga = __shfl_sync(0xffffffffu, r0.z, owner), gb = __shfl_sync(0xffffffffu, r0.w, owner);
-      const float gc = __shfl_sync(0xffffffffu, r1.x, owner), gcut = __shfl_sync(0xffffffffu, r2.w, owner) + kLog2_255;
-      const int gcam = __shfl_sync(0xffffffffu, c, owner), gslot = __shfl_sync(0xffffffffu, slot, owner);
-      const long long go = __shfl_sync(0xffffffffu, o, owner), gend = __shfl_sync(0xffffffffu, o_end, owner);
-      bool hit = false;
-      int tx = 0, ty = 0;
-      if (base + lane < total) {
-        const int ry = local / ow;
-        tx = ox0 + local - ry * ow;
-        ty = oy0 + ry;
-        hit = tile_hit(gx, gy, ga, gb, gc, gcut, tx, ty, p.d.width, p.d.height);
+  // Same flat warp-cooperative enumeration as the counting pass (projection.cu).  The capacity guard only
+  // makes a count / emission disagreement memory-safe should a toolchain ever break the shared-body
+  // contract; unfilled positions keep the sentinel the host wrote and become null records.
+  const int ncand = active ? (tr.x1 - tr.x0) * (tr.y1 - tr.y0) : 0;
+  const int incl = warp_inclusive_scan_i32(ncand);
+  const int total = __shfl_sync(0xffffffffu, incl, 31);
+  const int excl = incl - ncand;
+  const int rw = tr.x1 - tr.x0;
+  const unsigned key_lo = (unsigned)key, key_hi = (unsigned)(key >> 32);
+  for (int base = 0; base < total; base += 32) {
+    const int wi = min(base + lane, total - 1);
+    const int owner = warp_find_owner(excl, wi);
+    const int local = wi - __shfl_sync(0xffffffffu, excl, owner);
+    const int ow = __shfl_sync(0xffffffffu, rw, owner);
+    const int ox0 = __shfl_sync(0xffffffffu, tr.x0, owner), oy0 = __shfl_sync(0xffffffffu, tr.y0, owner);
+    const float gx = __shfl_sync(0xffffffffu, r0.x, owner), gy = __shfl_sync(0xffffffffu, r0.y, owner);
+    const float ga = __shfl_sync(0xffffffffu, r0.z, owner), gb = __shfl_sync(0xffffffffu, r0.w, owner);
+    const float gc = __shfl_sync(0xffffffffu, r1.x, owner), gcut = __shfl_sync(0xffffffffu, r2.w, owner) + kLog2_255;
+    const int gcam = __shfl_sync(0xffffffffu, c, owner);
+    const int gslot = (blockIdx.x * blockDim.x + (threadIdx.x & ~31)) + owner;
+    const unsigned glo = __shfl_sync(0xffffffffu, key_lo, owner), ghi = __shfl_sync(0xffffffffu, key_hi, owner);
+    if (base + lane < total) {
+      const int ry = local / ow;
+      const int tx = ox0 + local - ry * ow, ty = oy0 + ry;
+      if (tile_hit(gx, gy, ga, gb, gc, gcut, tx, ty, p.d.width, p.d.height)) {
+        const int tile = (gcam * p.tile_h + ty - p.d.row_begin) * p.tile_w + tx;
+        const int seg0 = p.tile_offsets[tile], cap = p.tile_offsets[tile + 1] - seg0;
+        const int pos = atomicAdd(p.cursors + tile, 1);
+        if (pos < cap) {
+          p.keys[seg0 + pos] = ((uint64_t)ghi << 32) | glo;
+          p.slots[seg0 + pos] = (uint32_t)gslot;
+        }
       }
-      const unsigned hm = __ballot_sync(0xffffffffu, hit);
-      const unsigned grp = __match_any_sync(0xffffffffu, owner);
-      const int before = run[owner];
-      __syncwarp();
-      const long long pos = go + before + __popc(hm & grp & ((1u << lane) - 1u));
-      if (hit && pos < gend) {
-        p.keys[pos] = (uint32_t)((gcam * p.tile_h + ty - p.d.row_begin) * p.tile_w + tx);
-        p.vals[pos] = (uint32_t)gslot;
-      }
-      if (lane == __ffs(grp) - 1) run[owner] = before + __popc(hm & grp);
-      __syncwarp();
     }
-    o += run[lane];
-    if (o > o_end) o = o_end;
-  }
-  for (; o < o_end; ++o) {
-    p.keys[o] = (uint32_t)p.n_tiles;
-    p.vals[o] = (uint32_t)slot;
   }
 }
 
-// per-tile start offsets from the sorted tile keys (the role of isect_offset_encode)
-__global__ void __launch_bounds__(256) tile_offsets_kernel(const uint32_t* __restrict__ keys, int64_t n, int n_tiles,
-                                                           int32_t* __restrict__ offsets) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (n == 0) {
-    if (i <= n_tiles) offsets[i] = 0;
-    return;
+// ---------------------------------------------------------------------------------------------
+// per-tile sort + gather.  Bitonic network in its "all merges ascending" form (first step of a merge
+// pairs i with its mirror inside the block, the rest pair i with i + j): every compare-exchange puts the
+// smaller key at the lower index, so positions >= n behave as +inf padding that never moves and pairs
+// reaching beyond n are simply skipped - any n, no power-of-two padding in memory.
+// ---------------------------------------------------------------------------------------------
+constexpr int kTileSortCap = 4096;    // records sorted in shared memory: 4096 x (8 + 4) B = 48 KB
+constexpr int kTileSortSmall = 1024;  // segments up to here go to the 12 KB instance
+constexpr uint32_t kNullSlot = 0xffffffffu;
+
+template <typename KeyPtr, typename SlotPtr>
+BDS_D void block_bitonic_sort(KeyPtr keys, SlotPtr slots, int n) {
+  int np2 = 1;
+  while (np2 < n) np2 <<= 1;
+  const int half = np2 >> 1;
+  for (int k = 2; k <= np2; k <<= 1) {
+    for (int j = k >> 1; j >= 1; j >>= 1) {
+      const bool mirror = (j == (k >> 1));
+      for (int t = threadIdx.x; t < half; t += blockDim.x) {
+        const int lo = t & (j - 1);
+        const int i = ((t - lo) << 1) + lo;              // 2 j (t / j) + t % j
+        const int q = mirror ? (i - lo) + (k - 1 - lo) : i + j;
+        if (q < n) {
+          const uint64_t a = keys[i], b = keys[q];
+          if (a > b) {
+            keys[i] = b; keys[q] = a;
+            const uint32_t sa = slots[i], sb = slots[q];
+            slots[i] = sb; slots[q] = sa;
+          }
+        }
+      }
+      __syncthreads();
+    }
   }
-  if (i >= n) return;
-  int cur = (int)keys[i];
-  if (i == 0) {
-    for (int t = 0; t <= cur && t <= n_tiles; ++t) offsets[t] = 0;
+}
+
+template <int CAP, bool BIG>
+__global__ void __launch_bounds__(256) tile_sort_gather_kernel(const int32_t* __restrict__ tile_offsets,
+                                                               uint64_t* __restrict__ keys, uint32_t* __restrict__ slots,
+                                                               const float4* __restrict__ splats,
+                                                               float4* __restrict__ sorted,
+                                                               int32_t* __restrict__ sorted_slots) {
+  __shared__ __align__(16) uint64_t s_keys[CAP];
+  __shared__ uint32_t s_slots[CAP];
+  const int tile = blockIdx.x;
+  const int seg0 = tile_offsets[tile];
+  const int n = tile_offsets[tile + 1] - seg0;
+  // two launches share the tiles: the small-footprint instance (many CTAs per SM) takes the common short
+  // segments, the 48 KB instance the long ones
+  if (n <= 0 || (BIG ? n <= kTileSortSmall : n > kTileSortSmall)) return;
+  const uint32_t* order;
+  if (n <= CAP) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      s_keys[i] = keys[seg0 + i];
+      s_slots[i] = slots[seg0 + i];
+    }
+    __syncthreads();
+    if (n > 1) block_bitonic_sort(s_keys, s_slots, n);
+    order = s_slots;
   } else {
-    int prev = (int)keys[i - 1];
-    for (int t = prev + 1; t <= cur && t <= n_tiles; ++t) offsets[t] = (int32_t)i;
+    block_bitonic_sort(keys + seg0, slots + seg0, n);  // rare: oversized segment, in place in global memory
+    order = slots + seg0;
   }
-  if (i == n - 1) {
-    for (int t = cur + 1; t <= n_tiles; ++t) offsets[t] = (int32_t)n;
+  // sorted[seg0 + i] = splats[order[i]] with the id field replaced by the slot; one thread per float4
+  for (int t = threadIdx.x; t < n * 3; t += blockDim.x) {
+    const int i = t / 3, part = t - i * 3;
+    const uint32_t slot = order[i];
+    float4 v;
+    if (slot == kNullSlot) {  // never-filled position (see emit_pairs_kernel): a record that contributes nothing
+      v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (part == 2) v = make_float4(0.f, 0.f, __int_as_float(0), -1.0e30f);
+    } else {
+      v = __ldg(splats + (size_t)slot * 3 + part);
+      if (part == 2) v.z = __int_as_float((int)slot);
+    }
+    sorted[(size_t)seg0 * 3 + t] = v;
   }
-}
-
-// sorted_splats[i] = splats[vals[i]] with the id field replaced by the slot; one thread per float4
-__global__ void __launch_bounds__(256) gather_records_kernel(const uint32_t* __restrict__ vals, int64_t n,
-                                                             const float4* __restrict__ splats,
-                                                             float4* __restrict__ sorted) {
-  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= n * 3) return;
-  int64_t i = t / 3;
-  int part = (int)(t - i * 3);
-  uint32_t slot = vals[i];
-  float4 v = __ldg(splats + (size_t)slot * 3 + part);
-  if (part == 2) v.z = __int_as_float((int)slot);
-  sorted[t] = v;
+  if (sorted_slots)
+    for (int i = threadIdx.x; i < n; i += blockDim.x) sorted_slots[seg0 + i] = (int32_t)order[i];
 }
 
 struct SortWorkspace {
-  size_t keys_a, keys_b, vals_a, vals_b, s1k_a, s1k_b, s1v_a, s1v_b, tiles_sorted, offs2, hist, scan, total;
+  size_t keys, slots, cursors, total;
 };
-static SortWorkspace carve_sort(int64_t n_isect, int64_t n_slots) {
+static SortWorkspace carve_sort(int64_t n_isect, int n_tiles) {
   SortWorkspace w;
   size_t off = 0;
-  size_t nk = (size_t)(n_isect > 0 ? n_isect : 1), ns = (size_t)(n_slots > 0 ? n_slots : 1);
-  size_t nmax = nk > ns ? nk : ns;
-  int nblocks = ceil_div((int64_t)nmax, kRsTile);
+  size_t nk = (size_t)(n_isect > 0 ? n_isect : 1);
   auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes, 256); return o; };
-  w.keys_a = take(nk * 4); w.keys_b = take(nk * 4); w.vals_a = take(nk * 4); w.vals_b = take(nk * 4);
-  w.s1k_a = take(ns * 4); w.s1k_b = take(ns * 4); w.s1v_a = take(ns * 4); w.s1v_b = take(ns * 4);
-  w.tiles_sorted = take(ns * 4); w.offs2 = take(ns * 8);
-  w.hist = take((size_t)256 * nblocks * 4);
-  size_t scan_n = (size_t)256 * nblocks;
-  w.scan = take(scan_workspace_bytes((int64_t)(scan_n > ns ? scan_n : ns)));
+  w.keys = take(nk * 8); w.slots = take(nk * 4); w.cursors = take((size_t)(n_tiles + 1) * 4);
   w.total = off;
   return w;
 }
-
-static int tile_bits_for(int n_tiles) {
-  int bits = 1;
-  while ((1 << bits) < n_tiles) ++bits;
-  return bits;
-}
-
-// packs (tiles > 0) << kRankShift | tiles so that ONE scan yields both the record count and the id-ordered
-// rank of every emitting splat
-__global__ void __launch_bounds__(256) pack_counts_kernel(const int32_t* __restrict__ tiles, int64_t n,
-                                                          int64_t* __restrict__ packed) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  int64_t t = tiles[i];
-  packed[i] = t > 0 ? (((int64_t)1 << kRankShift) | t) : 0;
-}
-__global__ void unpack_total_kernel(int64_t* total) { *total &= (((int64_t)1 << kRankShift) - 1); }
 
 int check_render_desc(const bds_render_desc* d);  // projection.cu
 
@@ -446,95 +314,61 @@ int check_render_desc(const bds_render_desc* d);  // projection.cu
 
 using namespace bds;
 
-extern "C" size_t bds_bin_count_workspace_bytes(int64_t n_elems) { return scan_workspace_bytes(n_elems) + 256; }
+static int band_tiles(const bds_render_desc* d) {
+  const int tile_w = (d->width + kTile - 1) / kTile;
+  return (d->row_end - d->row_begin) * tile_w;
+}
 
-extern "C" int bds_bin_count(const bds_render_desc* d, const int32_t* tiles_touched, int64_t* isect_offsets,
+extern "C" size_t bds_bin_count_workspace_bytes(const bds_render_desc* d) {
+  return scan_workspace_bytes(d ? (int64_t)band_tiles(d) + 1 : 1) + 256;
+}
+
+extern "C" int bds_bin_count(const bds_render_desc* d, const int32_t* tile_counts, int32_t* tile_offsets,
                              int64_t* n_isect_dev, void* workspace, bds_stream_t stream_) {
   if (int rc = check_render_desc(d)) return rc;
-  int64_t n = (int64_t)d->n_gauss * d->n_cams;
-  BDS_REQUIRE(n_isect_dev, "bin_count: null n_isect pointer");
+  BDS_REQUIRE(tile_counts && tile_offsets && n_isect_dev && workspace, "bin_count: null pointer");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  if (n == 0) {
-    BDS_CHECK_CUDA(cudaMemsetAsync(n_isect_dev, 0, sizeof(int64_t), stream));
-    return 0;
-  }
-  BDS_REQUIRE(tiles_touched && isect_offsets && workspace, "bin_count: null pointer");
-  pack_counts_kernel<<<ceil_div(n, 256), 256, 0, stream>>>(tiles_touched, n, isect_offsets);
-  BDS_CHECK_LAUNCH();
-  if (int rc = exclusive_scan<int64_t, int64_t>(isect_offsets, isect_offsets, n, n_isect_dev, workspace, stream)) return rc;
-  unpack_total_kernel<<<1, 1, 0, stream>>>(n_isect_dev);
-  BDS_CHECK_LAUNCH();
-  return 0;
+  // tile_counts holds n_tiles + 1 entries, the last one zero: the exclusive scan then also yields the end offset
+  return exclusive_scan<int32_t, int32_t>(tile_counts, tile_offsets, (int64_t)band_tiles(d) + 1, n_isect_dev, workspace,
+                                          stream);
 }
 
 extern "C" size_t bds_bin_sort_workspace_bytes(const bds_render_desc* d, int64_t n_isect) {
-  int64_t ns = d ? (int64_t)d->n_gauss * d->n_cams : 1;  // upper bound of the visible splats
-  if (ns > n_isect && n_isect > 0) ns = n_isect;         // every slot emits at least one record
-  return carve_sort(n_isect, ns).total + 256;
+  return carve_sort(n_isect, d ? band_tiles(d) : 1).total + 256;
 }
 
 extern "C" int bds_bin_sort(const bds_render_desc* d, int64_t n_isect, int32_t n_slots, const int32_t* radii,
-                            const int32_t* tiles_touched, const int64_t* isect_offsets, const float* splats,
-                            float* sorted_splats, int32_t* sorted_slots, int32_t* tile_offsets, void* workspace,
-                            bds_stream_t stream_) {
+                            const float* splats, const int32_t* tile_offsets, float* sorted_splats,
+                            int32_t* sorted_slots, void* workspace, bds_stream_t stream_) {
   if (int rc = check_render_desc(d)) return rc;
   BDS_REQUIRE(n_isect >= 0 && n_isect < ((int64_t)1 << 31), "bin_sort: n_isect must fit int32 (got %lld)", (long long)n_isect);
-  BDS_REQUIRE(tile_offsets, "bin_sort: null tile_offsets");
-  if (n_isect > 0)
-    BDS_REQUIRE(radii && tiles_touched && isect_offsets && splats && workspace && n_slots > 0 && n_slots <= n_isect,
-                "bin_sort: null pointer or inconsistent n_slots");
+  if (n_isect == 0) return 0;
+  BDS_REQUIRE(radii && splats && tile_offsets && sorted_splats && workspace && n_slots > 0 && n_slots <= n_isect,
+              "bin_sort: null pointer or inconsistent n_slots");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const int tile_w = (d->width + kTile - 1) / kTile, tile_h = (d->height + kTile - 1) / kTile;
-  const int n_tiles = (d->row_end - d->row_begin) * tile_w;
-  if (n_isect == 0) {
-    tile_offsets_kernel<<<ceil_div(n_tiles + 1, 256), 256, 0, stream>>>(nullptr, 0, n_tiles, tile_offsets);
-    BDS_CHECK_LAUNCH();
-    return 0;
-  }
-  BDS_REQUIRE(sorted_splats, "bin_sort: null sorted_splats");
+  const int n_tiles = band_tiles(d);
   char* ws = static_cast<char*>(workspace);
-  int64_t ns_cap = (int64_t)d->n_gauss * d->n_cams;
-  if (ns_cap > n_isect) ns_cap = n_isect;
-  SortWorkspace w = carve_sort(n_isect, ns_cap);
-  uint32_t* keys[2] = {reinterpret_cast<uint32_t*>(ws + w.keys_a), reinterpret_cast<uint32_t*>(ws + w.keys_b)};
-  uint32_t* vals[2] = {reinterpret_cast<uint32_t*>(ws + w.vals_a), reinterpret_cast<uint32_t*>(ws + w.vals_b)};
-  uint32_t* s1k[2] = {reinterpret_cast<uint32_t*>(ws + w.s1k_a), reinterpret_cast<uint32_t*>(ws + w.s1k_b)};
-  uint32_t* s1v[2] = {reinterpret_cast<uint32_t*>(ws + w.s1v_a), reinterpret_cast<uint32_t*>(ws + w.s1v_b)};
-  int32_t* tiles_sorted = reinterpret_cast<int32_t*>(ws + w.tiles_sorted);
-  int64_t* offs2 = reinterpret_cast<int64_t*>(ws + w.offs2);
-  uint32_t* hist = reinterpret_cast<uint32_t*>(ws + w.hist);
-  void* scan_ws = ws + w.scan;
-
-  // stage 1: visible splats by (depth bits, Gaussian id)
-  stage1_fill_kernel<<<ceil_div(n_slots, 256), 256, 0, stream>>>(splats, n_slots, isect_offsets, s1k[0], s1v[0]);
-  BDS_CHECK_LAUNCH();
-  int b1 = 0;
-  if (int rc = radix_sort_pairs<uint32_t>(s1k, s1v, n_slots, 32, hist, scan_ws, stream, &b1)) return rc;
-  // stage 2: emit in that order, stable sort on the band tile index
-  gather_tiles_kernel<<<ceil_div(n_slots, 256), 256, 0, stream>>>(splats, s1v[b1], n_slots, tiles_touched, tiles_sorted);
-  BDS_CHECK_LAUNCH();
-  if (int rc = exclusive_scan<int32_t, int64_t>(tiles_sorted, offs2, n_slots, nullptr, scan_ws, stream)) return rc;
+  SortWorkspace w = carve_sort(n_isect, n_tiles);
+  uint64_t* keys = reinterpret_cast<uint64_t*>(ws + w.keys);
+  uint32_t* slots = reinterpret_cast<uint32_t*>(ws + w.slots);
+  int32_t* cursors = reinterpret_cast<int32_t*>(ws + w.cursors);
+  // sentinels: a position the emission never fills sorts last and gathers a null record
+  BDS_CHECK_CUDA(cudaMemsetAsync(keys, 0xff, (size_t)n_isect * 8, stream));
+  BDS_CHECK_CUDA(cudaMemsetAsync(slots, 0xff, (size_t)n_isect * 4, stream));
+  BDS_CHECK_CUDA(cudaMemsetAsync(cursors, 0, (size_t)(n_tiles + 1) * 4, stream));
   EmitParams ep;
-  ep.d = *d; ep.tile_w = tile_w; ep.tile_h = tile_h; ep.radii = radii; ep.tiles_sorted = tiles_sorted; ep.offsets = offs2;
-  ep.sorted_slots = s1v[b1]; ep.n_tiles = n_tiles; ep.n_slots = n_slots; ep.splats = splats; ep.keys = keys[0];
-  ep.vals = vals[0];
-  {
-    static const uint32_t primes[] = {2654435761u, 2246822519u, 3266489917u, 668265263u, 374761393u};
-    ep.perm_mul = 1;
-    for (uint32_t pr : primes)
-      if ((uint64_t)n_slots % pr != 0) { ep.perm_mul = pr; break; }  // prime not dividing n => bijection mod n
-  }
-  emit_keys_kernel<<<ceil_div(n_slots, 256), 256, 0, stream>>>(ep);
+  ep.d = *d; ep.tile_w = tile_w; ep.tile_h = tile_h; ep.radii = radii; ep.tile_offsets = tile_offsets;
+  ep.cursors = cursors; ep.n_slots = n_slots; ep.splats = splats; ep.keys = keys; ep.slots = slots;
+  emit_pairs_kernel<<<ceil_div(n_slots, 256), 256, 0, stream>>>(ep);
   BDS_CHECK_LAUNCH();
-  int b2 = 0;
-  if (int rc = radix_sort_pairs<uint32_t>(keys, vals, n_isect, tile_bits_for(n_tiles + 1), hist, scan_ws, stream, &b2)) return rc;
-  tile_offsets_kernel<<<ceil_div(n_isect, 256), 256, 0, stream>>>(keys[b2], n_isect, n_tiles, tile_offsets);
+  tile_sort_gather_kernel<kTileSortSmall, false><<<n_tiles, 256, 0, stream>>>(
+      tile_offsets, keys, slots, reinterpret_cast<const float4*>(splats), reinterpret_cast<float4*>(sorted_splats),
+      sorted_slots);
   BDS_CHECK_LAUNCH();
-  gather_records_kernel<<<ceil_div(n_isect * 3, 256), 256, 0, stream>>>(vals[b2], n_isect,
-                                                                       reinterpret_cast<const float4*>(splats),
-                                                                       reinterpret_cast<float4*>(sorted_splats));
+  tile_sort_gather_kernel<kTileSortCap, true><<<n_tiles, 256, 0, stream>>>(
+      tile_offsets, keys, slots, reinterpret_cast<const float4*>(splats), reinterpret_cast<float4*>(sorted_splats),
+      sorted_slots);
   BDS_CHECK_LAUNCH();
-  if (sorted_slots)
-    BDS_CHECK_CUDA(cudaMemcpyAsync(sorted_slots, vals[b2], (size_t)n_isect * 4, cudaMemcpyDeviceToDevice, stream));
   return 0;
 }

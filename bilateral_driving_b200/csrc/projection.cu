@@ -19,6 +19,7 @@ struct ProjParams {
   int32_t* radii;
   float *means2d, *depths, *conics, *compensations;
   int32_t* tiles_touched;
+  int32_t* tile_counts;  // [band tiles + 1] per-tile record counts (atomics), or NULL
   float* splats;
   int32_t splat_cap;
   int32_t* slot_of;
@@ -239,10 +240,13 @@ __global__ void __launch_bounds__(kProjBlock) project_fwd_kernel(ProjParams p, i
           const float gx = __shfl_sync(0xffffffffu, mx, owner), gy = __shfl_sync(0xffffffffu, my, owner);
           const float ga = __shfl_sync(0xffffffffu, qa, owner), gb = __shfl_sync(0xffffffffu, qb, owner);
           const float gc = __shfl_sync(0xffffffffu, qc, owner), gcut = __shfl_sync(0xffffffffu, sigma_cut, owner);
+          const int gcam = __shfl_sync(0xffffffffu, c, owner);
           bool hit = false;
           if (base + lane < total) {
             const int ry = local / ow;
-            hit = tile_hit(gx, gy, ga, gb, gc, gcut, ox0 + local - ry * ow, oy0 + ry, p.d.width, p.d.height);
+            const int tx = ox0 + local - ry * ow, ty = oy0 + ry;
+            hit = tile_hit(gx, gy, ga, gb, gc, gcut, tx, ty, p.d.width, p.d.height);
+            if (hit && p.tile_counts) atomicAdd(p.tile_counts + ((gcam * p.tile_h + ty - p.d.row_begin) * p.tile_w + tx), 1);
           }
           const unsigned hm = __ballot_sync(0xffffffffu, hit);
           const unsigned grp = __match_any_sync(0xffffffffu, owner);
@@ -507,10 +511,14 @@ extern "C" int bds_project_fwd(const bds_render_desc* d, const float* means, con
                                const float* opacities, const float* colors, int colors_per_cam,
                                const float* features_dc, const float* features_rest, const float* viewmats,
                                const float* Ks, int32_t* radii, float* means2d, float* depths, float* conics,
-                               float* compensations, int32_t* tiles_touched, float* splats, int32_t splat_cap,
-                               int32_t* slot_of, int32_t* counters, bds_stream_t stream) {
+                               float* compensations, int32_t* tiles_touched, int32_t* tile_counts, float* splats,
+                               int32_t splat_cap, int32_t* slot_of, int32_t* counters, bds_stream_t stream) {
   if (int rc = check_render_desc(d)) return rc;
   int64_t total = (int64_t)d->n_gauss * d->n_cams;
+  if (tile_counts)
+    BDS_CHECK_CUDA(cudaMemsetAsync(tile_counts, 0,
+                                   ((size_t)(d->row_end - d->row_begin) * ((d->width + kTile - 1) / kTile) + 1) * sizeof(int32_t),
+                                   static_cast<cudaStream_t>(stream)));
   if (total == 0) return 0;
   BDS_REQUIRE(means && quats && scales && opacities && viewmats && Ks && tiles_touched && splats && counters,
               "project_fwd: null pointer");
@@ -525,8 +533,8 @@ extern "C" int bds_project_fwd(const bds_render_desc* d, const float* means, con
   p.means = means; p.quats = quats; p.scales = scales; p.opacities = opacities; p.colors = colors;
   p.fdc = features_dc; p.frest = features_rest; p.viewmats = viewmats; p.Ks = Ks; p.colors_per_cam = colors_per_cam;
   p.radii = radii; p.means2d = means2d; p.depths = depths; p.conics = conics; p.compensations = compensations;
-  p.tiles_touched = tiles_touched; p.splats = splats; p.splat_cap = splat_cap; p.slot_of = slot_of; p.counters = counters;
-  // tiles_touched of cameras outside the band must read 0 for the scan: the caller's buffer may be fresh
+  p.tiles_touched = tiles_touched; p.tile_counts = tile_counts; p.splats = splats; p.splat_cap = splat_cap; p.slot_of = slot_of; p.counters = counters;
+  // cameras outside the band are never visited: their tiles_touched must read 0 (the caller's buffer may be fresh)
   BDS_CHECK_CUDA(cudaMemsetAsync(tiles_touched, 0, (size_t)total * sizeof(int32_t), static_cast<cudaStream_t>(stream)));
   const int sh_floats = d->sh_degree >= 0 ? 3 * d->sh_K : 0;
   const size_t smem = proj_smem_bytes(sh_floats);

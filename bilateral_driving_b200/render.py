@@ -152,31 +152,30 @@ class _RenderFn(torch.autograd.Function):
             means2d = depths = conics = None
         comps = torch.zeros(Cn, N, **f32) if (cfg.antialiased and cfg.dense_info) else None
         tiles_touched = torch.empty(Cn, N, **i32)
+        tile_counts = torch.empty(n_band_tiles + 1, **i32)
         counters = torch.zeros(4, **i32)
         cap = cfg.splat_capacity or max(Cn * N, 1)
         splats = torch.empty(cap, 12, **f32)
         st = stream_ptr()
         check(lib.bds_project_fwd(C.byref(d), ptr(means), ptr(quats), ptr(scales), ptr(opacities), ptr(colors),
                                   colors_per_cam, ptr(fdc), ptr(frest), ptr(viewmats), ptr(Ks), ptr(radii),
-                                  ptr(means2d), ptr(depths), ptr(conics), ptr(comps), ptr(tiles_touched), ptr(splats),
-                                  C.c_int32(cap), NULL, ptr(counters), st), "bds_project_fwd")
-        offsets = torch.empty(Cn * N, device=dev, dtype=torch.int64)
+                                  ptr(means2d), ptr(depths), ptr(conics), ptr(comps), ptr(tiles_touched), ptr(tile_counts),
+                                  ptr(splats), C.c_int32(cap), NULL, ptr(counters), st), "bds_project_fwd")
         stats = torch.zeros(1, device=dev, dtype=torch.int64)
-        ws0 = torch.empty(int(lib.bds_bin_count_workspace_bytes(C.c_int64(Cn * N))), device=dev, dtype=torch.uint8)
-        check(lib.bds_bin_count(C.byref(d), ptr(tiles_touched), ptr(offsets), ptr(stats), ptr(ws0), st), "bds_bin_count")
+        tile_offsets = torch.empty(n_band_tiles + 1, **i32)
+        ws0 = torch.empty(int(lib.bds_bin_count_workspace_bytes(C.byref(d))), device=dev, dtype=torch.uint8)
+        check(lib.bds_bin_count(C.byref(d), ptr(tile_counts), ptr(tile_offsets), ptr(stats), ptr(ws0), st), "bds_bin_count")
         # the one host sync of the step: intersection count (sizes the sort) + slot count / overflow flag
         host = torch.cat([stats, counters[:2].to(torch.int64)]).tolist()
         n_isect, n_slots, overflow = int(host[0]), int(host[1]), int(host[2])
         if overflow:
             raise BdsError(f"splat capacity {cap} exceeded ({n_slots} visible splats); raise RenderCfg.splat_capacity")
         sorted_splats = torch.empty(max(n_isect, 1), 12, **f32)
-        tile_offsets = torch.empty(n_band_tiles + 1, **i32)
         ws1 = torch.empty(int(lib.bds_bin_sort_workspace_bytes(C.byref(d), C.c_int64(n_isect))), device=dev,
                           dtype=torch.uint8)
-        check(lib.bds_bin_sort(C.byref(d), C.c_int64(n_isect), C.c_int32(n_slots), ptr(radii), ptr(tiles_touched),
-                               ptr(offsets), ptr(splats), ptr(sorted_splats), NULL, ptr(tile_offsets), ptr(ws1), st),
-              "bds_bin_sort")
-        del ws1, offsets
+        check(lib.bds_bin_sort(C.byref(d), C.c_int64(n_isect), C.c_int32(n_slots), ptr(radii), ptr(splats),
+                               ptr(tile_offsets), ptr(sorted_splats), NULL, ptr(ws1), st), "bds_bin_sort")
+        del ws1
         ch = cfg.channels if cfg.mode == 0 else 3
         out_rgb = torch.empty(P, ch, **f32)
         out_alpha = torch.empty(P, **f32)
@@ -228,7 +227,12 @@ class _RenderFn(torch.autograd.Function):
         need = ctx.needs_input_grad  # (cfg, holder, means, quats, scales, opac, colors, fdc, frest, viewmats, Ks, bg, sky, *grids)
         v_sky = torch.empty_like(sky) if (sky is not None and need[12]) else None
         v_bg = torch.zeros_like(backgrounds) if (backgrounds is not None and need[11]) else None
-        v_grids = [None if g is None else torch.zeros_like(g) for g in grids]
+        # all grid-slot gradients are carved out of ONE zero-filled buffer (one fill instead of C x levels)
+        g_flat = torch.zeros(sum(g.numel() for g in grids if g is not None), **f32)
+        v_grids, g_off = [], 0
+        for g in grids:
+            v_grids.append(None if g is None else g_flat[g_off:g_off + g.numel()].view(g.shape))
+            g_off += 0 if g is None else g.numel()
         ws2 = torch.empty(int(lib.bds_composite_workspace_bytes(C.byref(d), C.byref(e))), device=dev, dtype=torch.uint8)
         with _timed("composite_bwd"):
             check(lib.bds_composite_bwd(C.byref(d), C.byref(e), ptr(sorted_splats), NULL, ptr(tile_offsets),

@@ -120,7 +120,9 @@ typedef struct {
 /* Projection (+ optional activations and SH).  Writes gsplat-shaped per-(cam,gauss) outputs
  * radii [C,N] int32, means2d [C,N,2], depths [C,N], conics [C,N,3], (compensations [C,N] or NULL),
  * tiles_touched [C,N] int32 (exact number of (tile) records the Gaussian will emit inside the
- * band), and compacts the visible splats into packed 48-byte records:
+ * band), tile_counts [band tiles + 1] int32 (records per band tile, last entry 0; zero-filled by the
+ * call; band tile t = (global_row - row_begin)*tile_w + tx), and compacts the visible splats into
+ * packed 48-byte records:
  *   splats [cap,12] = {x, y, a', b', c', opacity, r, g, b, depth, bits(flat id c*N+n), log2(opacity)}
  * with (a',b',c') = log2(e) * (a/2, b, c/2) of the conic (alpha = exp2(log2(opacity) - sigma'));
  * slot_of [C,N] int32 = record index or -1 (optional, may be NULL); counters[0] = number of records (device int32,
@@ -131,26 +133,25 @@ int bds_project_fwd(const bds_render_desc* d, const float* means, const float* q
                     int colors_per_cam, const float* features_dc /*[N,3] or NULL*/,
                     const float* features_rest /*[N,K-1,3] or NULL*/, const float* viewmats,
                     const float* Ks, int32_t* radii, float* means2d, float* depths, float* conics,
-                    float* compensations, int32_t* tiles_touched, float* splats, int32_t splat_cap,
-                    int32_t* slot_of, int32_t* counters, bds_stream_t stream);
+                    float* compensations, int32_t* tiles_touched, int32_t* tile_counts, float* splats,
+                    int32_t splat_cap, int32_t* slot_of, int32_t* counters, bds_stream_t stream);
 
-/* Binning: scan of tiles_touched, depth sort of the visible splats, emission of (tile, slot) records in
- * (depth, id) order, stable radix sort on the tile, per-tile start offsets, gather of the packed records.
- * Two steps because the intersection count is data dependent:
- *   bds_bin_count   -> isect_offsets [C*N] int64 = exclusive scan of a packed count: bits 40.. hold the
- *                      id-ordered rank among splats with tiles_touched > 0, bits 0..39 the record prefix;
+/* Binning: per-tile start offsets from the per-tile counts, emission of every (tile, splat) pair into its
+ * tile's segment (atomic cursor per tile), ONE CTA per tile sorts its segment by (depth bits, Gaussian
+ * id) - shared memory up to 4096 records, in place in global memory beyond - and gathers the packed
+ * records in that order.  Two steps because the record count is data dependent:
+ *   bds_bin_count   -> tile_offsets [band tiles + 1] int32 = exclusive scan of tile_counts;
  *                      n_isect_dev (device int64) = total number of records
- *   (caller reads n_isect, allocates)   bds_bin_sort -> sorted records + tile_offsets. */
-size_t bds_bin_count_workspace_bytes(int64_t n_elems);
-int bds_bin_count(const bds_render_desc* d, const int32_t* tiles_touched, int64_t* isect_offsets /*[C*N]*/,
-                  int64_t* n_isect_dev, void* workspace, bds_stream_t stream);
+ *   (caller reads n_isect, allocates)   bds_bin_sort -> sorted records. */
+size_t bds_bin_count_workspace_bytes(const bds_render_desc* d);
+int bds_bin_count(const bds_render_desc* d, const int32_t* tile_counts /*[band tiles + 1]*/,
+                  int32_t* tile_offsets /*[band tiles + 1]*/, int64_t* n_isect_dev, void* workspace,
+                  bds_stream_t stream);
 size_t bds_bin_sort_workspace_bytes(const bds_render_desc* d, int64_t n_isect);
-/* sorted_splats [n_isect,12]; sorted_slots [n_isect] int32 (record -> splat slot);
- * tile_offsets [n_band_tiles + 1] int32 where band tile t = (global_row - row_begin)*tile_w + tx */
+/* sorted_splats [n_isect,12] (field 10 = splat slot); sorted_slots [n_isect] int32 or NULL */
 int bds_bin_sort(const bds_render_desc* d, int64_t n_isect, int32_t n_slots /* = counters[0] */,
-                 const int32_t* radii, const int32_t* tiles_touched, const int64_t* isect_offsets,
-                 const float* splats, float* sorted_splats, int32_t* sorted_slots,
-                 int32_t* tile_offsets, void* workspace, bds_stream_t stream);
+                 const int32_t* radii, const float* splats, const int32_t* tile_offsets,
+                 float* sorted_splats, int32_t* sorted_slots, void* workspace, bds_stream_t stream);
 
 /* Epilogue description for the fused composite kernel. */
 typedef struct {
