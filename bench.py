@@ -32,6 +32,10 @@ if ROOT not in sys.path:
 METRIC = "fwd+bwd Mpix/s at 2M Gaussians, 6x1080p; achieved HBM GB/s vs B200 peak"
 UNIT = "Mpix/s"
 LAMBDA_D, LAMBDA_A, TV_W = 0.01, 0.05, 1.0
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the roofline kernel on the default workload
+# (2 M Gaussians, 6 x 1920x1080, N=1), from the `ncu --set full` capture summarised in
+# profiles/r01_ncu_full_key_metrics.txt (0.671667 GB read + 0.421343 GB written).  Reported only for that workload.
+NCU_TRAFFIC_BYTES = {"full": 671_667_000 + 421_342_720}
 
 
 def parse():
@@ -317,6 +321,7 @@ def main():
             dist.destroy_process_group()
         return
     peak, peak_src = measured_peaks()
+    default_workload = (world == 1 and (N, Cn, W, H) == (2_000_000, 6, 1920, 1080))
     I, Nv = info_box["n_isect"], info_box["n_visible"]
     V = 12 * sum(gx * gy * gl for gx, gy, gl in sizes)
     band_px = rows * W
@@ -342,7 +347,9 @@ def main():
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": "composite_fwd_kernel<2> (fused composite + glue + bilateral)" if args.guidance == "full" else "composite_fwd_kernel<1> (composite + glue)",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
-                     "algorithmic_bytes": b_fwd, "traffic": None},
+                     "algorithmic_bytes": b_fwd,
+                     "traffic": NCU_TRAFFIC_BYTES.get(args.guidance) if default_workload else None,
+                     "traffic_source": "ncu --set full, profiles/r01_ncu_full_key_metrics.txt" if default_workload and args.guidance in NCU_TRAFFIC_BYTES else None},
     }
     if world == 1 and not args.no_cpu_baseline:
         # CPU baseline on the box's host cores: bounded sample = ONE camera image, 1 warm-up + 2 timed
