@@ -49,6 +49,7 @@ def parse():
     ap.add_argument("--width", type=int, default=1920)
     ap.add_argument("--height", type=int, default=1080)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--breakdown", action="store_true", help="print the per-phase CUDA-event times of rank 0 to stderr")
     ap.add_argument("--guidance", default="full", choices=["full", "lowres"],
                     help="full: guidance_factor=None fused in the composite kernel (headline); lowres: the reference's "
                          "default [4,4,2] = composite mode 1 + stand-alone low-res bilateral kernels")
@@ -253,7 +254,8 @@ def main():
             for lvl, g in enumerate(grids):
                 loss = loss + total_variation_loss(g, TV_W * 0.5 * (sizes[lvl][0] * sizes[lvl][1] * sizes[lvl][2]) ** 0.5)
         loss.backward()
-        allreduce_grads([t.grad for t in leaves], flat=out["info"].get("grad_flat"))
+        with render._timed("allreduce"):
+            allreduce_grads([t.grad for t in leaves], flat=out["info"].get("grad_flat"))
         info_box.update(n_isect=out["info"]["n_isect"], n_visible=out["info"]["n_visible"])
         return loss
 
@@ -293,6 +295,11 @@ def main():
     render.KERNEL_EVENTS = None
     t_fwd = sum(a.elapsed_time(b) for a, b in ev.get("composite_fwd", [])) / max(len(ev.get("composite_fwd", [])), 1)
     t_bwd = sum(a.elapsed_time(b) for a, b in ev.get("composite_bwd", [])) / max(len(ev.get("composite_bwd", [])), 1)
+
+    if args.breakdown and rank == 0:
+        parts = {k: sum(a.elapsed_time(b) for a, b in v) / args.steps for k, v in ev.items()}
+        parts["other (loss, TV, fills, gaps)"] = ms / args.steps - sum(parts.values())
+        sys.stderr.write("phase ms/step: " + json.dumps({k: round(v, 3) for k, v in parts.items()}) + "\n")
 
     # end to end through the public API with HOST buffers: GT image + cameras copied from pinned
     # memory every step, loss read back

@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libbds_b200.so")
+# BDS_LIB selects another build of the same library (profiling aid: libbds_b200_stats.so); never a fallback
+LIB_PATH = os.path.join(_HERE, os.environ.get("BDS_LIB", "libbds_b200.so"))
 MAX_LEVELS = 4
 TILE = 16
 SPLAT_FLOATS = 12

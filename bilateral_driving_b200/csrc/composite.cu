@@ -471,6 +471,21 @@ __global__ void __launch_bounds__(256, 4) composite_bwd_kernel(CompParams p) {
           float araw = exp2f(e);                       // opacity * exp(-sigma)
           float alpha = fminf(kAlphaMax, araw);
           bool valid = g.inside && gidx <= last && e <= r2.w && e >= -kLog2_255;
+#ifdef BDS_STATS
+          {
+            unsigned vm = __ballot_sync(kFull, valid);
+            if (lane == 0) {
+              atomicAdd(&g_stats[10], 1ull);                                    // survivors of the rectangle cull
+              atomicAdd(&g_stats[11], vm ? 1ull : 0ull);                        // evaluations (any valid lane)
+              atomicAdd(&g_stats[12], (unsigned long long)__popc(vm));          // valid (pixel, record) pairs
+              // 4x4 halves (lanes with (lane & 7) < 4 = left) that hold a valid lane
+              unsigned left = 0x0f0f0f0fu;
+              atomicAdd(&g_stats[13], (unsigned long long)(((vm & left) != 0) + ((vm & ~left) != 0)));
+              atomicAdd(&g_stats[14], (unsigned long long)(__popc(vm) <= 2 && vm ? 1 : 0));
+              atomicAdd(&g_stats[15], (unsigned long long)(__popc(vm) <= 8 && vm ? 1 : 0));
+            }
+          }
+#endif
           if (!__any_sync(kFull, valid)) continue;
           float v[16];
 #pragma unroll

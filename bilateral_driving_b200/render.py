@@ -30,8 +30,8 @@ from ._lib import (TILE, BdsError, BilateralDesc, EpilogueDesc, RenderDesc, chec
 
 NULL = C.c_void_p(0)
 
-# bench.py sets this to a dict of lists to collect CUDA-event pairs around the dominant kernels
-# (recorded on the launching stream): keys "composite_fwd", "composite_bwd".
+# bench.py sets this to a dict of lists to collect CUDA-event pairs around the C-ABI calls (recorded on the
+# launching stream): keys "project_fwd", "bin_sort", "composite_fwd", "composite_bwd", "project_bwd".
 KERNEL_EVENTS: Optional[dict] = None
 
 
@@ -157,10 +157,12 @@ class _RenderFn(torch.autograd.Function):
         cap = cfg.splat_capacity or max(Cn * N, 1)
         splats = torch.empty(cap, 12, **f32)
         st = stream_ptr()
-        check(lib.bds_project_fwd(C.byref(d), ptr(means), ptr(quats), ptr(scales), ptr(opacities), ptr(colors),
-                                  colors_per_cam, ptr(fdc), ptr(frest), ptr(viewmats), ptr(Ks), ptr(radii),
-                                  ptr(means2d), ptr(depths), ptr(conics), ptr(comps), ptr(tiles_touched), ptr(tile_counts),
-                                  ptr(splats), C.c_int32(cap), NULL, ptr(counters), st), "bds_project_fwd")
+        with _timed("project_fwd"):
+            check(lib.bds_project_fwd(C.byref(d), ptr(means), ptr(quats), ptr(scales), ptr(opacities), ptr(colors),
+                                      colors_per_cam, ptr(fdc), ptr(frest), ptr(viewmats), ptr(Ks), ptr(radii),
+                                      ptr(means2d), ptr(depths), ptr(conics), ptr(comps), ptr(tiles_touched),
+                                      ptr(tile_counts), ptr(splats), C.c_int32(cap), NULL, ptr(counters), st),
+                  "bds_project_fwd")
         stats = torch.zeros(1, device=dev, dtype=torch.int64)
         tile_offsets = torch.empty(n_band_tiles + 1, **i32)
         ws0 = torch.empty(int(lib.bds_bin_count_workspace_bytes(C.byref(d))), device=dev, dtype=torch.uint8)
@@ -173,8 +175,9 @@ class _RenderFn(torch.autograd.Function):
         sorted_splats = torch.empty(max(n_isect, 1), 12, **f32)
         ws1 = torch.empty(int(lib.bds_bin_sort_workspace_bytes(C.byref(d), C.c_int64(n_isect))), device=dev,
                           dtype=torch.uint8)
-        check(lib.bds_bin_sort(C.byref(d), C.c_int64(n_isect), C.c_int32(n_slots), ptr(radii), ptr(splats),
-                               ptr(tile_offsets), ptr(sorted_splats), NULL, ptr(ws1), st), "bds_bin_sort")
+        with _timed("bin_sort"):
+            check(lib.bds_bin_sort(C.byref(d), C.c_int64(n_isect), C.c_int32(n_slots), ptr(radii), ptr(splats),
+                                   ptr(tile_offsets), ptr(sorted_splats), NULL, ptr(ws1), st), "bds_bin_sort")
         del ws1
         ch = cfg.channels if cfg.mode == 0 else 3
         out_rgb = torch.empty(P, ch, **f32)
@@ -265,11 +268,12 @@ class _RenderFn(torch.autograd.Function):
         extra = None
         if v_means2d_extra is not None and v_means2d_extra.numel() > 0:
             extra = v_means2d_extra.contiguous().float()
-        check(lib.bds_project_bwd(C.byref(d), ptr(means), ptr(quats), ptr(scales), ptr(opacities), ptr(colors),
-                                  ctx.colors_per_cam, ptr(fdc), ptr(frest), ptr(viewmats), ptr(Ks), ptr(splats),
-                                  ptr(counters), ptr(v_splats), ptr(extra), NULL, NULL, ptr(v_means), ptr(v_quats),
-                                  ptr(v_scales), ptr(v_opac), ptr(v_colors), ptr(v_fdc), ptr(v_frest), ptr(v_view),
-                                  ptr(v_m2d), ptr(absg), st), "bds_project_bwd")
+        with _timed("project_bwd"):
+            check(lib.bds_project_bwd(C.byref(d), ptr(means), ptr(quats), ptr(scales), ptr(opacities), ptr(colors),
+                                      ctx.colors_per_cam, ptr(fdc), ptr(frest), ptr(viewmats), ptr(Ks), ptr(splats),
+                                      ptr(counters), ptr(v_splats), ptr(extra), NULL, NULL, ptr(v_means), ptr(v_quats),
+                                      ptr(v_scales), ptr(v_opac), ptr(v_colors), ptr(v_fdc), ptr(v_frest), ptr(v_view),
+                                      ptr(v_m2d), ptr(absg), st), "bds_project_bwd")
         # densification taps (base.py:279-297 reads info["means2d"].grad / .absgrad)
         ref = ctx.holder.get("means2d_ref")
         m2d = ref() if ref is not None else None
