@@ -131,8 +131,10 @@ __global__ void __launch_bounds__(256, 5) composite_fwd_kernel(CompParams p) {
   const float rxmin = g.wx0 + 0.5f, rxmax = g.wx0 + 7.5f, rymin = g.wy0 + 0.5f, rymax = g.wy0 + 3.5f;
   float T = 1.f, cr = 0.f, cg = 0.f, cb = 0.f, cd = 0.f;
   int last = -1;
-  bool done = !g.inside;
-  bool warp_done = __all_sync(kFull, done);
+  // alpha >= 1/255  <=>  e >= -log2(255); a saturated (or outside) pixel raises its threshold to +inf, so
+  // "done" costs no extra test in the blend loop
+  float emin = g.inside ? -kLog2_255 : INFINITY;
+  bool warp_done = __all_sync(kFull, !g.inside);
 
   int waited = 0;
   for (int k = 0; k < nchunks; ++k) {
@@ -145,6 +147,7 @@ __global__ void __launch_bounds__(256, 5) composite_fwd_kernel(CompParams p) {
     if (!warp_done) {
       const int cnt = min(kChunk, n - k * kChunk);
       const float4* sr = &srec[st][0];
+      const int idx0 = g.start + k * kChunk;
       for (int base = 0; base < cnt && !warp_done; base += 32) {
         // lane j tests record base+j against the warp's 8x4 pixel rectangle
         int j = base + lane;
@@ -191,29 +194,27 @@ __global__ void __launch_bounds__(256, 5) composite_fwd_kernel(CompParams p) {
           // e = log2(opacity) - sigma', sigma' = a' dx^2 + b' dx dy + c' dy^2  (alpha = 2^e)
           float e = fmaf(-dx, fmaf(r0.w, dy, r0.z * dx), r2.w);
           e = fmaf(-(r1.x * dy), dy, e);
-          float alpha = fminf(kAlphaMax, exp2f(e));
+          const float alpha = fminf(kAlphaMax, exp2f(e));
+          const bool ok = e >= emin && e <= r2.w;   // alpha >= 1/255 (and not saturated) and sigma' >= 0
 #ifdef BDS_STATS
           {
-            unsigned vm = __ballot_sync(kFull, !done && e <= r2.w && e >= -kLog2_255);
+            unsigned vm = __ballot_sync(kFull, ok);
             if (lane == 0) atomicAdd(&g_stats[8], (unsigned long long)__popc(vm));
           }
 #endif
-          if (!done && e <= r2.w && e >= -kLog2_255) {  // sigma' >= 0 and alpha >= 1/255
-            float nT = T * (1.f - alpha);
-            if (nT <= kTStop) {
-              done = true;
-            } else {
-              float vis = alpha * T;
-              cr = fmaf(vis, r1.z, cr);
-              cg = fmaf(vis, r1.w, cg);
-              cb = fmaf(vis, r2.x, cb);
-              cd = fmaf(vis, r2.y, cd);
-              T = nT;
-              last = g.start + k * kChunk + jj;
-            }
-          }
+          // branch-free blend step: the rectangle cull leaves records most lanes need anyway
+          const float nT = T * (1.f - alpha);
+          const bool go = ok && nT > kTStop;         // gsplat stops BEFORE adding the saturating record
+          const float vis = go ? alpha * T : 0.f;
+          cr = fmaf(vis, r1.z, cr);
+          cg = fmaf(vis, r1.w, cg);
+          cb = fmaf(vis, r2.x, cb);
+          cd = fmaf(vis, r2.y, cd);
+          T = go ? nT : T;
+          last = go ? idx0 + jj : last;
+          emin = (ok && !go) ? INFINITY : emin;
         }
-        warp_done = __all_sync(kFull, done);
+        warp_done = __all_sync(kFull, emin > 0.f);
       }
     }
 #ifdef BDS_STATS
@@ -266,32 +267,103 @@ __global__ void __launch_bounds__(256, 5) composite_fwd_kernel(CompParams p) {
 // =================================================================================================
 // backward
 // =================================================================================================
-// Sum 16 per-lane values across the warp; afterwards lane L holds the total of value (L >> 1).
-BDS_D float warp_transpose_reduce16(float v[16]) {
-  const int lane = threadIdx.x & 31;
-#pragma unroll
-  for (int step = 0; step < 4; ++step) {
-    const int off = 16 >> step;        // 16, 8, 4, 2
-    const int half = 8 >> step;        // values kept after this step: 8, 4, 2, 1
-    const bool upper = (lane & off) != 0;
-#pragma unroll
-    for (int i = 0; i < half; ++i) {
-      float keep = upper ? v[i + half] : v[i];
-      float send = upper ? v[i] : v[i + half];
-      v[i] = keep + __shfl_xor_sync(kFull, send, off);
-    }
-  }
-  return v[0] + __shfl_xor_sync(kFull, v[0], 1);
+// Deferred per-record reduction.  Summing a record's per-pixel gradient terms across the 32 lanes right
+// away costs a 12-value transposing shuffle tree per (warp, record).  Instead the walk only stores the two
+// per-(pixel, record) scalars every gradient is linear in,
+//     w   = [alpha unclamped] * araw * v_alpha     (d loss / d log-ish opacity term; v_sigma' = -ln2 * w)
+//     fac = alpha * T                              (blend weight: v_colour = fac * v_C)
+// into a per-warp [kBatch records][32 pixels] shared-memory panel.  When kBatch records are pending the warp
+// TRANSPOSES the work: lane = (record, half of the 8x4 rectangle) walks its 16 pixels, forming the six
+// pixel-local moments of w (1, u, v, u^2, uv, v^2), the four colour sums and the two absgrad sums in
+// registers - no shuffles except one 16-lane fold - re-centres the moments on the record's mean and leaves
+// as three 128-bit vector reductions (red.global.add.v4.f32) into the record's 48-byte gradient line:
+//     {m_x, m_y, m_xx, m_xy, m_yy, m_0, v_r, v_g, v_b, v_depth, sum|w g_x|, sum|w g_y|}
+// with m_ab = sum_p w_p dx_p^a dy_p^b, (dx, dy) = mean2d - pixel centre, g = (2a' dx + b' dy, b' dx + 2c' dy).
+// project_bwd_kernel turns the moments into v_mean2d / v_conic / v_opacity (all linear in them).
+constexpr int kBStages = 2;            // backward: TMA stages of kChunk records
+constexpr int kBatch = 16;             // records per deferred-reduction batch
+constexpr int kPanelStride = 33;       // float2 per record row: 32 pixels + 1 pad (conflict-free transposed reads)
+
+struct BatchSmem {                     // per warp
+  float2 panel[kBatch * kPanelStride]; // {w, fac}
+  float4 meta0[kBatch];                // record {x, y, a', b'}
+  float2 meta1[kBatch];                // record {c', bits(slot)}
+  float4 vc[32];                       // per-pixel cotangent of the raw accumulators (C_r, C_g, C_b, D)
+};
+
+BDS_D void red_add_v4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+BDS_D float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
 }
 
-constexpr size_t kBwdSmemRec = (size_t)kStages * kChunk * kRecBytes;
-constexpr size_t kBwdSmem = kBwdSmemBil > kBwdSmemRec ? kBwdSmemBil : kBwdSmemRec;
+// rx0, ry0: centre of the warp rectangle's first pixel; nb: pending records (warp-uniform)
+BDS_D void flush_batch(const BatchSmem* bs, int nb, float rx0, float ry0, float* __restrict__ v_splats) {
+  __syncwarp();
+  const int lane = threadIdx.x & 31;
+  const int rec = lane & (kBatch - 1), half = lane >> 4;
+  const float2* row = bs->panel + rec * kPanelStride + half * 16;
+  const float4* vcp = bs->vc + half * 16;
+  const float4 q0 = bs->meta0[rec];
+  const float2 q1 = bs->meta1[rec];
+  const float X = q0.x - rx0, Y = q0.y - ry0;          // mean relative to pixel (u, v) = (0, 0)
+  const float A2 = 2.f * q0.z, B = q0.w, C2 = 2.f * q1.x;
+  float m0 = 0.f, mu = 0.f, mv = 0.f, muu = 0.f, muv = 0.f, mvv = 0.f;
+  float c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f, ax = 0.f, ay = 0.f;
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const float v = (float)(half * 2 + r);
+    const float dy = Y - v;
+    const float gxr = fmaf(A2, X, B * dy), gyr = fmaf(B, X, C2 * dy);   // g at u = 0
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const float2 d = row[r * 8 + u];
+      const float4 c = vcp[r * 8 + u];
+      s0 += d.x;
+      s1 = fmaf(d.x, (float)u, s1);
+      s2 = fmaf(d.x, (float)(u * u), s2);
+      c0 = fmaf(d.y, c.x, c0); c1 = fmaf(d.y, c.y, c1); c2 = fmaf(d.y, c.z, c2); c3 = fmaf(d.y, c.w, c3);
+      const float gx = fmaf(-A2, (float)u, gxr), gy = fmaf(-B, (float)u, gyr);
+      ax += fabsf(d.x * gx);
+      ay += fabsf(d.x * gy);
+    }
+    m0 += s0; mu += s1; muu += s2;
+    mv = fmaf(v, s0, mv); muv = fmaf(v, s1, muv); mvv = fmaf(v * v, s0, mvv);
+  }
+#define BDS_FOLD16(x) x += __shfl_xor_sync(kFull, x, 16)
+  BDS_FOLD16(m0); BDS_FOLD16(mu); BDS_FOLD16(mv); BDS_FOLD16(muu); BDS_FOLD16(muv); BDS_FOLD16(mvv);
+  BDS_FOLD16(c0); BDS_FOLD16(c1); BDS_FOLD16(c2); BDS_FOLD16(c3); BDS_FOLD16(ax); BDS_FOLD16(ay);
+#undef BDS_FOLD16
+  if (rec < nb) {
+    // pixel-local -> mean-centred moments: dx = X - u, dy = Y - v
+    const float mx = fmaf(X, m0, -mu), my = fmaf(Y, m0, -mv);
+    const float mxx = fmaf(X, mx - mu, muu);
+    const float mxy = fmaf(X, my, fmaf(-Y, mu, muv));
+    const float myy = fmaf(Y, my - mv, mvv);
+    float* dst = v_splats + (size_t)__float_as_int(q1.y) * 12;
+    if (half == 0) {
+      red_add_v4(dst, mx, my, mxx, mxy);
+      red_add_v4(dst + 4, myy, m0, c0, c1);
+    } else {
+      red_add_v4(dst + 8, c2, c3, ax, ay);
+    }
+  }
+  __syncwarp();
+}
+
+constexpr size_t kBwdSmemRec = (size_t)kBStages * kChunk * kRecBytes;
+constexpr size_t kBwdSmemWalk = kBwdSmemRec + 8 * sizeof(BatchSmem);
+constexpr size_t kBwdSmem = kBwdSmemBil > kBwdSmemWalk ? kBwdSmemBil : kBwdSmemWalk;
 
 template <int MODE>
 __global__ void __launch_bounds__(256, 4) composite_bwd_kernel(CompParams p) {
   extern __shared__ __align__(128) unsigned char dyn_smem[];
   float4 (*srec)[kChunk * 3] = reinterpret_cast<float4 (*)[kChunk * 3]>(dyn_smem);
-  __shared__ __align__(8) uint64_t bars[kStages];
+  __shared__ __align__(8) uint64_t bars[kBStages];
   __shared__ int s_last[8];
 
   const TileGeom g = tile_geom(p);
@@ -407,9 +479,13 @@ __global__ void __launch_bounds__(256, 4) composite_bwd_kernel(CompParams p) {
   for (int o = 16; o > 0; o >>= 1) wl = max(wl, __shfl_xor_sync(kFull, wl, o));
   if (lane == 0) s_last[warp] = wl;
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kStages; ++s) mbar_init(&bars[s], 1);
+    for (int s = 0; s < kBStages; ++s) mbar_init(&bars[s], 1);
     mbar_fence_init();
   }
+  // this warp's deferred-reduction panel (beyond the record stages; the bilateral prologue is done with
+  // the bytes it shared with them)
+  BatchSmem* bs = reinterpret_cast<BatchSmem*>(dyn_smem + kBwdSmemRec) + warp;
+  bs->vc[lane] = make_float4(vC[0], vC[1], vC[2], vC[3]);
   __syncthreads();
   int block_last = -1;
 #pragma unroll
@@ -421,7 +497,7 @@ __global__ void __launch_bounds__(256, 4) composite_bwd_kernel(CompParams p) {
   // chunks are walked from the back: walk index q = 0.. corresponds to chunk k = nchunks-1-q
   int issued = 0;
   if (threadIdx.x == 0) {
-    for (; issued < nchunks && issued < kStages; ++issued) {
+    for (; issued < nchunks && issued < kBStages; ++issued) {
       int k = nchunks - 1 - issued;
       int cnt = min(kChunk, n - k * kChunk);
       mbar_expect_tx(&bars[issued], cnt * kRecBytes);
@@ -431,20 +507,24 @@ __global__ void __launch_bounds__(256, 4) composite_bwd_kernel(CompParams p) {
 
   const float pxf = (float)g.px + 0.5f, pyf = (float)g.py + 0.5f;
   const float rxmin = g.wx0 + 0.5f, rxmax = g.wx0 + 7.5f, rymin = g.wy0 + 0.5f, rymax = g.wy0 + 3.5f;
-  float T = Tfin;
-  float buf[4] = {0.f, 0.f, 0.f, 0.f};
   // background: render = C + T_final * bg  ->  d/dalpha_i carries -T_final/(1-alpha_i) <bg, v>
   float bg_dot = 0.f;
   if (MODE == 0 && p.backgrounds) {
     bg_dot = bgv[0] * vC[0] + bgv[1] * vC[1] + bgv[2] * vC[2];
     if (p.channels == 4) bg_dot += bgv[3] * vC[3];
   }
-  const float vA_eff = vA - bg_dot;  // both multiply T_final / (1 - alpha_i)
+  // per-pixel walk state.  With S_i = sum over the records behind i of fac_j <c_j, v_C>:
+  //   v_alpha_i = T_i <c_i, v_C> - (S_i - T_final (v_A - <bg, v_C>)) / (1 - alpha_i)
+  // so ONE running scalar (bufdot) replaces the four colour buffers of the textbook form.
+  float T = Tfin;
+  float bufdot = -Tfin * (vA - bg_dot);
+  if (!g.inside) last = -1;   // pixels outside the image never match a record
+  int nb = 0;                 // records pending in this warp's panel (warp-uniform)
 
   for (int q = 0; q < nchunks; ++q) {
-    const int st = q % kStages;
+    const int st = q % kBStages;
     const int k = nchunks - 1 - q;
-    mbar_wait(&bars[st], (q / kStages) & 1);
+    mbar_wait(&bars[st], (q / kBStages) & 1);
     const int cnt = min(kChunk, n - k * kChunk);
     const int chunk0 = g.start + k * kChunk;
     if (warp_last >= chunk0) {
@@ -460,17 +540,15 @@ __global__ void __launch_bounds__(256, 4) composite_bwd_kernel(CompParams p) {
         }
         unsigned m = __ballot_sync(kFull, hit);
         while (m) {
-          int bit = 31 - __clz(m);
+          const int bit = 31 - __clz(m);
           m &= ~(1u << bit);
-          int jj = base + bit;
-          int gidx = chunk0 + jj;
-          float4 r0 = sr[jj * 3], r1 = sr[jj * 3 + 1], r2 = sr[jj * 3 + 2];
-          float dx = r0.x - pxf, dy = r0.y - pyf;
+          const int jj = base + bit;
+          const float4 r0 = sr[jj * 3], r1 = sr[jj * 3 + 1], r2 = sr[jj * 3 + 2];
+          const float dx = r0.x - pxf, dy = r0.y - pyf;
+          // e = log2(opacity) - sigma', sigma' = a' dx^2 + b' dx dy + c' dy^2  (alpha = 2^e)
           float e = fmaf(-dx, fmaf(r0.w, dy, r0.z * dx), r2.w);
           e = fmaf(-(r1.x * dy), dy, e);
-          float araw = exp2f(e);                       // opacity * exp(-sigma)
-          float alpha = fminf(kAlphaMax, araw);
-          bool valid = g.inside && gidx <= last && e <= r2.w && e >= -kLog2_255;
+          const bool valid = chunk0 + jj <= last && e <= r2.w && e >= -kLog2_255;
 #ifdef BDS_STATS
           {
             unsigned vm = __ballot_sync(kFull, valid);
@@ -487,40 +565,26 @@ __global__ void __launch_bounds__(256, 4) composite_bwd_kernel(CompParams p) {
           }
 #endif
           if (!__any_sync(kFull, valid)) continue;
-          float v[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = 0.f;
+          float w = 0.f, fac = 0.f;
           if (valid) {
-            float ra = 1.f / (1.f - alpha);
-            T *= ra;
-            float fac = alpha * T;
-            float col[4] = {r1.z, r1.w, r2.x, r2.y};
-            float v_alpha = 0.f;
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              v[6 + c] = fac * vC[c];
-              v_alpha = fmaf(col[c] * T - buf[c] * ra, vC[c], v_alpha);
-              buf[c] = fmaf(col[c], fac, buf[c]);
-            }
-            v_alpha = fmaf(Tfin * ra, vA_eff, v_alpha);
-            if (araw <= kAlphaMax) {
-              float v_s = -kLn2 * araw * v_alpha;         // d alpha / d sigma' = -ln2 * alpha
-              v[2] = v_s * dx * dx;
-              v[3] = v_s * dx * dy;
-              v[4] = v_s * dy * dy;
-              float vx = v_s * (2.f * r0.z * dx + r0.w * dy);
-              float vy = v_s * (r0.w * dx + 2.f * r1.x * dy);
-              v[0] = vx; v[1] = vy;
-              v[10] = fabsf(vx); v[11] = fabsf(vy);
-              v[5] = araw * v_alpha;                   // x 1/opacity after the reduction (linear)
-            }
+            const float araw = exp2f(e);                 // opacity * exp(-sigma)
+            const float alpha = fminf(kAlphaMax, araw);
+            const float ra = rcp_approx(1.f - alpha);
+            T *= ra;                                     // transmittance in front of this record
+            fac = alpha * T;
+            const float cdot = fmaf(r1.z, vC[0], fmaf(r1.w, vC[1], fmaf(r2.x, vC[2], r2.y * vC[3])));
+            const float v_alpha = fmaf(T, cdot, -ra * bufdot);
+            bufdot = fmaf(fac, cdot, bufdot);
+            w = araw <= kAlphaMax ? araw * v_alpha : 0.f;  // the clamp at 0.999 blocks the gradient
           }
-          float tot = warp_transpose_reduce16(v);
-          int comp = lane >> 1;
-          if (comp == 5) tot = __fdividef(tot, r1.y);   // v_opacity = sum(vis * v_alpha), vis = araw / opacity
-          if ((lane & 1) == 0 && comp < 12 && tot != 0.f) {
-            int slot = __float_as_int(r2.z);
-            red_add(p.v_splats + (size_t)slot * 12 + comp, tot);
+          bs->panel[nb * kPanelStride + lane] = make_float2(w, fac);
+          if (lane == 0) {
+            bs->meta0[nb] = r0;
+            bs->meta1[nb] = make_float2(r1.x, r2.z);
+          }
+          if (++nb == kBatch) {
+            flush_batch(bs, kBatch, rxmin, rymin, p.v_splats);
+            nb = 0;
           }
         }
       }
@@ -534,6 +598,7 @@ __global__ void __launch_bounds__(256, 4) composite_bwd_kernel(CompParams p) {
       ++issued;
     }
   }
+  if (nb > 0) flush_batch(bs, nb, rxmin, rymin, p.v_splats);
   // v_backgrounds: sum over pixels of T_final * v (MODE 0)
   if (MODE == 0 && p.v_backgrounds) {
     for (int c = 0; c < p.channels; ++c) {
@@ -738,8 +803,16 @@ extern "C" int bds_composite_bwd(const bds_render_desc* d, const bds_epilogue_de
     }
   }
   switch (e->mode) {
-    case 0: composite_bwd_kernel<0><<<n_tiles, 256, kBwdSmemRec, stream>>>(p); break;
-    case 1: composite_bwd_kernel<1><<<n_tiles, 256, kBwdSmemRec, stream>>>(p); break;
+    case 0:
+      BDS_CHECK_CUDA(cudaFuncSetAttribute(composite_bwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)kBwdSmemWalk));
+      composite_bwd_kernel<0><<<n_tiles, 256, kBwdSmemWalk, stream>>>(p);
+      break;
+    case 1:
+      BDS_CHECK_CUDA(cudaFuncSetAttribute(composite_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)kBwdSmemWalk));
+      composite_bwd_kernel<1><<<n_tiles, 256, kBwdSmemWalk, stream>>>(p);
+      break;
     default:
       BDS_CHECK_CUDA(cudaFuncSetAttribute(composite_bwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)kBwdSmem));

@@ -349,12 +349,18 @@ __global__ void __launch_bounds__(256) project_bwd_kernel(ProjBwdParams p) {
     const int N = p.d.n_gauss;
     c = (int)(idx / N);
     int n = (int)(idx - (int64_t)c * N);
-    // v_splats = {v_x, v_y, v_a', v_b', v_c', v_op, v_r, v_g, v_b, v_depth, |v_x|, |v_y|}
-    float vmx = g0.x, vmy = g0.y;
-    float va = g0.z * (0.5f * kLog2e), vb = g0.w * kLog2e, vc = g1.x * (0.5f * kLog2e);
-    float vop = g1.y, vr = g1.z, vg = g1.w, vbl = g2.x, vz = g2.y;
+    // v_splats = {m_x, m_y, m_xx, m_xy, m_yy, m_0, v_r, v_g, v_b, v_depth, sum|w g_x|, sum|w g_y|}: moments of
+    // w = araw * v_alpha over the pixels (composite.cu, flush_batch).  With sigma' = a' dx^2 + b' dx dy + c' dy^2
+    // and v_sigma' = -ln2 * w per pixel:  v_mean2d = -ln2 (2a' m_x + b' m_y, b' m_x + 2c' m_y),
+    // v_(a',b',c') = -ln2 (m_xx, m_xy, m_yy) and (a', b', c') = log2e (a/2, b, c/2)  =>  v_conic = (-m_xx/2, -m_xy, -m_yy/2);
+    // v_opacity = m_0 / opacity (alpha = opacity * vis).
+    float vmx = -kLn2 * fmaf(2.f * r0.z, g0.x, r0.w * g0.y);
+    float vmy = -kLn2 * fmaf(r0.w, g0.x, 2.f * r1.x * g0.y);
+    float va = -0.5f * g0.z, vb = -g0.w, vc = -0.5f * g1.x;
+    float vop = r1.y > 0.f ? g1.y / r1.y : 0.f;
+    float vr = g1.z, vg = g1.w, vbl = g2.x, vz = g2.y;
     if (p.v_means2d) { p.v_means2d[2 * idx] = vmx; p.v_means2d[2 * idx + 1] = vmy; }
-    if (p.absgrad) { p.absgrad[2 * idx] = g2.z; p.absgrad[2 * idx + 1] = g2.w; }
+    if (p.absgrad) { p.absgrad[2 * idx] = kLn2 * g2.z; p.absgrad[2 * idx + 1] = kLn2 * g2.w; }
     if (p.v_means2d_extra) { vmx += p.v_means2d_extra[2 * idx]; vmy += p.v_means2d_extra[2 * idx + 1]; }
     if (p.v_depths_extra) vz += p.v_depths_extra[idx];
     if (p.v_conics_extra) { va += p.v_conics_extra[3 * idx]; vb += p.v_conics_extra[3 * idx + 1]; vc += p.v_conics_extra[3 * idx + 2]; }
