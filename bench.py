@@ -179,17 +179,37 @@ def run_reference(args):
     val = H * W * len(times) / total / 1e6
     sample = ("bilateral half only (the reference's rasteriser is gsplat CUDA, no CPU path exists): oracle port of "
               "MultiScaleBilateralAffineTransform(guidance_factor=None)+apply, fwd+bwd, one 1920x1080 image per step")
-    print(json.dumps({
+    _emit({
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"bilateral fwd+bwd, 1 cam {W}x{H}, 3-scale grids 8/16/32, CPU torch {torch.__version__}"},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }))
+    })
+
+
+_JSON_OUT = None
+
+
+def _claim_stdout():
+    """stdout carries exactly ONE JSON line: everything else that writes to fd 1 (NCCL's version banner, library
+    chatter) is sent to stderr; the JSON line goes to the saved descriptor."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def _emit(line):
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def main():
+    _claim_stdout()
     args = parse()
     if args.impl == "reference":
         run_reference(args)
@@ -367,7 +387,7 @@ def main():
             "sample": f"oracle port of the reference's pure-PyTorch bilateral path (guidance_factor=None) fwd+bwd on one "
                       f"{W}x{H} image, best of 2 after 1 warm-up, {sec:.2f} s/iter; the rasteriser half has no CPU "
                       f"implementation in the reference (gsplat CUDA)"}
-    print(json.dumps(line))
+    _emit(line)
     if world > 1:
         dist.destroy_process_group()
 

@@ -231,7 +231,7 @@ __global__ void __launch_bounds__(256) apply_bwd_tiled_kernel(const float* __res
           for (int k = 0; k < 12; ++k) s = fmaf(vA[k], dAdz[k], s);
           v_lum += s * (float)(lv.L - 1);
         }
-        level_grad_accumulate(smem, t, vA, inside, tile_x0, tile_y0, ch.W, ch.H, lv.L, lv.GY, lv.GX, lv.v_grid_cl);
+        level_grad_accumulate(smem, t, vA, inside, lin01(tile_x0, ch.W), lin01(tile_y0, ch.H), lv.L, lv.GY, lv.GX, lv.v_grid_cl);
       }
     }
   }
@@ -284,7 +284,7 @@ __global__ void __launch_bounds__(256) lowres_slice_bwd_tiled_kernel(const float
       red_add(p11 + c, h1 * w1 * v);
     }
   }
-  level_grad_accumulate(smem, t, vA, inside, tile_x0, tile_y0, lv.Wd, lv.Hd, lv.L, lv.GY, lv.GX, lv.v_grid_cl);
+  level_grad_accumulate(smem, t, vA, inside, lin01(tile_x0, lv.Wd), lin01(tile_y0, lv.Hd), lv.L, lv.GY, lv.GX, lv.v_grid_cl);
 }
 
 // generic per-sample slice on the channel-first parameter layout (BilateralGrid.forward) ----------

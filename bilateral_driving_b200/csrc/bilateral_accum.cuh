@@ -29,8 +29,10 @@ constexpr int kSlotFloats = 16 * 96;  // last-run register sums of the 16 half-w
 constexpr size_t kBwdSmemBil =
     (size_t)(256 * kStageFloats + kWinFloats + kSlotFloats) * sizeof(float) + 2 * 160 * sizeof(int);
 
-BDS_D void level_grad_accumulate(float* smem, const Tri& t, const float vAff[12], bool valid, int tile_x0,
-                                 int tile_y0, int W, int H, int L, int GY, int GX, float* __restrict__ v_grid) {
+// tile_x01, tile_y01: lin01() of the tile's first pixel column / row (hoisted by the caller: one IEEE
+// division per axis per thread instead of one per level)
+BDS_D void level_grad_accumulate(float* smem, const Tri& t, const float vAff[12], bool valid, float tile_x01,
+                                 float tile_y01, int L, int GY, int GX, float* __restrict__ v_grid) {
   float* stage = smem;
   float* win = smem + 256 * kStageFloats;
   int* hist = reinterpret_cast<int*>(win + kWinFloats);  // [160] counts -> start offsets
@@ -38,8 +40,8 @@ BDS_D void level_grad_accumulate(float* smem, const Tri& t, const float vAff[12]
   int* slot_key = misc + 8;                              // [16] window offset of each half-warp's last run (-1: none)
   float* slot_val = reinterpret_cast<float*>(hist + 320);  // [16][12 lanes][a0 | a1]
   // window origin = cell of the tile's first pixel (uniform over the block)
-  const float fx0 = fminf(fmaxf(lattice_coord(tile_x0, W, GX), 0.f), (float)(GX - 1));
-  const float fy0 = fminf(fmaxf(lattice_coord(tile_y0, H, GY), 0.f), (float)(GY - 1));
+  const float fx0 = fminf(fmaxf(unit_coord(tile_x01, GX), 0.f), (float)(GX - 1));
+  const float fy0 = fminf(fmaxf(unit_coord(tile_y01, GY), 0.f), (float)(GY - 1));
   const int nx0 = (int)floorf(fx0), ny0 = (int)floorf(fy0);
   const bool use_win = L <= kWinMaxL;
   const int slab = kWinNodes * kWinNodes * 12;           // floats per z slab
@@ -98,31 +100,43 @@ BDS_D void level_grad_accumulate(float* smem, const Tri& t, const float vAff[12]
     float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
     int cur = -1;
     if (worker) {
-      for (int px = p0; px < p1; ++px) {
-        const float4* sp = reinterpret_cast<const float4*>(stage + px * kStageFloats);
-        const float4 m = sp[4];
-        const int base = __float_as_int(m.z);
-        const float4 va = sp[quad];
-        const float wc = stage[px * kStageFloats + 12 + corner];
-        if (base != cur) {  // run boundary inside the slice: flush the registers
-          if (cur >= 0) {
-            float* c0 = win + cur + coff;
-            if (a0.x != 0.f) atomicAdd(c0, a0.x);
-            if (a0.y != 0.f) atomicAdd(c0 + 1, a0.y);
-            if (a0.z != 0.f) atomicAdd(c0 + 2, a0.z);
-            if (a0.w != 0.f) atomicAdd(c0 + 3, a0.w);
-            if (a1.x != 0.f) atomicAdd(c0 + slab, a1.x);
-            if (a1.y != 0.f) atomicAdd(c0 + slab + 1, a1.y);
-            if (a1.z != 0.f) atomicAdd(c0 + slab + 2, a1.z);
-            if (a1.w != 0.f) atomicAdd(c0 + slab + 3, a1.w);
-          }
+      if (p0 < p1) {
+        // outer loop = runs of equal cell key, inner loop = the pixels of one run (register accumulation
+        // with nothing else live across it); the key of the next pixel rides on the float4 the next
+        // iteration needs anyway
+        const float* sp = stage + p0 * kStageFloats;
+        float4 m = *reinterpret_cast<const float4*>(sp + 16);
+        int px = p0;
+        for (;;) {
+          cur = __float_as_int(m.z);
           a0 = make_float4(0.f, 0.f, 0.f, 0.f);
           a1 = a0;
-          cur = base;
+          int key;
+          do {
+            const float4 va = *reinterpret_cast<const float4*>(sp + quad * 4);
+            const float wc = sp[12 + corner];
+            const float w0 = wc * m.x, w1 = wc * m.y;
+            a0.x = fmaf(w0, va.x, a0.x); a0.y = fmaf(w0, va.y, a0.y); a0.z = fmaf(w0, va.z, a0.z); a0.w = fmaf(w0, va.w, a0.w);
+            a1.x = fmaf(w1, va.x, a1.x); a1.y = fmaf(w1, va.y, a1.y); a1.z = fmaf(w1, va.z, a1.z); a1.w = fmaf(w1, va.w, a1.w);
+            ++px;
+            sp += kStageFloats;
+            key = -1;
+            if (px < p1) {
+              m = *reinterpret_cast<const float4*>(sp + 16);
+              key = __float_as_int(m.z);
+            }
+          } while (key == cur);
+          if (px >= p1) break;  // the slice's last run stays in registers (parked below)
+          float* c0 = win + cur + coff;   // a run that ends inside the slice: shared atomics (rare)
+          if (a0.x != 0.f) atomicAdd(c0, a0.x);
+          if (a0.y != 0.f) atomicAdd(c0 + 1, a0.y);
+          if (a0.z != 0.f) atomicAdd(c0 + 2, a0.z);
+          if (a0.w != 0.f) atomicAdd(c0 + 3, a0.w);
+          if (a1.x != 0.f) atomicAdd(c0 + slab, a1.x);
+          if (a1.y != 0.f) atomicAdd(c0 + slab + 1, a1.y);
+          if (a1.z != 0.f) atomicAdd(c0 + slab + 2, a1.z);
+          if (a1.w != 0.f) atomicAdd(c0 + slab + 3, a1.w);
         }
-        const float w0 = wc * m.x, w1 = wc * m.y;
-        a0.x = fmaf(w0, va.x, a0.x); a0.y = fmaf(w0, va.y, a0.y); a0.z = fmaf(w0, va.z, a0.z); a0.w = fmaf(w0, va.w, a0.w);
-        a1.x = fmaf(w1, va.x, a1.x); a1.y = fmaf(w1, va.y, a1.y); a1.z = fmaf(w1, va.z, a1.z); a1.w = fmaf(w1, va.w, a1.w);
       }
       // every slice ends at about the same time and mostly on the same few cells: instead of 16 x 96
       // contended shared atomics the last runs are parked in per-half-warp slots ...

@@ -87,9 +87,12 @@ BDS_D TileGeom tile_geom(const CompParams& p) {
 // full-resolution-guidance chain on one pixel; fills A (all levels) and the level inputs xs
 BDS_D void fused_chain_fwd(const FusedBil& b, int cam, int H, int W, int i, int j, float& r, float& g, float& bl,
                            float lum) {
+  // the lattice coordinate of (pixel, level) is unit_coord(lin01(pixel), grid size): the IEEE division inside
+  // lin01 is paid once per axis instead of once per level
+  const float x01 = lin01(j, W), y01 = lin01(i, H);
   for (int l = 0; l < b.n_levels; ++l) {
     const float* grid = b.grid_cl[l] + (size_t)cam * b.L[l] * b.GY[l] * b.GX[l] * 12;
-    Tri t = tri_setup(lattice_coord(j, W, b.GX[l]), lattice_coord(i, H, b.GY[l]), luma_coord(lum, b.L[l]), b.L[l],
+    Tri t = tri_setup(unit_coord(x01, b.GX[l]), unit_coord(y01, b.GY[l]), luma_coord(lum, b.L[l]), b.L[l],
                       b.GY[l], b.GX[l]);
     float A[12];
     tri_fetch<false>(grid, t, A, nullptr);
@@ -409,30 +412,33 @@ __global__ void __launch_bounds__(256, 4) composite_bwd_kernel(CompParams p) {
     const float x0r = fmaf(sk[0], Tfin, rg), x0g = fmaf(sk[1], Tfin, gg), x0b = fmaf(sk[2], Tfin, bg);
     const float lum = luma_of(x0r, x0g, x0b);
     const int pxc = min(g.px, p.W - 1), pyc = min(g.py, p.H - 1);
+    const float x01 = lin01(pxc, p.W), y01 = lin01(pyc, p.H);   // one IEEE division per axis, not per level
     float xs[BDS_MAX_LEVELS][3];
     {
       float r = x0r, gq = x0g, b = x0b;
 #pragma unroll
       for (int l = 0; l < BDS_MAX_LEVELS; ++l) {
         if (l < p.bil.n_levels) {
-          const float* grid = p.bil.grid_cl[l] + (size_t)g.cam * p.bil.L[l] * p.bil.GY[l] * p.bil.GX[l] * 12;
-          Tri t = tri_setup(lattice_coord(pxc, p.W, p.bil.GX[l]), lattice_coord(pyc, p.H, p.bil.GY[l]),
-                            luma_coord(lum, p.bil.L[l]), p.bil.L[l], p.bil.GY[l], p.bil.GX[l]);
           xs[l][0] = r; xs[l][1] = gq; xs[l][2] = b;
-          float Al[12];
-          tri_fetch<false>(grid, t, Al, nullptr);
-          affine_apply(Al, r, gq, b);
+          if (l + 1 < p.bil.n_levels) {   // the last level's output is not an input of anything
+            const float* grid = p.bil.grid_cl[l] + (size_t)g.cam * p.bil.L[l] * p.bil.GY[l] * p.bil.GX[l] * 12;
+            Tri t = tri_setup(unit_coord(x01, p.bil.GX[l]), unit_coord(y01, p.bil.GY[l]),
+                              luma_coord(lum, p.bil.L[l]), p.bil.L[l], p.bil.GY[l], p.bil.GX[l]);
+            float Al[12];
+            tri_fetch<false>(grid, t, Al, nullptr);
+            affine_apply(Al, r, gq, b);
+          }
         }
       }
     }
     float v_lum = 0.f;
-    const int tile_x0 = (blockIdx.x % p.tile_w) * kTile;
-    const int tile_y0 = ((p.row_begin + blockIdx.x / p.tile_w) % p.tile_h) * kTile;
+    const float tile_x01 = lin01((blockIdx.x % p.tile_w) * kTile, p.W);
+    const float tile_y01 = lin01(((p.row_begin + blockIdx.x / p.tile_w) % p.tile_h) * kTile, p.H);
 #pragma unroll
     for (int l = BDS_MAX_LEVELS - 1; l >= 0; --l) {
       if (l < p.bil.n_levels) {
         const size_t goff = (size_t)g.cam * p.bil.L[l] * p.bil.GY[l] * p.bil.GX[l] * 12;
-        Tri t = tri_setup(lattice_coord(pxc, p.W, p.bil.GX[l]), lattice_coord(pyc, p.H, p.bil.GY[l]),
+        Tri t = tri_setup(unit_coord(x01, p.bil.GX[l]), unit_coord(y01, p.bil.GY[l]),
                           luma_coord(lum, p.bil.L[l]), p.bil.L[l], p.bil.GY[l], p.bil.GX[l]);
         float Al[12], dAdz[12], vAff[12];
         tri_fetch<true>(p.bil.grid_cl[l] + goff, t, Al, dAdz);
@@ -447,7 +453,7 @@ __global__ void __launch_bounds__(256, 4) composite_bwd_kernel(CompParams p) {
           for (int k = 0; k < 12; ++k) sdot = fmaf(vAff[k], dAdz[k], sdot);
           v_lum += sdot * (float)(p.bil.L[l] - 1);
         }
-        level_grad_accumulate(reinterpret_cast<float*>(dyn_smem), t, vAff, g.inside, tile_x0, tile_y0, p.W, p.H,
+        level_grad_accumulate(reinterpret_cast<float*>(dyn_smem), t, vAff, g.inside, tile_x01, tile_y01,
                               p.bil.L[l], p.bil.GY[l], p.bil.GX[l], p.bil.v_grid_cl[l] + goff);
       }
     }
@@ -520,6 +526,7 @@ __global__ void __launch_bounds__(256, 4) composite_bwd_kernel(CompParams p) {
   float bufdot = -Tfin * (vA - bg_dot);
   if (!g.inside) last = -1;   // pixels outside the image never match a record
   int nb = 0;                 // records pending in this warp's panel (warp-uniform)
+  float2* pw = bs->panel + lane;   // this lane's cell of the next panel row
 
   for (int q = 0; q < nchunks; ++q) {
     const int st = q % kBStages;
@@ -577,7 +584,8 @@ __global__ void __launch_bounds__(256, 4) composite_bwd_kernel(CompParams p) {
             bufdot = fmaf(fac, cdot, bufdot);
             w = araw <= kAlphaMax ? araw * v_alpha : 0.f;  // the clamp at 0.999 blocks the gradient
           }
-          bs->panel[nb * kPanelStride + lane] = make_float2(w, fac);
+          *pw = make_float2(w, fac);
+          pw += kPanelStride;
           if (lane == 0) {
             bs->meta0[nb] = r0;
             bs->meta1[nb] = make_float2(r1.x, r2.z);
@@ -585,6 +593,7 @@ __global__ void __launch_bounds__(256, 4) composite_bwd_kernel(CompParams p) {
           if (++nb == kBatch) {
             flush_batch(bs, kBatch, rxmin, rymin, p.v_splats);
             nb = 0;
+            pw = bs->panel + lane;
           }
         }
       }
