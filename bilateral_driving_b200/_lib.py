@@ -87,6 +87,7 @@ ABI_SYMBOLS = (
     "bds_project_fwd", "bds_project_bwd",
     "bds_bin_count_workspace_bytes", "bds_bin_count", "bds_bin_sort_workspace_bytes", "bds_bin_sort",
     "bds_composite_workspace_bytes", "bds_composite_fwd", "bds_composite_bwd",
+    "bds_slot_keep", "bds_composite_fwd_masked",
     "bds_loss_fwd_bwd",
 )
 

@@ -50,6 +50,7 @@ struct CompParams {
   const float* sky;          // band pixels x 3 or null
   float *out_rgb, *out_rgbg, *out_depth, *out_alpha;
   int32_t* last_ids;
+  const uint8_t* slot_keep;  // optional per-splat keep flags (masked re-render over the same sorted lists)
   FusedBil bil;
   // backward only
   const float *v_rgb, *v_rgbg, *v_depth, *v_alpha;
@@ -159,6 +160,8 @@ __global__ void __launch_bounds__(256, 5) composite_fwd_kernel(CompParams p) {
           float4 r0 = sr[j * 3], r1 = sr[j * 3 + 1], r2 = sr[j * 3 + 2];
           float s = min_sigma_rect(r0.x, r0.y, r0.z, r0.w, r1.x, rxmin, rxmax, rymin, rymax);
           hit = !(s > r2.w + (kLog2_255 + kCullMargin));
+          // a masked-out splat is a splat of opacity 0: it fails the alpha >= 1/255 test on every pixel
+          if (p.slot_keep && hit) hit = p.slot_keep[__float_as_int(r2.z)] != 0;
         }
         unsigned m = __ballot_sync(kFull, hit);
 #ifdef BDS_STATS
@@ -284,7 +287,12 @@ __global__ void __launch_bounds__(256, 5) composite_fwd_kernel(CompParams p) {
 // with m_ab = sum_p w_p dx_p^a dy_p^b, (dx, dy) = mean2d - pixel centre, g = (2a' dx + b' dy, b' dx + 2c' dy).
 // project_bwd_kernel turns the moments into v_mean2d / v_conic / v_opacity (all linear in them).
 constexpr int kBStages = 2;            // backward: TMA stages of kChunk records
-constexpr int kBatch = 16;             // records per deferred-reduction batch
+#ifndef BDS_BATCH
+#define BDS_BATCH 16
+#endif
+constexpr int kBatch = BDS_BATCH;      // records per deferred-reduction batch (8 or 16)
+constexpr int kParts = 32 / kBatch;    // lanes per record in the transposed phase
+constexpr int kPartPix = 32 / kParts;  // pixels per lane: 8 = one row of the 8x4 rectangle, 16 = two rows
 constexpr int kPanelStride = 33;       // float2 per record row: 32 pixels + 1 pad (conflict-free transposed reads)
 
 struct BatchSmem {                     // per warp
@@ -307,9 +315,9 @@ BDS_D float rcp_approx(float x) {
 BDS_D void flush_batch(const BatchSmem* bs, int nb, float rx0, float ry0, float* __restrict__ v_splats) {
   __syncwarp();
   const int lane = threadIdx.x & 31;
-  const int rec = lane & (kBatch - 1), half = lane >> 4;
-  const float2* row = bs->panel + rec * kPanelStride + half * 16;
-  const float4* vcp = bs->vc + half * 16;
+  const int rec = lane & (kBatch - 1), part = lane / kBatch;
+  const float2* row = bs->panel + rec * kPanelStride + part * kPartPix;
+  const float4* vcp = bs->vc + part * kPartPix;
   const float4 q0 = bs->meta0[rec];
   const float2 q1 = bs->meta1[rec];
   const float X = q0.x - rx0, Y = q0.y - ry0;          // mean relative to pixel (u, v) = (0, 0)
@@ -317,8 +325,8 @@ BDS_D void flush_batch(const BatchSmem* bs, int nb, float rx0, float ry0, float*
   float m0 = 0.f, mu = 0.f, mv = 0.f, muu = 0.f, muv = 0.f, mvv = 0.f;
   float c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f, ax = 0.f, ay = 0.f;
 #pragma unroll
-  for (int r = 0; r < 2; ++r) {
-    const float v = (float)(half * 2 + r);
+  for (int r = 0; r < kPartPix / 8; ++r) {
+    const float v = (float)(part * (kPartPix / 8) + r);
     const float dy = Y - v;
     const float gxr = fmaf(A2, X, B * dy), gyr = fmaf(B, X, C2 * dy);   // g at u = 0
     float s0 = 0.f, s1 = 0.f, s2 = 0.f;
@@ -337,18 +345,25 @@ BDS_D void flush_batch(const BatchSmem* bs, int nb, float rx0, float ry0, float*
     m0 += s0; mu += s1; muu += s2;
     mv = fmaf(v, s0, mv); muv = fmaf(v, s1, muv); mvv = fmaf(v * v, s0, mvv);
   }
-#define BDS_FOLD16(x) x += __shfl_xor_sync(kFull, x, 16)
-  BDS_FOLD16(m0); BDS_FOLD16(mu); BDS_FOLD16(mv); BDS_FOLD16(muu); BDS_FOLD16(muv); BDS_FOLD16(mvv);
-  BDS_FOLD16(c0); BDS_FOLD16(c1); BDS_FOLD16(c2); BDS_FOLD16(c3); BDS_FOLD16(ax); BDS_FOLD16(ay);
-#undef BDS_FOLD16
-  if (rec < nb) {
+#pragma unroll
+  for (int o = 16; o >= kBatch; o >>= 1) {   // fold the kParts partial sums of each record
+    m0 += __shfl_xor_sync(kFull, m0, o); mu += __shfl_xor_sync(kFull, mu, o); mv += __shfl_xor_sync(kFull, mv, o);
+    muu += __shfl_xor_sync(kFull, muu, o); muv += __shfl_xor_sync(kFull, muv, o); mvv += __shfl_xor_sync(kFull, mvv, o);
+    c0 += __shfl_xor_sync(kFull, c0, o); c1 += __shfl_xor_sync(kFull, c1, o); c2 += __shfl_xor_sync(kFull, c2, o);
+    c3 += __shfl_xor_sync(kFull, c3, o); ax += __shfl_xor_sync(kFull, ax, o); ay += __shfl_xor_sync(kFull, ay, o);
+  }
+  if (rec < nb && part < 3) {
     // pixel-local -> mean-centred moments: dx = X - u, dy = Y - v
     const float mx = fmaf(X, m0, -mu), my = fmaf(Y, m0, -mv);
     const float mxx = fmaf(X, mx - mu, muu);
     const float mxy = fmaf(X, my, fmaf(-Y, mu, muv));
     const float myy = fmaf(Y, my - mv, mvv);
     float* dst = v_splats + (size_t)__float_as_int(q1.y) * 12;
-    if (half == 0) {
+    if (kParts >= 3) {          // one 128-bit reduction per lane
+      if (part == 0) red_add_v4(dst, mx, my, mxx, mxy);
+      else if (part == 1) red_add_v4(dst + 4, myy, m0, c0, c1);
+      else red_add_v4(dst + 8, c2, c3, ax, ay);
+    } else if (part == 0) {
       red_add_v4(dst, mx, my, mxx, mxy);
       red_add_v4(dst + 4, myy, m0, c0, c1);
     } else {
@@ -453,8 +468,12 @@ __global__ void __launch_bounds__(256, 4) composite_bwd_kernel(CompParams p) {
           for (int k = 0; k < 12; ++k) sdot = fmaf(vAff[k], dAdz[k], sdot);
           v_lum += sdot * (float)(p.bil.L[l] - 1);
         }
+#ifndef BDS_DIAG_NO_ACCUM   // timing experiments only (scripts/gpu_variants.sh): results are wrong without it
         level_grad_accumulate(reinterpret_cast<float*>(dyn_smem), t, vAff, g.inside, tile_x01, tile_y01,
                               p.bil.L[l], p.bil.GY[l], p.bil.GX[l], p.bil.v_grid_cl[l] + goff);
+#else
+        if (vAff[0] == 123.456f) p.bil.v_grid_cl[l][goff] = vAff[5] + vAff[11];
+#endif
       }
     }
     gr += v_lum * kLumaR; gg2 += v_lum * kLumaG; gb += v_lum * kLumaB;
@@ -710,11 +729,57 @@ extern "C" size_t bds_composite_workspace_bytes(const bds_render_desc* d, const 
   return carve_comp(d, e).total + 256;
 }
 
+static int composite_fwd_impl(const bds_render_desc* d, const bds_epilogue_desc* e, const float* sorted_splats,
+                              const int32_t* tile_offsets, const float* backgrounds, const float* sky,
+                              const float* const* host_grids, float* out_rgb, float* out_rgb_gauss,
+                              float* out_depth, float* out_alpha, int32_t* last_ids, void* workspace,
+                              const uint8_t* slot_keep, bds_stream_t stream_);
+
 extern "C" int bds_composite_fwd(const bds_render_desc* d, const bds_epilogue_desc* e, const float* sorted_splats,
                                  const int32_t* tile_offsets, const float* backgrounds, const float* sky,
                                  const float* const* host_grids, float* out_rgb, float* out_rgb_gauss,
                                  float* out_depth, float* out_alpha, int32_t* last_ids, void* workspace,
                                  bds_stream_t stream_) {
+  return composite_fwd_impl(d, e, sorted_splats, tile_offsets, backgrounds, sky, host_grids, out_rgb, out_rgb_gauss,
+                            out_depth, out_alpha, last_ids, workspace, nullptr, stream_);
+}
+
+extern "C" int bds_composite_fwd_masked(const bds_render_desc* d, const bds_epilogue_desc* e,
+                                        const float* sorted_splats, const int32_t* tile_offsets,
+                                        const uint8_t* slot_keep, const float* backgrounds, const float* sky,
+                                        const float* const* host_grids, float* out_rgb, float* out_rgb_gauss,
+                                        float* out_depth, float* out_alpha, int32_t* last_ids, void* workspace,
+                                        bds_stream_t stream_) {
+  BDS_REQUIRE(slot_keep, "composite_fwd_masked: slot_keep is null");
+  return composite_fwd_impl(d, e, sorted_splats, tile_offsets, backgrounds, sky, host_grids, out_rgb, out_rgb_gauss,
+                            out_depth, out_alpha, last_ids, workspace, slot_keep, stream_);
+}
+
+// slot_keep[slot] = gaussian_keep[Gaussian of the splat]
+__global__ void slot_keep_kernel(const float* __restrict__ splats, const int32_t* __restrict__ counters, int n_gauss,
+                                 const uint8_t* __restrict__ gaussian_keep, uint8_t* __restrict__ slot_keep) {
+  const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+  if (slot >= counters[0]) return;
+  const int64_t idx = (int64_t)__float_as_int(splats[(size_t)slot * 12 + 10]);   // camera * N + Gaussian
+  slot_keep[slot] = gaussian_keep[idx % n_gauss];
+}
+
+extern "C" int bds_slot_keep(const bds_render_desc* d, const float* splats, const int32_t* counters, int32_t n_slots,
+                             const uint8_t* gaussian_keep, uint8_t* slot_keep, bds_stream_t stream_) {
+  if (int rc = check_render_desc(d)) return rc;
+  BDS_REQUIRE(splats && counters && gaussian_keep && slot_keep && n_slots >= 0, "slot_keep: bad arguments");
+  if (n_slots == 0) return 0;
+  slot_keep_kernel<<<ceil_div(n_slots, 256), 256, 0, static_cast<cudaStream_t>(stream_)>>>(splats, counters, d->n_gauss,
+                                                                                        gaussian_keep, slot_keep);
+  BDS_CHECK_LAUNCH();
+  return 0;
+}
+
+static int composite_fwd_impl(const bds_render_desc* d, const bds_epilogue_desc* e, const float* sorted_splats,
+                              const int32_t* tile_offsets, const float* backgrounds, const float* sky,
+                              const float* const* host_grids, float* out_rgb, float* out_rgb_gauss,
+                              float* out_depth, float* out_alpha, int32_t* last_ids, void* workspace,
+                              const uint8_t* slot_keep, bds_stream_t stream_) {
   if (int rc = check_render_desc(d)) return rc;
   CompParams p{};
   if (int rc = fill_common(p, d, e)) return rc;
@@ -727,6 +792,7 @@ extern "C" int bds_composite_fwd(const bds_render_desc* d, const bds_epilogue_de
   p.tile_offsets = tile_offsets;
   p.backgrounds = backgrounds; p.sky = sky;
   p.out_rgb = out_rgb; p.out_rgbg = out_rgb_gauss; p.out_depth = out_depth; p.out_alpha = out_alpha; p.last_ids = last_ids;
+  p.slot_keep = slot_keep;
   if (e->mode == 2) {
     BDS_REQUIRE(host_grids && workspace, "composite_fwd: mode 2 needs grids and workspace");
     CompWorkspace w = carve_comp(d, e);

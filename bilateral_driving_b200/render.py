@@ -198,7 +198,10 @@ class _RenderFn(torch.autograd.Function):
                               splats, counters, sorted_splats, tile_offsets, out_rgbg, out_depth, out_alpha, last_ids,
                               out_rgb if (cfg.mode == 0 and cfg.channels == 4 and cfg.expected_depth) else None, *grids)
         holder.update(n_isect=n_isect, n_visible=n_slots, depths=depths, conics=conics, tiles_touched=tiles_touched,
-                      tile_offsets=tile_offsets, compensations=comps, sorted_splats=sorted_splats, last_ids=last_ids)
+                      tile_offsets=tile_offsets, compensations=comps, sorted_splats=sorted_splats, last_ids=last_ids,
+                      # what rasterize_masked() needs to composite again over the same sorted lists
+                      cache=dict(cfg=cfg, d=d, e=e, splats=splats, counters=counters, n_slots=n_slots, P=P, N=N, Cn=Cn,
+                                 sorted_splats=sorted_splats, tile_offsets=tile_offsets, backgrounds=backgrounds))
         m2d = means2d if means2d is not None else torch.empty(0, **f32)
         ctx.mark_non_differentiable(radii)
         return (out_rgb, out_rgbg if out_rgbg is not None else torch.empty(0, **f32),
@@ -360,8 +363,46 @@ def rasterization(means, quats, scales, opacities, colors, viewmats, Ks, width, 
         "tile_width": tw, "tile_height": th, "tiles_per_gauss": holder["tiles_touched"],
         "isect_offsets": holder["tile_offsets"][:-1].view(Cn, th, tw), "width": W, "height": H, "tile_size": 16,
         "n_cameras": Cn, "n_isect": holder["n_isect"], "n_visible": holder["n_visible"],
+        "_bds_cache": holder["cache"],   # private: sorted lists for rasterize_masked()
     }
     return renders, alphas, info
+
+
+@torch.no_grad()
+def rasterize_masked(info, gaussian_mask):
+    """Re-render the scene of a previous ``rasterization`` call with a per-Gaussian keep mask, reusing its
+    projection, binning and depth-sorted tile lists (one composite launch instead of the whole pipeline).
+
+    Replaces the reference's ``render_fn(opacity_mask)`` (``models/trainers/base.py:392-419``), which calls
+    ``rasterization`` again with ``opacities * mask`` for every class at eval time
+    (``models/trainers/scene_graph.py:296-313``).  ``gaussian_mask`` is a bool/0-1 tensor ``[N]``; a masked-out
+    Gaussian is exactly a Gaussian of opacity 0, so the images equal the re-rasterization bit for bit.
+    No autograd (the reference calls it under ``torch.no_grad()``).  Returns ``(renders [C,H,W,D], alphas
+    [C,H,W,1])`` like ``rasterization``.
+    """
+    c = info["_bds_cache"] if isinstance(info, dict) and "_bds_cache" in info else info
+    cfg, d, e = c["cfg"], c["d"], c["e"]
+    if cfg.mode != 0:
+        raise NotImplementedError("rasterize_masked re-renders gsplat-shaped outputs (mode 0)")
+    if not gaussian_mask.is_cuda:
+        raise BdsError("bds operators run on CUDA tensors only (no CPU fallback exists)")
+    N, Cn, P = c["N"], c["Cn"], c["P"]
+    if gaussian_mask.numel() != N:
+        raise ValueError(f"gaussian_mask has {gaussian_mask.numel()} entries for {N} Gaussians")
+    dev = gaussian_mask.device
+    keep = (gaussian_mask.reshape(-1) != 0).to(torch.uint8).contiguous()
+    slot_keep = torch.empty(max(c["n_slots"], 1), device=dev, dtype=torch.uint8)
+    st = stream_ptr()
+    check(lib.bds_slot_keep(C.byref(d), ptr(c["splats"]), ptr(c["counters"]), C.c_int32(c["n_slots"]), ptr(keep),
+                            ptr(slot_keep), st), "bds_slot_keep")
+    f32 = dict(device=dev, dtype=torch.float32)
+    out_rgb = torch.empty(P, cfg.channels, **f32)
+    out_alpha = torch.empty(P, **f32)
+    last_ids = torch.empty(P, device=dev, dtype=torch.int32)
+    check(lib.bds_composite_fwd_masked(C.byref(d), C.byref(e), ptr(c["sorted_splats"]), ptr(c["tile_offsets"]),
+                                       ptr(slot_keep), ptr(c["backgrounds"]), NULL, NULL, ptr(out_rgb), NULL, NULL,
+                                       ptr(out_alpha), ptr(last_ids), NULL, st), "bds_composite_fwd_masked")
+    return out_rgb.view(Cn, cfg.height, cfg.width, cfg.channels), out_alpha.view(Cn, cfg.height, cfg.width, 1)
 
 
 class _SHFn(torch.autograd.Function):

@@ -7,6 +7,8 @@
 * ``affine_transformation`` (``scene_graph.py:86-120``): for ``MultiScaleBilateralAffineTransform`` /
   ``BilateralAffineTransform`` it calls the module's fused ``transform`` (slice + sequential apply in one
   op, no 100 MB-per-level affine fields) instead of ``forward`` + the Python apply loop;
+* ``render_gaussians`` (``base.py:385-432``) hands back a ``render_fn`` whose masked re-renders
+  (``scene_graph.py:296-313``) reuse the sorted tile lists of the first render (``render.rasterize_masked``);
 * ``forward`` additionally emits ``outputs["original_rgb"]``, which ``compute_losses`` reads at
   ``base.py:628-631`` but ``MultiTrainer.forward`` never sets (a bug of the published ms-bilateral configs:
   the first training step raises ``KeyError``).
@@ -54,6 +56,27 @@ def _build():
                     return affine.transform(rgb_blended, image_infos, guidance_factor=self.guidance_factor)
                 return affine.transform(rgb_blended, image_infos)
             return super().affine_transformation(rgb_blended, image_infos)
+
+        def render_gaussians(self, gs, cam, **kwargs):
+            """``base.py:385-432``: same results, but the ``render_fn(opacity_mask)`` closure handed back to
+            ``MultiTrainer.forward`` (per-class / dynamic-only renders, ``scene_graph.py:296-313``) composites
+            again over the sorted tile lists of the first render instead of re-running the whole rasterization."""
+            results, render_fn = super().render_gaussians(gs, cam, **kwargs)
+            info = self.info
+
+            def cached_render_fn(opaticy_mask=None, return_info=False):
+                reusable = (opaticy_mask is not None and not return_info and not torch.is_grad_enabled()
+                            and isinstance(info, dict) and "_bds_cache" in info
+                            and opaticy_mask.dtype in (torch.bool, torch.uint8))
+                if not reusable:
+                    return render_fn(opaticy_mask, return_info)
+                from .render import rasterize_masked
+                renders, alphas = rasterize_masked(info, opaticy_mask)
+                renders, alphas = renders[0], alphas[0].squeeze(-1)
+                rendered_rgb, rendered_depth = torch.split(renders, [3, 1], dim=-1)
+                return torch.clamp(rendered_rgb, max=1.0), rendered_depth, alphas[..., None]
+
+            return results, cached_render_fn
 
         def forward(self, image_infos, camera_infos, novel_view: bool = False):
             self._original_rgb = None

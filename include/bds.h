@@ -176,6 +176,21 @@ int bds_composite_fwd(const bds_render_desc* d, const bds_epilogue_desc* e, cons
                       bds_stream_t stream);
 size_t bds_composite_workspace_bytes(const bds_render_desc* d, const bds_epilogue_desc* e);
 
+/* Masked re-render over the SAME sorted lists (no projection / binning / sort): replaces the reference's
+ * render_fn(opacity_mask) = a second full gsplat rasterization with opacities * mask
+ * (models/trainers/base.py:392-419, called per class at models/trainers/scene_graph.py:296-313).
+ * A splat whose keep flag is 0 behaves exactly like a splat of opacity 0 (it fails alpha >= 1/255 on
+ * every pixel), so the images equal the reference's re-rasterization bit for bit.
+ * bds_slot_keep: slot_keep[slot] = gaussian_keep[Gaussian of that splat]  (gaussian_keep [N] bytes,
+ * slot_keep [n_slots] bytes; splats / counters as written by bds_project_fwd). */
+int bds_slot_keep(const bds_render_desc* d, const float* splats, const int32_t* counters, int32_t n_slots,
+                  const uint8_t* gaussian_keep, uint8_t* slot_keep, bds_stream_t stream);
+int bds_composite_fwd_masked(const bds_render_desc* d, const bds_epilogue_desc* e, const float* sorted_splats,
+                             const int32_t* tile_offsets, const uint8_t* slot_keep, const float* backgrounds,
+                             const float* sky, const float* const* host_grids, float* out_rgb,
+                             float* out_rgb_gauss, float* out_depth, float* out_alpha, int32_t* last_ids,
+                             void* workspace, bds_stream_t stream);
+
 /* Backward of the above.  Cotangents: v_rgb [P,D or 3], v_rgb_gauss [P,3] (optional), v_depth [P]
  * (optional), v_alpha [P] (optional).  Outputs: v_splats [n_slots,12] ACCUMULATED (caller zeroes):
  * {m_x, m_y, m_xx, m_xy, m_yy, m_0, v_r, v_g, v_b, v_depth, sum|w g_x|, sum|w g_y|} - the pixel moments of

@@ -288,3 +288,35 @@ def test_full_size_properties():
     same = tile_of[1:] == tile_of[:-1]
     assert bool((depth[1:][same] >= depth[:-1][same]).all())
     assert holder["n_isect"] > 100_000
+
+
+@pytest.mark.gpu
+def test_masked_rerender_reuses_sorted_lists():
+    """render_fn(opacity_mask) (base.py:392-419, scene_graph.py:296-313): compositing again over the cached sorted
+    lists with a per-Gaussian keep mask equals a full re-rasterization with opacities * mask, bit for bit."""
+    from bilateral_driving_b200 import _lib
+    from bilateral_driving_b200.render import rasterization, rasterize_masked
+
+    p, vm, Ks, W, H = _small_scene()
+    leaves = {k: v.cuda() for k, v in p.items()}
+    vm, Ks = vm.cuda(), Ks.cuda()
+    cols = _activated_colors(leaves, vm)
+    quats = leaves["_quats"] / leaves["_quats"].norm(dim=-1, keepdim=True)
+    scales, opac = torch.exp(leaves["_scales"]), torch.sigmoid(leaves["_opacities"])
+    N = opac.shape[0]
+    g = torch.Generator().manual_seed(5)
+    kw = dict(viewmats=vm[:1], Ks=Ks[:1], width=W, height=H, packed=False, absgrad=True, near_plane=0.1,
+              render_mode="RGB+ED")
+    with torch.no_grad():
+        _, _, info = rasterization(leaves["_means"], quats, scales, opac, cols[0], **kw)
+        for frac in (0.5, 0.1, 1.0, 0.0):
+            mask = (torch.rand(N, generator=g) < frac).cuda()
+            launches = _lib.lib.bds_launch_count()
+            r1, a1 = rasterize_masked(info, mask)
+            assert _lib.lib.bds_launch_count() - launches == 2   # keep-flag kernel + ONE composite launch
+            r2, a2, _ = rasterization(leaves["_means"], quats, scales, opac * mask, cols[0], **kw)
+            assert r1.shape == r2.shape and a1.shape == a2.shape
+            assert torch.equal(a1, a2)
+            assert torch.equal(r1, r2)
+    with pytest.raises(ValueError):
+        rasterize_masked(info, torch.ones(N + 1, dtype=torch.bool, device="cuda"))
