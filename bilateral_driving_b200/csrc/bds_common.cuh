@@ -78,6 +78,39 @@ BDS_D void st_stream_f4(float4* p, float4 v) {
                "f"(v.z), "f"(v.w));
 }
 
+// Packed fp32x2 arithmetic (sm_100a FFMA2 / FADD2 / FMUL2): two IEEE fp32 operations per issue slot; a scalar
+// operand is broadcast by the instruction itself.  Same rounding as the scalar forms.
+typedef unsigned long long f32x2;
+BDS_D f32x2 pk2(float a, float b) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+BDS_D void upk2(f32x2 v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+BDS_D f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 d;
+  asm("fma.rn.ftz.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+BDS_D void fma2_acc(f32x2& c, f32x2 a, f32x2 b) {   // c += a * b, accumulator updated in place
+  asm("fma.rn.ftz.f32x2 %0, %1, %2, %0;" : "+l"(c) : "l"(a), "l"(b));
+}
+BDS_D f32x2 mul2(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("mul.rn.ftz.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+BDS_D f32x2 add2(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("add.rn.ftz.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+BDS_D f32x2 sub2(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("sub.rn.ftz.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+
 // fire-and-forget fp32 reduction into global memory (RED.ADD.F32)
 BDS_D void red_add(float* p, float v) { atomicAdd(p, v); }
 #endif  // __CUDACC__

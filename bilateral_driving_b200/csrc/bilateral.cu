@@ -4,7 +4,7 @@
 // kernel: default low-resolution guidance ([4,4,2]) and the guidance_factor=None branch.
 //
 // Kernels (all HBM/L2-bound gather / pointwise work; no tensor cores):
-//   repack_grid_kernel       [12,L,GY,GX] -> [L,GY,GX,12]                       (tiny)
+//   repack_grid_kernel       [12,L,GY,GX] -> value repack [GY,GX,3,L,4]          (tiny)
 //   lowres_slice_fwd_kernel  per low-res pixel: bilinear-down guidance -> luma -> trilerp -> A_low
 //   apply_fwd_kernel         per pixel: A_l = up(A_low) or direct trilerp; x <- A_l x
 //   apply_bwd_tiled_kernel   per 16x16 tile: recompute chain; g_l; vA_l -> v_A_low by a shared-memory
@@ -20,8 +20,7 @@ namespace bds {
 __global__ void repack_grid_kernel(const float* __restrict__ cf, float* __restrict__ cl, int L, int GY, int GX) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;  // over nodes*12, channel fastest
   if (i >= L * GY * GX * 12) return;
-  int node = i / 12, ch = i - node * 12;
-  cl[i] = cf[bil_param_index(node, ch, L, GY, GX)];
+  cl[i] = cf[bil_value_param_index(i, L, GY, GX)];   // value repack [GY][GX][3][L][4]
 }
 
 __global__ void unpack_add_grid_kernel(const float* __restrict__ cl, float* __restrict__ cf, int L, int GY, int GX) {

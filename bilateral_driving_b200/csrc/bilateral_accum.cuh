@@ -109,15 +109,15 @@ BDS_D void level_grad_accumulate(float* smem, const Tri& t, const float vAff[12]
         int px = p0;
         for (;;) {
           cur = __float_as_int(m.z);
-          a0 = make_float4(0.f, 0.f, 0.f, 0.f);
-          a1 = a0;
+          f32x2 a0l = pk2(0.f, 0.f), a0h = a0l, a1l = a0l, a1h = a0l;   // packed fp32x2 accumulators (FFMA2)
           int key;
           do {
             const float4 va = *reinterpret_cast<const float4*>(sp + quad * 4);
             const float wc = sp[12 + corner];
             const float w0 = wc * m.x, w1 = wc * m.y;
-            a0.x = fmaf(w0, va.x, a0.x); a0.y = fmaf(w0, va.y, a0.y); a0.z = fmaf(w0, va.z, a0.z); a0.w = fmaf(w0, va.w, a0.w);
-            a1.x = fmaf(w1, va.x, a1.x); a1.y = fmaf(w1, va.y, a1.y); a1.z = fmaf(w1, va.z, a1.z); a1.w = fmaf(w1, va.w, a1.w);
+            const f32x2 ww0 = pk2(w0, w0), ww1 = pk2(w1, w1), vl = pk2(va.x, va.y), vh = pk2(va.z, va.w);
+            fma2_acc(a0l, ww0, vl); fma2_acc(a0h, ww0, vh);
+            fma2_acc(a1l, ww1, vl); fma2_acc(a1h, ww1, vh);
             ++px;
             sp += kStageFloats;
             key = -1;
@@ -126,6 +126,8 @@ BDS_D void level_grad_accumulate(float* smem, const Tri& t, const float vAff[12]
               key = __float_as_int(m.z);
             }
           } while (key == cur);
+          upk2(a0l, a0.x, a0.y); upk2(a0h, a0.z, a0.w);
+          upk2(a1l, a1.x, a1.y); upk2(a1h, a1.z, a1.w);
           if (px >= p1) break;  // the slice's last run stays in registers (parked below)
           float* c0 = win + cur + coff;   // a run that ends inside the slice: shared atomics (rare)
           if (a0.x != 0.f) atomicAdd(c0, a0.x);

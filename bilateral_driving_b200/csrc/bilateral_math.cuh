@@ -8,10 +8,14 @@
 //   models/modules.py:494-504, 409-420  bilinear resize, align_corners=False (low-res guidance)
 //   models/trainers/scene_graph.py:112-117   x <- A[:, :3] x + A[:, 3], level after level
 //
-// Grids are read in a channel-LAST, guidance-contiguous repack [GY][GX][L][12] (three float4 per
-// lattice node; the L slabs of one xy node are 48*L contiguous bytes, so lanes of a warp that differ
-// only in their guidance cell touch a handful of cache lines) that the host entry points build from
-// the reference's channel-first [12][L][GY][GX] parameter slot.
+// Grid VALUES are read from a guidance-contiguous, quad-major repack [GY][GX][3][L][4] that the host
+// entry points build from the reference's channel-first [12][L][GY][GX] parameter slot: the four floats
+// of one affine row (one 128-bit load) of the L slabs of an xy node are 16*L contiguous bytes.  The lanes
+// of a warp share the xy cell and differ in their guidance slab, so ONE load instruction (fixed corner,
+// fixed row) touches at most 16*L bytes = 2 cache lines at L = 16 - the slice is L1-wavefront bound, and
+// the node-major [GY][GX][L][12] order it replaced spread the same instruction over 48*L bytes (6 lines).
+// Grid GRADIENTS keep the node-major [GY][GX][L][12] order (bil_node), which is what the window flush of
+// bilateral_accum.cuh writes.
 #pragma once
 #include "bds_common.cuh"
 
@@ -76,6 +80,16 @@ BDS_HD size_t bil_param_index(int node, int ch, int L, int GY, int GX) {
   int x = xy % GX, y = xy / GX;
   return (((size_t)ch * L + z) * GY + y) * GX + x;
 }
+// value repack [GY][GX][3][L][4]: float offset of (node = xy * L + z, affine row k), and the inverse map
+// (element i of the value repack -> element of the parameter layout) used by the repack kernels
+BDS_HD int bil_value_offset(int node, int z, int k, int L) { return 12 * node - 8 * z + 4 * k * L; }
+BDS_HD size_t bil_value_param_index(int i, int L, int GY, int GX) {
+  int xy = i / (12 * L), rem = i - xy * 12 * L;
+  int k = rem / (4 * L), rem2 = rem - k * 4 * L;
+  int z = rem2 >> 2, ch = 4 * k + (rem2 & 3);
+  int x = xy % GX, y = xy / GX;
+  return (((size_t)ch * L + z) * GY + y) * GX + x;
+}
 
 // Trilinear set-up with border clamping.  Offsets are in lattice NODES of the [GY][GX][L] repack.
 struct Tri {
@@ -84,6 +98,7 @@ struct Tri {
   int x0, y0, z0;          // lower lattice node of the cell
   float wx1, wy1, wz1;     // upper weights; lower = 1 - upper
   bool z_inside;           // 0 < fz < L-1 (strict): guidance gradient flows
+  int L;                   // slabs of the level (value-repack addressing)
 };
 BDS_HD Tri tri_setup(float fx, float fy, float fz, int L, int GY, int GX) {
   Tri t;
@@ -104,6 +119,7 @@ BDS_HD Tri tri_setup(float fx, float fy, float fz, int L, int GY, int GX) {
   t.n10 = bil_node(x0, y1, z0, L, GX);
   t.n11 = bil_node(x1, y1, z0, L, GX);
   t.dz = z1 - z0;
+  t.L = L;
   return t;
 }
 
@@ -116,40 +132,60 @@ BDS_D void load12(const float* p, float v[12]) {
   v[8] = c.x; v[9] = c.y; v[10] = c.z; v[11] = c.w;
 }
 
-// A = trilerp(grid)(t); optionally dA/dfz (slab difference, xy-interpolated)
+// the three affine rows of one node of the value repack (rows are 4 L floats apart) as six fp32 pairs
+BDS_D void load12v(const float* p, int L, f32x2 v[6]) {
+  const float4* q = reinterpret_cast<const float4*>(p);
+  float4 a = __ldg(q), b = __ldg(q + L), c = __ldg(q + 2 * L);
+  v[0] = pk2(a.x, a.y); v[1] = pk2(a.z, a.w);
+  v[2] = pk2(b.x, b.y); v[3] = pk2(b.z, b.w);
+  v[4] = pk2(c.x, c.y); v[5] = pk2(c.z, c.w);
+}
+
+// A = trilerp(grid)(t); optionally dA/dfz (slab difference, xy-interpolated).  g = value repack.
+// 8 corners x 12 channels as packed fp32x2 FMAs (48 FFMA2 instead of 96 FFMA): the slice is issue-bound.
 template <bool WITH_DZ>
 BDS_D void tri_fetch(const float* __restrict__ g, const Tri& t, float A[12], float dAdz[12]) {
-  float w00 = (1.f - t.wx1) * (1.f - t.wy1), w01 = t.wx1 * (1.f - t.wy1);
-  float w10 = (1.f - t.wx1) * t.wy1, w11 = t.wx1 * t.wy1;
-  float c0[12], c1[12], v[12];
-  load12(g + 12 * t.n00, v);
+#ifdef BDS_DIAG_NO_FETCH   // timing experiments only: no grid loads (results are wrong)
 #pragma unroll
-  for (int k = 0; k < 12; ++k) c0[k] = w00 * v[k];
-  load12(g + 12 * t.n01, v);
+  for (int k = 0; k < 12; ++k) { A[k] = t.wx1 + (float)k; if (WITH_DZ) dAdz[k] = t.wy1 * (float)k; }
+  return;
+#endif
+  const float w00 = (1.f - t.wx1) * (1.f - t.wy1), w01 = t.wx1 * (1.f - t.wy1);
+  const float w10 = (1.f - t.wx1) * t.wy1, w11 = t.wx1 * t.wy1;
+  const f32x2 p00 = pk2(w00, w00), p01 = pk2(w01, w01), p10 = pk2(w10, w10), p11 = pk2(w11, w11);
+  f32x2 c0[6], c1[6], v[6];
+  g -= 8 * t.z0;   // value repack: row k of node n lives at 12 n - 8 z + 4 k L (bil_value_offset)
+  load12v(g + 12 * t.n00, t.L, v);
 #pragma unroll
-  for (int k = 0; k < 12; ++k) c0[k] = fmaf(w01, v[k], c0[k]);
-  load12(g + 12 * t.n10, v);
+  for (int k = 0; k < 6; ++k) c0[k] = mul2(p00, v[k]);
+  load12v(g + 12 * t.n01, t.L, v);
 #pragma unroll
-  for (int k = 0; k < 12; ++k) c0[k] = fmaf(w10, v[k], c0[k]);
-  load12(g + 12 * t.n11, v);
+  for (int k = 0; k < 6; ++k) fma2_acc(c0[k], p01, v[k]);
+  load12v(g + 12 * t.n10, t.L, v);
 #pragma unroll
-  for (int k = 0; k < 12; ++k) c0[k] = fmaf(w11, v[k], c0[k]);
-  load12(g + 12 * (t.n00 + t.dz), v);
+  for (int k = 0; k < 6; ++k) fma2_acc(c0[k], p10, v[k]);
+  load12v(g + 12 * t.n11, t.L, v);
 #pragma unroll
-  for (int k = 0; k < 12; ++k) c1[k] = w00 * v[k];
-  load12(g + 12 * (t.n01 + t.dz), v);
+  for (int k = 0; k < 6; ++k) fma2_acc(c0[k], p11, v[k]);
+  g += 4 * t.dz;   // upper slab: node + dz, z + dz  ->  12 dz - 8 dz
+  load12v(g + 12 * t.n00, t.L, v);
 #pragma unroll
-  for (int k = 0; k < 12; ++k) c1[k] = fmaf(w01, v[k], c1[k]);
-  load12(g + 12 * (t.n10 + t.dz), v);
+  for (int k = 0; k < 6; ++k) c1[k] = mul2(p00, v[k]);
+  load12v(g + 12 * t.n01, t.L, v);
 #pragma unroll
-  for (int k = 0; k < 12; ++k) c1[k] = fmaf(w10, v[k], c1[k]);
-  load12(g + 12 * (t.n11 + t.dz), v);
+  for (int k = 0; k < 6; ++k) fma2_acc(c1[k], p01, v[k]);
+  load12v(g + 12 * t.n10, t.L, v);
 #pragma unroll
-  for (int k = 0; k < 12; ++k) c1[k] = fmaf(w11, v[k], c1[k]);
+  for (int k = 0; k < 6; ++k) fma2_acc(c1[k], p10, v[k]);
+  load12v(g + 12 * t.n11, t.L, v);
 #pragma unroll
-  for (int k = 0; k < 12; ++k) {
-    A[k] = fmaf(t.wz1, c1[k] - c0[k], c0[k]);
-    if (WITH_DZ) dAdz[k] = c1[k] - c0[k];
+  for (int k = 0; k < 6; ++k) fma2_acc(c1[k], p11, v[k]);
+  const f32x2 pz = pk2(t.wz1, t.wz1);
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    const f32x2 d = sub2(c1[k], c0[k]);
+    upk2(fma2(pz, d, c0[k]), A[2 * k], A[2 * k + 1]);
+    if (WITH_DZ) upk2(d, dAdz[2 * k], dAdz[2 * k + 1]);
   }
 }
 

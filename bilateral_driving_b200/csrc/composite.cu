@@ -107,8 +107,11 @@ __device__ unsigned long long g_stats[16];
 // =================================================================================================
 // forward
 // =================================================================================================
+#ifndef BDS_FWD_MINB
+#define BDS_FWD_MINB 5     // resident CTAs per SM the forward is compiled for (register cap 65536 / (256 * MINB))
+#endif
 template <int MODE>
-__global__ void __launch_bounds__(256, 5) composite_fwd_kernel(CompParams p) {
+__global__ void __launch_bounds__(256, BDS_FWD_MINB) composite_fwd_kernel(CompParams p) {
   __shared__ __align__(128) float4 srec[kStages][kChunk * 3];
   __shared__ __align__(8) uint64_t bars[kStages];
 
@@ -133,7 +136,14 @@ __global__ void __launch_bounds__(256, 5) composite_fwd_kernel(CompParams p) {
 
   const float pxf = (float)g.px + 0.5f, pyf = (float)g.py + 0.5f;
   const float rxmin = g.wx0 + 0.5f, rxmax = g.wx0 + 7.5f, rymin = g.wy0 + 0.5f, rymax = g.wy0 + 3.5f;
-  float T = 1.f, cr = 0.f, cg = 0.f, cb = 0.f, cd = 0.f;
+  float T = 1.f;
+#if BDS_FWD_MINB <= 4
+  f32x2 crg = pk2(0.f, 0.f), cbd = crg;   // (C_r, C_g), (C_b, D) accumulated with packed fp32x2 FMAs
+#else
+  // under the 51-register cap of 5 CTAs/SM ptxas does not keep 64-bit accumulators in place (it copies them
+  // every iteration): scalar FMAs there
+  float cr = 0.f, cg = 0.f, cb = 0.f, cd = 0.f;
+#endif
   int last = -1;
   // alpha >= 1/255  <=>  e >= -log2(255); a saturated (or outside) pixel raises its threshold to +inf, so
   // "done" costs no extra test in the blend loop
@@ -212,10 +222,16 @@ __global__ void __launch_bounds__(256, 5) composite_fwd_kernel(CompParams p) {
           const float nT = T * (1.f - alpha);
           const bool go = ok && nT > kTStop;         // gsplat stops BEFORE adding the saturating record
           const float vis = go ? alpha * T : 0.f;
+#if BDS_FWD_MINB <= 4
+          const f32x2 vis2 = pk2(vis, vis);
+          fma2_acc(crg, vis2, pk2(r1.z, r1.w));
+          fma2_acc(cbd, vis2, pk2(r2.x, r2.y));
+#else
           cr = fmaf(vis, r1.z, cr);
           cg = fmaf(vis, r1.w, cg);
           cb = fmaf(vis, r2.x, cb);
           cd = fmaf(vis, r2.y, cd);
+#endif
           T = go ? nT : T;
           last = go ? idx0 + jj : last;
           emin = (ok && !go) ? INFINITY : emin;
@@ -245,6 +261,11 @@ __global__ void __launch_bounds__(256, 5) composite_fwd_kernel(CompParams p) {
   }
 
   if (!g.inside) return;
+#if BDS_FWD_MINB <= 4
+  float cr, cg, cb, cd;
+  upk2(crg, cr, cg);
+  upk2(cbd, cb, cd);
+#endif
   const float A = 1.f - T;
   p.last_ids[g.pix] = last;
   p.out_alpha[g.pix] = A;
@@ -323,7 +344,8 @@ BDS_D void flush_batch(const BatchSmem* bs, int nb, float rx0, float ry0, float*
   const float X = q0.x - rx0, Y = q0.y - ry0;          // mean relative to pixel (u, v) = (0, 0)
   const float A2 = 2.f * q0.z, B = q0.w, C2 = 2.f * q1.x;
   float m0 = 0.f, mu = 0.f, mv = 0.f, muu = 0.f, muv = 0.f, mvv = 0.f;
-  float c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f, ax = 0.f, ay = 0.f;
+  float ax = 0.f, ay = 0.f;
+  f32x2 c01 = pk2(0.f, 0.f), c23 = c01;   // colour sums as packed fp32x2 (FFMA2)
 #pragma unroll
   for (int r = 0; r < kPartPix / 8; ++r) {
     const float v = (float)(part * (kPartPix / 8) + r);
@@ -337,7 +359,9 @@ BDS_D void flush_batch(const BatchSmem* bs, int nb, float rx0, float ry0, float*
       s0 += d.x;
       s1 = fmaf(d.x, (float)u, s1);
       s2 = fmaf(d.x, (float)(u * u), s2);
-      c0 = fmaf(d.y, c.x, c0); c1 = fmaf(d.y, c.y, c1); c2 = fmaf(d.y, c.z, c2); c3 = fmaf(d.y, c.w, c3);
+      const f32x2 fac2 = pk2(d.y, d.y);
+      fma2_acc(c01, fac2, pk2(c.x, c.y));
+      fma2_acc(c23, fac2, pk2(c.z, c.w));
       const float gx = fmaf(-A2, (float)u, gxr), gy = fmaf(-B, (float)u, gyr);
       ax += fabsf(d.x * gx);
       ay += fabsf(d.x * gy);
@@ -345,6 +369,9 @@ BDS_D void flush_batch(const BatchSmem* bs, int nb, float rx0, float ry0, float*
     m0 += s0; mu += s1; muu += s2;
     mv = fmaf(v, s0, mv); muv = fmaf(v, s1, muv); mvv = fmaf(v * v, s0, mvv);
   }
+  float c0, c1, c2, c3;
+  upk2(c01, c0, c1);
+  upk2(c23, c2, c3);
 #pragma unroll
   for (int o = 16; o >= kBatch; o >>= 1) {   // fold the kParts partial sums of each record
     m0 += __shfl_xor_sync(kFull, m0, o); mu += __shfl_xor_sync(kFull, mu, o); mv += __shfl_xor_sync(kFull, mv, o);
@@ -657,9 +684,8 @@ __global__ void repack_jobs_kernel(RepackJobs jobs) {
       int ch = i / nodes, rem = i - ch * nodes;
       int x = rem % GX, y = (rem / GX) % GY, z = rem / (GX * GY);
       dst[i] += src[(size_t)bil_node(x, y, z, L, GX) * 12 + ch];
-    } else {           // dst = repack [GY][GX][L][12] = src parameter layout
-      int node = i / 12, ch = i - node * 12;
-      dst[i] = src[bil_param_index(node, ch, L, GY, GX)];
+    } else {           // dst = value repack [GY][GX][3][L][4] = src parameter layout
+      dst[i] = src[bil_value_param_index(i, L, GY, GX)];
     }
   }
 }
