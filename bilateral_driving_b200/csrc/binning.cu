@@ -152,8 +152,7 @@ struct EmitParams {
   int32_t* cursors;             // [n_tiles], zero on entry
   int n_slots;
   const float* splats;
-  uint64_t* keys;               // [n_isect] (depth bits << 32) | Gaussian id
-  uint32_t* slots;              // [n_isect]
+  uint64_t* keys;               // [n_isect] (fp32 depth bits << 32) | splat slot: ONE word per record, key and payload
 };
 
 __global__ void __launch_bounds__(256) emit_pairs_kernel(EmitParams p) {
@@ -174,8 +173,9 @@ __global__ void __launch_bounds__(256) emit_pairs_kernel(EmitParams p) {
     band_rows2(p.d, p.tile_h, c, ty0, ty1);
     // same candidate rectangle + same hit test (both non-inlined bodies) as the counting pass
     tr = candidate_rect(r0.x, r0.y, (float)p.radii[idx], r0.z, r0.w, r1.x, r2.w + kLog2_255, p.tile_w, p.tile_h, ty0, ty1);
-    // positive floats order like their bit patterns; ties by Gaussian id (the camera is implied by the tile)
-    key = ((uint64_t)(uint32_t)__float_as_int(r2.y) << 32) | (uint64_t)(uint32_t)(idx - (int64_t)c * N);
+    // positive floats order like their bit patterns; the low word carries the splat slot (exact depth ties are
+    // re-ordered by Gaussian id after the sort, tile_sort_gather_kernel)
+    key = ((uint64_t)(uint32_t)__float_as_int(r2.y) << 32) | (uint64_t)(uint32_t)slot;
   }
   // Same flat warp-cooperative enumeration as the counting pass (projection.cu).  The capacity guard only
   // makes a count / emission disagreement memory-safe should a toolchain ever break the shared-body
@@ -196,7 +196,6 @@ __global__ void __launch_bounds__(256) emit_pairs_kernel(EmitParams p) {
     const float ga = __shfl_sync(0xffffffffu, r0.z, owner), gb = __shfl_sync(0xffffffffu, r0.w, owner);
     const float gc = __shfl_sync(0xffffffffu, r1.x, owner), gcut = __shfl_sync(0xffffffffu, r2.w, owner) + kLog2_255;
     const int gcam = __shfl_sync(0xffffffffu, c, owner);
-    const int gslot = (blockIdx.x * blockDim.x + (threadIdx.x & ~31)) + owner;
     const unsigned glo = __shfl_sync(0xffffffffu, key_lo, owner), ghi = __shfl_sync(0xffffffffu, key_hi, owner);
     if (base + lane < total) {
       const int ry = local / ow;
@@ -205,10 +204,7 @@ __global__ void __launch_bounds__(256) emit_pairs_kernel(EmitParams p) {
         const int tile = (gcam * p.tile_h + ty - p.d.row_begin) * p.tile_w + tx;
         const int seg0 = p.tile_offsets[tile], cap = p.tile_offsets[tile + 1] - seg0;
         const int pos = atomicAdd(p.cursors + tile, 1);
-        if (pos < cap) {
-          p.keys[seg0 + pos] = ((uint64_t)ghi << 32) | glo;
-          p.slots[seg0 + pos] = (uint32_t)gslot;
-        }
+        if (pos < cap) p.keys[seg0 + pos] = ((uint64_t)ghi << 32) | glo;
       }
     }
   }
@@ -220,12 +216,12 @@ __global__ void __launch_bounds__(256) emit_pairs_kernel(EmitParams p) {
 // smaller key at the lower index, so positions >= n behave as +inf padding that never moves and pairs
 // reaching beyond n are simply skipped - any n, no power-of-two padding in memory.
 // ---------------------------------------------------------------------------------------------
-constexpr int kTileSortCap = 4096;    // records sorted in shared memory: 4096 x (8 + 4) B = 48 KB
-constexpr int kTileSortSmall = 1024;  // segments up to here go to the 12 KB instance
+constexpr int kTileSortCap = 4096;    // records sorted in shared memory: 4096 x 8 B = 32 KB
+constexpr int kTileSortSmall = 1024;  // segments up to here go to the 8 KB instance
 constexpr uint32_t kNullSlot = 0xffffffffu;
 
-template <typename KeyPtr, typename SlotPtr>
-BDS_D void block_bitonic_sort(KeyPtr keys, SlotPtr slots, int n) {
+template <typename KeyPtr>
+BDS_D void block_bitonic_sort(KeyPtr keys, int n) {
   int np2 = 1;
   while (np2 < n) np2 <<= 1;
   const int half = np2 >> 1;
@@ -238,11 +234,7 @@ BDS_D void block_bitonic_sort(KeyPtr keys, SlotPtr slots, int n) {
         const int q = mirror ? (i - lo) + (k - 1 - lo) : i + j;
         if (q < n) {
           const uint64_t a = keys[i], b = keys[q];
-          if (a > b) {
-            keys[i] = b; keys[q] = a;
-            const uint32_t sa = slots[i], sb = slots[q];
-            slots[i] = sb; slots[q] = sa;
-          }
+          if (a > b) { keys[i] = b; keys[q] = a; }
         }
       }
       __syncthreads();
@@ -250,37 +242,71 @@ BDS_D void block_bitonic_sort(KeyPtr keys, SlotPtr slots, int n) {
   }
 }
 
+// gsplat orders equal depths by Gaussian id (stable radix sort over Gaussian-major intersections).  The sort above
+// orders them by splat slot; slots are handed out by warp-aggregated atomics, so exact fp32 depth ties (a few
+// hundred tiles per step at the bench size) are put into id order here: one thread, insertion sort inside each run
+// of equal depth.  Uniform early-out when the tile has no tie.
+template <typename KeyPtr>
+BDS_D void fix_depth_ties(KeyPtr keys, int n, const float4* __restrict__ splats) {
+  int tie = 0;
+  for (int i = threadIdx.x; i + 1 < n; i += blockDim.x) {
+    const uint64_t a = keys[i], b = keys[i + 1];
+    tie |= (uint32_t)(a >> 32) == (uint32_t)(b >> 32) && (uint32_t)b != kNullSlot;
+  }
+  if (!__syncthreads_or(tie)) return;
+  if (threadIdx.x == 0) {
+    int i = 0;
+    while (i + 1 < n) {
+      int e = i + 1;
+      const uint32_t depth = (uint32_t)(keys[i] >> 32);
+      while (e < n && (uint32_t)(keys[e] >> 32) == depth && (uint32_t)keys[e] != kNullSlot) ++e;
+      for (int a = i + 1; a < e; ++a) {          // insertion sort of [i, e) by Gaussian id
+        const uint64_t ka = keys[a];
+        const int ida = __float_as_int(__ldg(splats + (size_t)(uint32_t)ka * 3 + 2).z);
+        int b = a - 1;
+        while (b >= i && __float_as_int(__ldg(splats + (size_t)(uint32_t)keys[b] * 3 + 2).z) > ida) {
+          keys[b + 1] = keys[b];
+          --b;
+        }
+        keys[b + 1] = ka;
+      }
+      i = e;
+    }
+  }
+  __syncthreads();
+}
+
 template <int CAP, bool BIG>
 __global__ void __launch_bounds__(256) tile_sort_gather_kernel(const int32_t* __restrict__ tile_offsets,
-                                                               uint64_t* __restrict__ keys, uint32_t* __restrict__ slots,
+                                                               uint64_t* __restrict__ keys,
                                                                const float4* __restrict__ splats,
                                                                float4* __restrict__ sorted,
                                                                int32_t* __restrict__ sorted_slots) {
   __shared__ __align__(16) uint64_t s_keys[CAP];
-  __shared__ uint32_t s_slots[CAP];
   const int tile = blockIdx.x;
   const int seg0 = tile_offsets[tile];
   const int n = tile_offsets[tile + 1] - seg0;
   // two launches share the tiles: the small-footprint instance (many CTAs per SM) takes the common short
-  // segments, the 48 KB instance the long ones
+  // segments, the 32 KB instance the long ones
   if (n <= 0 || (BIG ? n <= kTileSortSmall : n > kTileSortSmall)) return;
-  const uint32_t* order;
+  const uint64_t* order;
   if (n <= CAP) {
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-      s_keys[i] = keys[seg0 + i];
-      s_slots[i] = slots[seg0 + i];
-    }
+    for (int i = threadIdx.x; i < n; i += blockDim.x) s_keys[i] = keys[seg0 + i];
     __syncthreads();
-    if (n > 1) block_bitonic_sort(s_keys, s_slots, n);
-    order = s_slots;
+    if (n > 1) {
+      block_bitonic_sort(s_keys, n);
+      fix_depth_ties(s_keys, n, splats);
+    }
+    order = s_keys;
   } else {
-    block_bitonic_sort(keys + seg0, slots + seg0, n);  // rare: oversized segment, in place in global memory
-    order = slots + seg0;
+    block_bitonic_sort(keys + seg0, n);  // rare: oversized segment, in place in global memory
+    fix_depth_ties(keys + seg0, n, splats);
+    order = keys + seg0;
   }
-  // sorted[seg0 + i] = splats[order[i]] with the id field replaced by the slot; one thread per float4
+  // sorted[seg0 + i] = splats[slot of order[i]] with the id field replaced by the slot; one thread per float4
   for (int t = threadIdx.x; t < n * 3; t += blockDim.x) {
     const int i = t / 3, part = t - i * 3;
-    const uint32_t slot = order[i];
+    const uint32_t slot = (uint32_t)order[i];
     float4 v;
     if (slot == kNullSlot) {  // never-filled position (see emit_pairs_kernel): a record that contributes nothing
       v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -292,18 +318,18 @@ __global__ void __launch_bounds__(256) tile_sort_gather_kernel(const int32_t* __
     sorted[(size_t)seg0 * 3 + t] = v;
   }
   if (sorted_slots)
-    for (int i = threadIdx.x; i < n; i += blockDim.x) sorted_slots[seg0 + i] = (int32_t)order[i];
+    for (int i = threadIdx.x; i < n; i += blockDim.x) sorted_slots[seg0 + i] = (int32_t)(uint32_t)order[i];
 }
 
 struct SortWorkspace {
-  size_t keys, slots, cursors, total;
+  size_t keys, cursors, total;
 };
 static SortWorkspace carve_sort(int64_t n_isect, int n_tiles) {
   SortWorkspace w;
   size_t off = 0;
   size_t nk = (size_t)(n_isect > 0 ? n_isect : 1);
   auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes, 256); return o; };
-  w.keys = take(nk * 8); w.slots = take(nk * 4); w.cursors = take((size_t)(n_tiles + 1) * 4);
+  w.keys = take(nk * 8); w.cursors = take((size_t)(n_tiles + 1) * 4);
   w.total = off;
   return w;
 }
@@ -351,23 +377,21 @@ extern "C" int bds_bin_sort(const bds_render_desc* d, int64_t n_isect, int32_t n
   char* ws = static_cast<char*>(workspace);
   SortWorkspace w = carve_sort(n_isect, n_tiles);
   uint64_t* keys = reinterpret_cast<uint64_t*>(ws + w.keys);
-  uint32_t* slots = reinterpret_cast<uint32_t*>(ws + w.slots);
   int32_t* cursors = reinterpret_cast<int32_t*>(ws + w.cursors);
   // sentinels: a position the emission never fills sorts last and gathers a null record
   BDS_CHECK_CUDA(cudaMemsetAsync(keys, 0xff, (size_t)n_isect * 8, stream));
-  BDS_CHECK_CUDA(cudaMemsetAsync(slots, 0xff, (size_t)n_isect * 4, stream));
   BDS_CHECK_CUDA(cudaMemsetAsync(cursors, 0, (size_t)(n_tiles + 1) * 4, stream));
   EmitParams ep;
   ep.d = *d; ep.tile_w = tile_w; ep.tile_h = tile_h; ep.radii = radii; ep.tile_offsets = tile_offsets;
-  ep.cursors = cursors; ep.n_slots = n_slots; ep.splats = splats; ep.keys = keys; ep.slots = slots;
+  ep.cursors = cursors; ep.n_slots = n_slots; ep.splats = splats; ep.keys = keys;
   emit_pairs_kernel<<<ceil_div(n_slots, 256), 256, 0, stream>>>(ep);
   BDS_CHECK_LAUNCH();
   tile_sort_gather_kernel<kTileSortSmall, false><<<n_tiles, 256, 0, stream>>>(
-      tile_offsets, keys, slots, reinterpret_cast<const float4*>(splats), reinterpret_cast<float4*>(sorted_splats),
+      tile_offsets, keys, reinterpret_cast<const float4*>(splats), reinterpret_cast<float4*>(sorted_splats),
       sorted_slots);
   BDS_CHECK_LAUNCH();
   tile_sort_gather_kernel<kTileSortCap, true><<<n_tiles, 256, 0, stream>>>(
-      tile_offsets, keys, slots, reinterpret_cast<const float4*>(splats), reinterpret_cast<float4*>(sorted_splats),
+      tile_offsets, keys, reinterpret_cast<const float4*>(splats), reinterpret_cast<float4*>(sorted_splats),
       sorted_slots);
   BDS_CHECK_LAUNCH();
   return 0;

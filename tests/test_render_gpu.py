@@ -320,3 +320,31 @@ def test_masked_rerender_reuses_sorted_lists():
             assert torch.equal(r1, r2)
     with pytest.raises(ValueError):
         rasterize_masked(info, torch.ones(N + 1, dtype=torch.bool, device="cuda"))
+
+
+def test_equal_depth_ties_follow_gaussian_order():
+    """gsplat orders splats of exactly equal depth by Gaussian id (stable sort over Gaussian-major intersections).
+    The tile sort here keys on (depth bits, splat slot) and repairs ties afterwards: co-located Gaussians with
+    different colours must blend in id order, whatever slots the projection handed out."""
+    from bilateral_driving_b200.render import render_fused
+    from oracle.path_ref import render_path
+
+    p, vm, Ks, W, H, _, sky = _fused_inputs()
+    Cn = vm.shape[0]
+    N = p["_means"].shape[0]
+    gen = torch.Generator(); gen.manual_seed(21)
+    p = {k: v.clone() for k, v in p.items()}
+    # 300 groups of 3 co-located Gaussians scattered over the id range (identical mean => identical fp32 depth)
+    perm = torch.randperm(N, generator=gen)[:900].view(300, 3)
+    p["_means"][perm[:, 1]] = p["_means"][perm[:, 0]]
+    p["_means"][perm[:, 2]] = p["_means"][perm[:, 0]]
+    p["_opacities"][perm.reshape(-1)] = 1.5           # opaque enough for the order to matter
+    o_p = {k: v.double() for k, v in p.items()}
+    with torch.no_grad():
+        o = render_path(o_p, vm.double(), Ks.double(), W, H, sky=sky.double(), grid_slots=None, guidance_factor=None)
+        keep = (~o["ambiguous"])[..., None].cuda()
+        out = render_fused({k: v.cuda() for k, v in p.items()}, vm.cuda(), Ks.cuda(), W, H,
+                           sky=sky.cuda().view(Cn * H, W, 3), grid_slots=None, bil_sizes=(), sh_degree=3, near_plane=0.1)
+    for k in ("rgb", "opacity"):
+        ours = out[k].view(Cn, H, W, -1)
+        assert ((ours - o[k].float().cuda()).abs() * keep).max() < 1e-5, k
