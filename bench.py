@@ -321,6 +321,15 @@ def main():
         parts["other (loss, TV, fills, gaps)"] = ms / args.steps - sum(parts.values())
         sys.stderr.write("phase ms/step: " + json.dumps({k: round(v, 3) for k, v in parts.items()}) + "\n")
 
+    if os.environ.get("BDS_TIMELINE") and rank == 0:
+        # profiling aid: kernel timeline of three steps (torch.profiler / CUPTI) -> gaps between kernels
+        from torch.profiler import ProfilerActivity, profile
+        with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+            for _ in range(3):
+                step(gt_dev, vm_d, Ks_d)
+            torch.cuda.synchronize()
+        prof.export_chrome_trace(os.environ["BDS_TIMELINE"])
+
     # end to end through the public API with HOST buffers: GT image + cameras copied from pinned
     # memory every step, loss read back
     copy_stream = torch.cuda.Stream()

@@ -134,9 +134,11 @@ class _TVFn(torch.autograd.Function):
         N, _, L, GY, GX = g.shape
         v_g = torch.zeros_like(g)
         scratch = torch.zeros((), device=g.device, dtype=torch.float32)
-        check(lib.bds_tv_fwd_bwd(ptr(g), N, L, GY, GX, C.c_float(ctx.weight), C.c_float(float(v_loss)),
+        # the upstream cotangent stays on the device (reading it here would stall the host at the very start of the
+        # backward, before the long kernels are queued): unit cotangent in the kernel, scaled afterwards
+        check(lib.bds_tv_fwd_bwd(ptr(g), N, L, GY, GX, C.c_float(ctx.weight), C.c_float(1.0),
                                  ptr(scratch), ptr(v_g), stream_ptr()), "bds_tv_fwd_bwd")
-        return v_g, None
+        return v_g.mul_(v_loss.to(v_g.dtype)), None
 
 
 def total_variation_loss(x, weight: float = 1.0):
