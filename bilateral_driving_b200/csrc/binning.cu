@@ -216,8 +216,8 @@ __global__ void __launch_bounds__(256) emit_pairs_kernel(EmitParams p) {
 // smaller key at the lower index, so positions >= n behave as +inf padding that never moves and pairs
 // reaching beyond n are simply skipped - any n, no power-of-two padding in memory.
 // ---------------------------------------------------------------------------------------------
-constexpr int kTileSortCap = 4096;    // records sorted in shared memory: 4096 x 8 B = 32 KB
-constexpr int kTileSortSmall = 1024;  // segments up to here go to the 8 KB instance
+constexpr int kTileSortCap = 4096;    // 64 KB instance: 2 x 4096 x 8 B (merge sort ping-pong)
+constexpr int kTileSortSmall = 2048;  // segments up to here go to the 32 KB instance
 constexpr uint32_t kNullSlot = 0xffffffffu;
 
 template <typename KeyPtr>
@@ -240,6 +240,59 @@ BDS_D void block_bitonic_sort(KeyPtr keys, int n) {
       __syncthreads();
     }
   }
+}
+
+// Block merge sort for a segment that fits shared memory: every warp sorts 32-key chunks in registers (bitonic over
+// the lanes, shuffles only), then log2(n / 32) merge levels in which each key finds its output position by a
+// binary search in the partner run (keys are unique - the slot is part of the word - so the position is
+// unambiguous; the left run counts strictly smaller partners, the right run smaller-or-equal ones, which also
+// keeps equal sentinels apart).  Less than half the instructions of the bitonic network at the segment lengths
+// that hold most records (500-1400) and 5-7 block barriers instead of 55-66.
+BDS_D uint64_t warp_sort32(uint64_t key) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j >= 1; j >>= 1) {
+      const uint64_t other = __shfl_xor_sync(0xffffffffu, key, j);
+      const bool take_min = ((lane & j) == 0) == ((lane & k) == 0);
+      key = (take_min == (key < other)) ? key : other;
+    }
+  }
+  return key;
+}
+
+// a: the n keys (shared), b: scratch of the same size; returns the buffer that holds the sorted keys
+BDS_D uint64_t* block_merge_sort(uint64_t* a, uint64_t* b, int n) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int c0 = warp * 32; c0 < n; c0 += 256) {
+    const int i = c0 + lane;
+    uint64_t k = i < n ? a[i] : ~0ull;   // padding sorts to the end of the chunk and is not stored
+    k = warp_sort32(k);
+    if (i < n) a[i] = k;
+  }
+  __syncthreads();
+  uint64_t *src = a, *dst = b;
+  for (int m = 32; m < n; m <<= 1) {
+    for (int i = threadIdx.x; i < n; i += 256) {
+      const int run = i / m;
+      const bool right = run & 1;
+      const int pair0 = (run & ~1) * m;
+      const int other0 = right ? pair0 : pair0 + m;   // start of the partner run
+      const int olen = max(0, min(m, n - other0));
+      const uint64_t x = src[i];
+      int lo = 0, hi = olen;
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        const uint64_t y = src[other0 + mid];
+        if (right ? (y <= x) : (y < x)) lo = mid + 1; else hi = mid;
+      }
+      dst[i - (right ? m : 0) + lo] = x;   // pair0 + (index inside the own run) + (partners in front)
+    }
+    __syncthreads();
+    uint64_t* t = src; src = dst; dst = t;
+  }
+  return src;
 }
 
 // gsplat orders equal depths by Gaussian id (stable radix sort over Gaussian-major intersections).  The sort above
@@ -281,55 +334,65 @@ __global__ void __launch_bounds__(256) tile_sort_gather_kernel(const int32_t* __
                                                                uint64_t* __restrict__ keys,
                                                                const float4* __restrict__ splats,
                                                                float4* __restrict__ sorted,
-                                                               int32_t* __restrict__ sorted_slots) {
-  __shared__ __align__(16) uint64_t s_keys[CAP];
-  const int tile = blockIdx.x;
-  const int seg0 = tile_offsets[tile];
-  const int n = tile_offsets[tile + 1] - seg0;
-  // two launches share the tiles: the small-footprint instance (many CTAs per SM) takes the common short
-  // segments, the 32 KB instance the long ones
-  if (n <= 0 || (BIG ? n <= kTileSortSmall : n > kTileSortSmall)) return;
-  const uint64_t* order;
-  if (n <= CAP) {
-    for (int i = threadIdx.x; i < n; i += blockDim.x) s_keys[i] = keys[seg0 + i];
-    __syncthreads();
-    if (n > 1) {
-      block_bitonic_sort(s_keys, n);
-      fix_depth_ties(s_keys, n, splats);
+                                                               int32_t* __restrict__ sorted_slots,
+                                                               int32_t* __restrict__ big_list) {
+  extern __shared__ __align__(16) uint64_t s_keys[];   // 2 x CAP keys (merge sort ping-pong)
+  // the 32 KB instance (one CTA per tile, 7 CTAs per SM) sorts every segment up to kTileSortSmall records and
+  // queues longer ones (big_list[0] = count, then tile ids) for the 64 KB instance, a fixed grid over that queue
+  // that costs a few microseconds when the queue is empty
+  for (int item = blockIdx.x; BIG ? item < big_list[0] : item == (int)blockIdx.x; item += gridDim.x) {
+    const int tile = BIG ? big_list[1 + item] : item;
+    const int seg0 = tile_offsets[tile];
+    const int n = tile_offsets[tile + 1] - seg0;
+    if (n <= 0) continue;
+    if (!BIG && n > CAP) {
+      if (threadIdx.x == 0) big_list[1 + atomicAdd(big_list, 1)] = tile;
+      return;
     }
-    order = s_keys;
-  } else {
-    block_bitonic_sort(keys + seg0, n);  // rare: oversized segment, in place in global memory
-    fix_depth_ties(keys + seg0, n, splats);
-    order = keys + seg0;
-  }
-  // sorted[seg0 + i] = splats[slot of order[i]] with the id field replaced by the slot; one thread per float4
-  for (int t = threadIdx.x; t < n * 3; t += blockDim.x) {
-    const int i = t / 3, part = t - i * 3;
-    const uint32_t slot = (uint32_t)order[i];
-    float4 v;
-    if (slot == kNullSlot) {  // never-filled position (see emit_pairs_kernel): a record that contributes nothing
-      v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (part == 2) v = make_float4(0.f, 0.f, __int_as_float(0), -1.0e30f);
+    if (BIG) __syncthreads();   // the previous item's gather is done with the shared keys
+    const uint64_t* order;
+    if (n <= CAP) {
+      for (int i = threadIdx.x; i < n; i += blockDim.x) s_keys[i] = keys[seg0 + i];
+      __syncthreads();
+      uint64_t* sorted_keys = s_keys;
+      if (n > 1) {
+        sorted_keys = block_merge_sort(s_keys, s_keys + CAP, n);
+        fix_depth_ties(sorted_keys, n, splats);
+      }
+      order = sorted_keys;
     } else {
-      v = __ldg(splats + (size_t)slot * 3 + part);
-      if (part == 2) v.z = __int_as_float((int)slot);
+      block_bitonic_sort(keys + seg0, n);  // rare: oversized segment, in place in global memory
+      fix_depth_ties(keys + seg0, n, splats);
+      order = keys + seg0;
     }
-    sorted[(size_t)seg0 * 3 + t] = v;
+    // sorted[seg0 + i] = splats[slot of order[i]] with the id field replaced by the slot; one thread per float4
+    for (int t = threadIdx.x; t < n * 3; t += blockDim.x) {
+      const int i = t / 3, part = t - i * 3;
+      const uint32_t slot = (uint32_t)order[i];
+      float4 v;
+      if (slot == kNullSlot) {  // never-filled position (see emit_pairs_kernel): a record that contributes nothing
+        v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (part == 2) v = make_float4(0.f, 0.f, __int_as_float(0), -1.0e30f);
+      } else {
+        v = __ldg(splats + (size_t)slot * 3 + part);
+        if (part == 2) v.z = __int_as_float((int)slot);
+      }
+      sorted[(size_t)seg0 * 3 + t] = v;
+    }
+    if (sorted_slots)
+      for (int i = threadIdx.x; i < n; i += blockDim.x) sorted_slots[seg0 + i] = (int32_t)(uint32_t)order[i];
   }
-  if (sorted_slots)
-    for (int i = threadIdx.x; i < n; i += blockDim.x) sorted_slots[seg0 + i] = (int32_t)(uint32_t)order[i];
 }
 
 struct SortWorkspace {
-  size_t keys, cursors, total;
+  size_t keys, cursors, big_list, total;
 };
 static SortWorkspace carve_sort(int64_t n_isect, int n_tiles) {
   SortWorkspace w;
   size_t off = 0;
   size_t nk = (size_t)(n_isect > 0 ? n_isect : 1);
   auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes, 256); return o; };
-  w.keys = take(nk * 8); w.cursors = take((size_t)(n_tiles + 1) * 4);
+  w.keys = take(nk * 8); w.cursors = take((size_t)(n_tiles + 1) * 4); w.big_list = take((size_t)(n_tiles + 1) * 4);
   w.total = off;
   return w;
 }
@@ -381,18 +444,23 @@ extern "C" int bds_bin_sort(const bds_render_desc* d, int64_t n_isect, int32_t n
   // sentinels: a position the emission never fills sorts last and gathers a null record
   BDS_CHECK_CUDA(cudaMemsetAsync(keys, 0xff, (size_t)n_isect * 8, stream));
   BDS_CHECK_CUDA(cudaMemsetAsync(cursors, 0, (size_t)(n_tiles + 1) * 4, stream));
+  int32_t* big_list = reinterpret_cast<int32_t*>(ws + w.big_list);
+  BDS_CHECK_CUDA(cudaMemsetAsync(big_list, 0, 4, stream));
   EmitParams ep;
   ep.d = *d; ep.tile_w = tile_w; ep.tile_h = tile_h; ep.radii = radii; ep.tile_offsets = tile_offsets;
   ep.cursors = cursors; ep.n_slots = n_slots; ep.splats = splats; ep.keys = keys;
   emit_pairs_kernel<<<ceil_div(n_slots, 256), 256, 0, stream>>>(ep);
   BDS_CHECK_LAUNCH();
-  tile_sort_gather_kernel<kTileSortSmall, false><<<n_tiles, 256, 0, stream>>>(
+  BDS_CHECK_CUDA(cudaFuncSetAttribute(tile_sort_gather_kernel<kTileSortCap, true>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kTileSortCap * 8));
+  tile_sort_gather_kernel<kTileSortSmall, false><<<n_tiles, 256, 2 * kTileSortSmall * 8, stream>>>(
       tile_offsets, keys, reinterpret_cast<const float4*>(splats), reinterpret_cast<float4*>(sorted_splats),
-      sorted_slots);
+      sorted_slots, big_list);
   BDS_CHECK_LAUNCH();
-  tile_sort_gather_kernel<kTileSortCap, true><<<n_tiles, 256, 0, stream>>>(
+  const int big_grid = n_tiles < 3 * 148 ? n_tiles : 3 * 148;   // 64 KB of shared memory: 3 CTAs per SM
+  tile_sort_gather_kernel<kTileSortCap, true><<<big_grid, 256, 2 * kTileSortCap * 8, stream>>>(
       tile_offsets, keys, reinterpret_cast<const float4*>(splats), reinterpret_cast<float4*>(sorted_splats),
-      sorted_slots);
+      sorted_slots, big_list);
   BDS_CHECK_LAUNCH();
   return 0;
 }
