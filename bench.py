@@ -34,8 +34,8 @@ UNIT = "Mpix/s"
 LAMBDA_D, LAMBDA_A, TV_W = 0.01, 0.05, 1.0
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the roofline kernel on the default workload
 # (2 M Gaussians, 6 x 1920x1080, N=1), from the `ncu --set full` capture summarised in
-# profiles/r01_ncu_full_key_metrics.txt (0.671667 GB read + 0.421343 GB written).  Reported only for that workload.
-NCU_TRAFFIC_BYTES = {"full": 671_667_000 + 421_342_720}
+# profiles/r01_ncu_full_key_metrics.txt (0.674020 GB read + 0.425888 GB written).  Reported only for that workload.
+NCU_TRAFFIC_BYTES = {"full": 674_020_000 + 425_887_744}
 
 
 def parse():
