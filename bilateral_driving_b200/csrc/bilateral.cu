@@ -118,6 +118,7 @@ __global__ void __launch_bounds__(256) apply_fwd_kernel(const float* __restrict_
 //                                 per low-res pixel).
 // ---------------------------------------------------------------------------------------------
 constexpr int kMaxFoot = 18;  // low-res rows/cols a 16-pixel tile edge can touch (factor >= 2 -> <= 10)
+static_assert((256 * 12 + 16 * kMaxFoot * 12) * sizeof(float) <= kBwdSmemBil, "cotangent stage + row sums must fit the tile's shared memory");
 
 __global__ void __launch_bounds__(256) apply_bwd_tiled_kernel(const float* __restrict__ rgb_in,
                                                               const float* __restrict__ v_rgb_out,
@@ -203,19 +204,38 @@ __global__ void __launch_bounds__(256) apply_bwd_tiled_kernel(const float* __res
           wx_tab[q][t] = wx;
         }
         __syncthreads();
-        for (int item = threadIdx.x; item < nly * nlx * 12; item += 256) {
-          const int c = item % 12, q = item / 12;
-          const int qx = q % nlx, qy = q / nlx;
-          float acc = 0.f;
-          for (int ty = 0; ty < 16; ++ty) {
-            const float wy = wy_tab[qy][ty];
-            if (wy == 0.f) continue;
-            float row = 0.f;
+        // separable gather: along x first (tile row ty, low-res column qx), then along y - 16 x fewer FMAs than
+        // the direct double sum; one thread per (row, column, channel quad)
+        float4* rows = reinterpret_cast<float4*>(smem + 256 * 12);   // [16][nlx][3]
+        const float4* sva4 = reinterpret_cast<const float4*>(sva);
+        for (int item = threadIdx.x; item < 16 * nlx * 3; item += 256) {
+          const int q4 = item % 3, r = item / 3;
+          const int qx = r % nlx, ty = r / nlx;
+          float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-            for (int tx = 0; tx < 16; ++tx) row = fmaf(wx_tab[qx][tx], sva[(ty * 16 + tx) * 12 + c], row);
-            acc = fmaf(wy, row, acc);
+          for (int tx = 0; tx < 16; ++tx) {
+            const float w = wx_tab[qx][tx];
+            const float4 v = sva4[(ty * 16 + tx) * 3 + q4];
+            acc.x = fmaf(w, v.x, acc.x); acc.y = fmaf(w, v.y, acc.y); acc.z = fmaf(w, v.z, acc.z); acc.w = fmaf(w, v.w, acc.w);
           }
-          if (acc != 0.f) red_add(lv.v_a_low + ((size_t)(qy0 + qy) * lv.Wd + qx0 + qx) * 12 + c, acc);
+          rows[(ty * nlx + qx) * 3 + q4] = acc;
+        }
+        __syncthreads();
+        for (int item = threadIdx.x; item < nly * nlx * 3; item += 256) {
+          const int q4 = item % 3, q = item / 3;
+          const int qx = q % nlx, qy = q / nlx;
+          float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int ty = 0; ty < 16; ++ty) {
+            const float w = wy_tab[qy][ty];
+            const float4 v = rows[(ty * nlx + qx) * 3 + q4];
+            acc.x = fmaf(w, v.x, acc.x); acc.y = fmaf(w, v.y, acc.y); acc.z = fmaf(w, v.z, acc.z); acc.w = fmaf(w, v.w, acc.w);
+          }
+          float* dst = lv.v_a_low + ((size_t)(qy0 + qy) * lv.Wd + qx0 + qx) * 12 + q4 * 4;
+          if (acc.x != 0.f) red_add(dst, acc.x);
+          if (acc.y != 0.f) red_add(dst + 1, acc.y);
+          if (acc.z != 0.f) red_add(dst + 2, acc.z);
+          if (acc.w != 0.f) red_add(dst + 3, acc.w);
         }
         __syncthreads();
         // a tile wider than kMaxFoot low-res pixels cannot happen for factor >= 2 (<= 10)
