@@ -1,12 +1,13 @@
 // Tile binning.  The projection kernel counted, per band tile, the splats that reach it; here
 //   bds_bin_count  scans those counts into per-tile start offsets (+ the record total), and
 //   bds_bin_sort   (1) emits every (tile, splat) pair into its tile's segment through a per-tile atomic
-//                  cursor (unordered inside the segment), (2) sorts each segment by (fp32 depth bits,
-//                  Gaussian id) with ONE CTA per tile - in shared memory for segments up to
-//                  kTileSortCap records, in place in global memory beyond - and gathers the packed
+//                  cursor (unordered inside the segment) as ONE 64-bit word (fp32 depth bits << 32 | splat
+//                  slot), (2) sorts each segment with ONE CTA per tile - block merge sort in shared memory
+//                  for segments up to kTileSortCap records, bitonic in place in global memory beyond -
+//                  restores gsplat's Gaussian-id order among exact depth ties, and gathers the packed
 //                  48-byte splat records into that order, so that the composite kernels read contiguous
 //                  chunks (TMA bulk copies).
-// No global sort: a record is written once as a 12-byte (key, slot) pair and once as its 48-byte record.
+// No global sort: a record is written once as an 8-byte word and once as its 48-byte record.
 //
 // Replaces gsplat's isect_tiles + torch.cumsum + cub::DeviceRadixSort + isect_offset_encode for the
 // reference call at models/trainers/base.py:393-408.  Ordering contract = gsplat's: per (camera, tile)

@@ -16,9 +16,12 @@
 //     exact ellipse-vs-rectangle bound, ballots, and only walks the survivors - the blend itself reads
 //     records from shared memory as 128-bit broadcasts; transmittance lives in a register per pixel and
 //     a warp vote retires the warp when all its pixels are saturated;
-//   * the backward re-walks the same records back to front; per-record gradients are reduced across
-//     the warp with a 16-value transposing shuffle reduction (16 shuffles instead of 12x5) and leave as
-//     ONE 12-lane red.global.add.f32 per (warp, record) into a 48-byte-per-splat gradient record;
+//   * the backward re-walks the same records back to front (2 stages of 128 records) with one running scalar
+//     per pixel; the per-record reduction across the warp is DEFERRED: the walk stores two scalars per (pixel,
+//     record) into a per-warp shared panel and every 16 records the warp transposes the work (lane = record)
+//     and sums the panel into pixel moments in registers - no shuffle tree - that leave as three 128-bit vector
+//     reductions into a 48-byte-per-splat gradient record (see flush_batch);
+//   * FMA-dense parts (trilinear slice, colour sums) use packed fp32x2 FMAs (FFMA2);
 //   * no tensor cores: the work is gather / pointwise / scatter.
 #include <stdlib.h>
 
