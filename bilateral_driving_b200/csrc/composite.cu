@@ -407,8 +407,11 @@ constexpr size_t kBwdSmemRec = (size_t)kBStages * kChunk * kRecBytes;
 constexpr size_t kBwdSmemWalk = kBwdSmemRec + 8 * sizeof(BatchSmem);
 constexpr size_t kBwdSmem = kBwdSmemBil > kBwdSmemWalk ? kBwdSmemBil : kBwdSmemWalk;
 
+#ifndef BDS_BWD_MINB
+#define BDS_BWD_MINB 4     // resident CTAs per SM the backward is compiled for
+#endif
 template <int MODE>
-__global__ void __launch_bounds__(256, 4) composite_bwd_kernel(CompParams p) {
+__global__ void __launch_bounds__(256, BDS_BWD_MINB) composite_bwd_kernel(CompParams p) {
   extern __shared__ __align__(128) unsigned char dyn_smem[];
   float4 (*srec)[kChunk * 3] = reinterpret_cast<float4 (*)[kChunk * 3]>(dyn_smem);
   __shared__ __align__(8) uint64_t bars[kBStages];
