@@ -12,6 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, os.environ.get("BDS_LIB", "libbds_b200.so"))
 MAX_LEVELS = 4
 TILE = 16
+COUNTERS_LEN = 4096  # BDS_COUNTERS_LEN (include/bds.h)
 SPLAT_FLOATS = 12
 
 

@@ -15,7 +15,7 @@
 //
 // All kernels are HBM-bound integer / copy work: coalesced loads where the data allows, grid sized to
 // the data.
-#include "projection_math.cuh"
+#include "big_splats.cuh"
 
 namespace bds {
 
@@ -154,6 +154,7 @@ struct EmitParams {
   int n_slots;
   const float* splats;
   uint64_t* keys;               // [n_isect] (fp32 depth bits << 32) | splat slot: ONE word per record, key and payload
+  int32_t* big_q;               // [0] = count, [1..] = slots of the very large splats (big_splats.cuh)
 };
 
 __global__ void __launch_bounds__(256) emit_pairs_kernel(EmitParams p) {
@@ -180,8 +181,15 @@ __global__ void __launch_bounds__(256) emit_pairs_kernel(EmitParams p) {
   }
   // Same flat warp-cooperative enumeration as the counting pass (projection.cu).  The capacity guard only
   // makes a count / emission disagreement memory-safe should a toolchain ever break the shared-body
-  // contract; unfilled positions keep the sentinel the host wrote and become null records.
-  const int ncand = active ? (tr.x1 - tr.x0) * (tr.y1 - tr.y0) : 0;
+  // contract; positions a tile's cursor never reached are read as sentinels by the sort and become null records.
+  int ncand = active ? (tr.x1 - tr.x0) * (tr.y1 - tr.y0) : 0;
+  if (ncand > kBigCand) {   // very large footprint: queued for big_splat_kernel (one CTA per splat)
+    const int q = atomicAdd(p.big_q, 1);
+    if (q < kBigQueueCap) {
+      p.big_q[1 + q] = slot;
+      ncand = 0;
+    }
+  }
   const int incl = warp_inclusive_scan_i32(ncand);
   const int total = __shfl_sync(0xffffffffu, incl, 31);
   const int excl = incl - ncand;
@@ -336,7 +344,8 @@ __global__ void __launch_bounds__(256) tile_sort_gather_kernel(const int32_t* __
                                                                const float4* __restrict__ splats,
                                                                float4* __restrict__ sorted,
                                                                int32_t* __restrict__ sorted_slots,
-                                                               int32_t* __restrict__ big_list) {
+                                                               int32_t* __restrict__ big_list,
+                                                               const int32_t* __restrict__ cursors) {
   extern __shared__ __align__(16) uint64_t s_keys[];   // 2 x CAP keys (merge sort ping-pong)
   // the 32 KB instance (one CTA per tile, 7 CTAs per SM) sorts every segment up to kTileSortSmall records and
   // queues longer ones (big_list[0] = count, then tile ids) for the 64 KB instance, a fixed grid over that queue
@@ -351,9 +360,12 @@ __global__ void __launch_bounds__(256) tile_sort_gather_kernel(const int32_t* __
       return;
     }
     if (BIG) __syncthreads();   // the previous item's gather is done with the shared keys
+    // the emission filled the first cursors[tile] positions of the segment; should a toolchain ever make the
+    // counting and the emission pass disagree, the rest are sentinels (they sort last and gather null records)
+    const int filled = min(cursors[tile], n);
     const uint64_t* order;
     if (n <= CAP) {
-      for (int i = threadIdx.x; i < n; i += blockDim.x) s_keys[i] = keys[seg0 + i];
+      for (int i = threadIdx.x; i < n; i += blockDim.x) s_keys[i] = i < filled ? keys[seg0 + i] : ~0ull;
       __syncthreads();
       uint64_t* sorted_keys = s_keys;
       if (n > 1) {
@@ -362,6 +374,8 @@ __global__ void __launch_bounds__(256) tile_sort_gather_kernel(const int32_t* __
       }
       order = sorted_keys;
     } else {
+      for (int i = filled + threadIdx.x; i < n; i += blockDim.x) keys[seg0 + i] = ~0ull;
+      __syncthreads();
       block_bitonic_sort(keys + seg0, n);  // rare: oversized segment, in place in global memory
       fix_depth_ties(keys + seg0, n, splats);
       order = keys + seg0;
@@ -386,14 +400,19 @@ __global__ void __launch_bounds__(256) tile_sort_gather_kernel(const int32_t* __
 }
 
 struct SortWorkspace {
-  size_t keys, cursors, big_list, total;
+  size_t keys, cursors, big_list, big_q, total;
 };
 static SortWorkspace carve_sort(int64_t n_isect, int n_tiles) {
   SortWorkspace w;
   size_t off = 0;
   size_t nk = (size_t)(n_isect > 0 ? n_isect : 1);
   auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes, 256); return o; };
-  w.keys = take(nk * 8); w.cursors = take((size_t)(n_tiles + 1) * 4); w.big_list = take((size_t)(n_tiles + 1) * 4);
+  w.keys = take(nk * 8);
+  // cursors | big_list | big_q are contiguous: ONE memset zeroes the cursors and the two queue counters
+  w.cursors = off; off += (size_t)(n_tiles + 1) * 4;
+  w.big_list = off; off += (size_t)(n_tiles + 1) * 4;
+  w.big_q = off; off += (size_t)(kBigQueueCap + 1) * 4;
+  off = align_up(off, 256);
   w.total = off;
   return w;
 }
@@ -442,26 +461,37 @@ extern "C" int bds_bin_sort(const bds_render_desc* d, int64_t n_isect, int32_t n
   SortWorkspace w = carve_sort(n_isect, n_tiles);
   uint64_t* keys = reinterpret_cast<uint64_t*>(ws + w.keys);
   int32_t* cursors = reinterpret_cast<int32_t*>(ws + w.cursors);
-  // sentinels: a position the emission never fills sorts last and gathers a null record
-  BDS_CHECK_CUDA(cudaMemsetAsync(keys, 0xff, (size_t)n_isect * 8, stream));
-  BDS_CHECK_CUDA(cudaMemsetAsync(cursors, 0, (size_t)(n_tiles + 1) * 4, stream));
   int32_t* big_list = reinterpret_cast<int32_t*>(ws + w.big_list);
-  BDS_CHECK_CUDA(cudaMemsetAsync(big_list, 0, 4, stream));
+  BDS_CHECK_CUDA(cudaMemsetAsync(cursors, 0, w.big_q + (size_t)(kBigQueueCap + 1) * 4 - w.cursors, stream));
   EmitParams ep;
   ep.d = *d; ep.tile_w = tile_w; ep.tile_h = tile_h; ep.radii = radii; ep.tile_offsets = tile_offsets;
   ep.cursors = cursors; ep.n_slots = n_slots; ep.splats = splats; ep.keys = keys;
+  ep.big_q = reinterpret_cast<int32_t*>(ws + w.big_q);
   emit_pairs_kernel<<<ceil_div(n_slots, 256), 256, 0, stream>>>(ep);
   BDS_CHECK_LAUNCH();
-  BDS_CHECK_CUDA(cudaFuncSetAttribute(tile_sort_gather_kernel<kTileSortCap, true>,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kTileSortCap * 8));
+  {
+    BigSplatParams b{};
+    b.d = *d; b.tile_w = tile_w; b.tile_h = tile_h; b.splats = splats; b.radii = radii;
+    b.n_queue = ep.big_q; b.queue = ep.big_q + 1; b.tile_offsets = tile_offsets; b.cursors = cursors; b.keys = keys;
+    big_splat_kernel<true><<<4 * 148, 256, 0, stream>>>(b);
+    BDS_CHECK_LAUNCH();
+  }
+  static bool attr_set[64] = {};   // per device; idempotent: two racing first calls set the same value twice
+  int dev = 0;
+  BDS_CHECK_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+    BDS_CHECK_CUDA(cudaFuncSetAttribute(tile_sort_gather_kernel<kTileSortCap, true>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kTileSortCap * 8));
+    if (dev >= 0 && dev < 64) attr_set[dev] = true;
+  }
   tile_sort_gather_kernel<kTileSortSmall, false><<<n_tiles, 256, 2 * kTileSortSmall * 8, stream>>>(
       tile_offsets, keys, reinterpret_cast<const float4*>(splats), reinterpret_cast<float4*>(sorted_splats),
-      sorted_slots, big_list);
+      sorted_slots, big_list, cursors);
   BDS_CHECK_LAUNCH();
   const int big_grid = n_tiles < 3 * 148 ? n_tiles : 3 * 148;   // 64 KB of shared memory: 3 CTAs per SM
   tile_sort_gather_kernel<kTileSortCap, true><<<big_grid, 256, 2 * kTileSortCap * 8, stream>>>(
       tile_offsets, keys, reinterpret_cast<const float4*>(splats), reinterpret_cast<float4*>(sorted_splats),
-      sorted_slots, big_list);
+      sorted_slots, big_list, cursors);
   BDS_CHECK_LAUNCH();
   return 0;
 }

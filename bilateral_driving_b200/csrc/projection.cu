@@ -5,7 +5,7 @@
 // One thread per (camera, Gaussian): 44-56 B read, <= 48 B written; HBM-bound pointwise work.
 // Replaces gsplat's fully_fused_projection_fwd/bwd + compute_sh_fwd/bwd for the reference call
 // sites models/trainers/base.py:393-408 and models/gaussians/vanilla.py:383-395.
-#include "projection_math.cuh"
+#include "big_splats.cuh"
 #include "sh_math.cuh"
 #include "tma.cuh"
 
@@ -222,8 +222,17 @@ __global__ void __launch_bounds__(kProjBlock) project_fwd_kernel(ProjParams p, i
       }
       // ---- exact tile count.  The candidates of the warp's splats form one flat list that the 32 lanes
       // test 32 at a time (splat footprints differ by orders of magnitude: per-lane loops would idle).
+      // A splat with more than kBigCand candidate tiles goes to the big-splat queue (big_splats.cuh) instead:
+      // its tiles are counted by a follow-up launch, one CTA per splat.
+      int qpos = -1;
+      bool deferred = false;
       {
-        const int ncand = cand ? (tr.x1 - tr.x0) * (tr.y1 - tr.y0) : 0;
+        int ncand = cand ? (tr.x1 - tr.x0) * (tr.y1 - tr.y0) : 0;
+        if (ncand > kBigCand && p.radii) {   // the follow-up launch rebuilds the candidate rectangle from radii
+          qpos = atomicAdd(p.counters + 2, 1);
+          deferred = qpos < kBigQueueCap;
+          if (deferred) ncand = 0;
+        }
         const int incl = warp_inclusive_scan_i32(ncand);
         const int total = __shfl_sync(0xffffffffu, incl, 31);
         const int excl = incl - ncand;
@@ -257,7 +266,7 @@ __global__ void __launch_bounds__(kProjBlock) project_fwd_kernel(ProjParams p, i
         __syncwarp();
       }
       // ---- packed record (SH colour only for splats that reach some tile)
-      const bool emit = n_tiles > 0;
+      const bool emit = n_tiles > 0 || deferred;   // a footprint that large reaches some tile
       float rec[12];
       if (emit) {
         rec[0] = mx; rec[1] = my; rec[2] = qa; rec[3] = qb; rec[4] = qc; rec[5] = op;
@@ -306,9 +315,10 @@ __global__ void __launch_bounds__(kProjBlock) project_fwd_kernel(ProjParams p, i
           }
         }
       }
+      if (deferred) p.counters[4 + qpos] = slot;   // -1 when the record was dropped
       if (active) {
         if (p.radii) p.radii[idx] = radius_i;
-        p.tiles_touched[idx] = n_tiles;
+        p.tiles_touched[idx] = n_tiles;             // deferred: 0 here, written by big_splat_kernel
         if (p.slot_of) p.slot_of[idx] = slot;
         if (slot >= 0) {
           float4* dst = reinterpret_cast<float4*>(p.splats + (size_t)slot * 12);
@@ -550,6 +560,13 @@ extern "C" int bds_project_fwd(const bds_render_desc* d, const float* means, con
   project_fwd_kernel<<<ceil_div(d->n_gauss, kProjBlock), kProjBlock, smem, static_cast<cudaStream_t>(stream)>>>(
       p, sh_floats, sh_bulk_ok);
   BDS_CHECK_LAUNCH();
+  if (radii) {  // tiles of the queued very large splats (a few microseconds when the queue is empty)
+    BigSplatParams b{};
+    b.d = *d; b.tile_w = p.tile_w; b.tile_h = p.tile_h; b.splats = splats; b.radii = radii;
+    b.n_queue = counters + 2; b.queue = counters + 4; b.tile_counts = tile_counts; b.tiles_touched = tiles_touched;
+    big_splat_kernel<false><<<4 * 148, 256, 0, static_cast<cudaStream_t>(stream)>>>(b);
+    BDS_CHECK_LAUNCH();
+  }
   return 0;
 }
 

@@ -25,7 +25,7 @@ from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
 
-from ._lib import (TILE, BdsError, BilateralDesc, EpilogueDesc, RenderDesc, check, lib, ptr, ptr_array,
+from ._lib import (COUNTERS_LEN, TILE, BdsError, BilateralDesc, EpilogueDesc, RenderDesc, check, lib, ptr, ptr_array,
                    require_cuda, stream_ptr)
 
 NULL = C.c_void_p(0)
@@ -153,7 +153,7 @@ class _RenderFn(torch.autograd.Function):
         comps = torch.zeros(Cn, N, **f32) if (cfg.antialiased and cfg.dense_info) else None
         tiles_touched = torch.empty(Cn, N, **i32)
         tile_counts = torch.empty(n_band_tiles + 1, **i32)
-        counters = torch.zeros(4, **i32)
+        counters = torch.zeros(COUNTERS_LEN, **i32)   # [0] records, [1] overflow flag, [2..] queue of very large splats
         cap = cfg.splat_capacity or max(Cn * N, 1)
         splats = torch.empty(cap, 12, **f32)
         st = stream_ptr()

@@ -25,6 +25,7 @@ extern "C" {
 
 #define BDS_ABI_VERSION 1
 #define BDS_MAX_LEVELS 4
+#define BDS_COUNTERS_LEN 4096  /* int32 entries of the projection counters buffer */
 #define BDS_TILE 16
 #define BDS_SPLAT_FLOATS 12 /* one packed splat record = 48 bytes */
 
@@ -125,8 +126,9 @@ typedef struct {
  * packed 48-byte records:
  *   splats [cap,12] = {x, y, a', b', c', opacity, r, g, b, depth, bits(flat id c*N+n), log2(opacity)}
  * with (a',b',c') = log2(e) * (a/2, b, c/2) of the conic (alpha = exp2(log2(opacity) - sigma'));
- * slot_of [C,N] int32 = record index or -1 (optional, may be NULL); counters[0] = number of records (device int32,
- * caller zero-fills counters[0..3]); counters[1] is set to 1 on capacity overflow.
+ * slot_of [C,N] int32 = record index or -1 (optional, may be NULL); counters = BDS_COUNTERS_LEN device int32,
+ * zero-filled by the caller: [0] = number of records, [1] is set to 1 on capacity overflow, [2] = length of the
+ * queue of very large splats (slots in [4..]) whose tiles are counted by a follow-up launch of the same call.
  * camera position for the SH view direction is taken from viewmats. */
 int bds_project_fwd(const bds_render_desc* d, const float* means, const float* quats,
                     const float* scales, const float* opacities, const float* colors /*[N,3] or [C,N,3] or NULL*/,
