@@ -8,7 +8,10 @@
 
 namespace bds {
 
-constexpr int kBigCand = 256;        // candidate tiles above which a splat leaves the warp-cooperative loop
+#ifndef BDS_BIG_CAND
+#define BDS_BIG_CAND 256
+#endif
+constexpr int kBigCand = BDS_BIG_CAND;        // candidate tiles above which a splat leaves the warp-cooperative loop
 constexpr int kBigQueueCap = BDS_COUNTERS_LEN - 4;   // queue entries; splats beyond it stay in the warp loop
 
 struct BigSplatParams {
