@@ -115,6 +115,17 @@ def band_pixel_rows(cfg: RenderCfg, Cn: int) -> Tuple[int, int]:
     return row_of(rb), (row_of(re) if re < Cn * th else Cn * cfg.height)
 
 
+_PINNED = {}
+
+
+def _pinned_sync_buffers(dev):
+    """Per-device pinned landing buffers of the step's one device -> host read."""
+    key = (dev.type, dev.index if dev.index is not None else torch.cuda.current_device())
+    if key not in _PINNED:
+        _PINNED[key] = (torch.zeros(1, dtype=torch.int64).pin_memory(), torch.zeros(2, dtype=torch.int32).pin_memory())
+    return _PINNED[key]
+
+
 class _RenderFn(torch.autograd.Function):
     """Inputs (tensors, may be None): means, quats, scales, opacities, colors, features_dc,
     features_rest, viewmats, Ks, backgrounds, sky, *grids (C * n_levels slots [12,L,GY,GX]).
@@ -167,9 +178,13 @@ class _RenderFn(torch.autograd.Function):
         tile_offsets = torch.empty(n_band_tiles + 1, **i32)
         ws0 = torch.empty(int(lib.bds_bin_count_workspace_bytes(C.byref(d))), device=dev, dtype=torch.uint8)
         check(lib.bds_bin_count(C.byref(d), ptr(tile_counts), ptr(tile_offsets), ptr(stats), ptr(ws0), st), "bds_bin_count")
-        # the one host sync of the step: intersection count (sizes the sort) + slot count / overflow flag
-        host = torch.cat([stats, counters[:2].to(torch.int64)]).tolist()
-        n_isect, n_slots, overflow = int(host[0]), int(host[1]), int(host[2])
+        # the one host sync of the step: intersection count (sizes the sort) + slot count / overflow flag, copied
+        # straight into pinned host memory (no staging kernels, no pageable bounce) and waited for on the stream
+        h_stats, h_counters = _pinned_sync_buffers(dev)
+        h_stats.copy_(stats, non_blocking=True)
+        h_counters.copy_(counters[:2], non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+        n_isect, n_slots, overflow = int(h_stats[0]), int(h_counters[0]), int(h_counters[1])
         if overflow:
             raise BdsError(f"splat capacity {cap} exceeded ({n_slots} visible splats); raise RenderCfg.splat_capacity")
         sorted_splats = torch.empty(max(n_isect, 1), 12, **f32)
