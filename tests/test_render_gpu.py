@@ -399,3 +399,36 @@ def test_very_large_splats_vs_oracle():
     for k in c_p:
         r = _rel(c_p[k].grad.cpu(), o_p[k].grad.float())
         assert r < 1e-3, (k, r)
+
+
+def test_big_splat_queue_overflow_and_oversized_tile_lists():
+    """4800+ visible full-image splats on a 17x16-tile image: more than the big-splat queue holds (the rest stay in
+    the warp-cooperative loop) and every tile list is longer than the shared-memory sort capacity (bitonic sort in
+    global memory).  Forward parity against the oracle."""
+    from bilateral_driving_b200 import synthetic as S
+    from bilateral_driving_b200.render import render_fused
+    from oracle.path_ref import render_path
+
+    n = 6000
+    p = S.make_gaussians(n, extent=10.0, scale_mean=0.12)
+    W, H = 272, 256
+    vm, Ks = S.make_rig(1, W, H)
+    g = torch.Generator().manual_seed(44)
+    p["_means"][:, 0] = 1.0 + 3.0 * torch.rand(n, generator=g)
+    p["_means"][:, 1] = (torch.rand(n, generator=g) - 0.5) * 1.5
+    p["_means"][:, 2] = 1.5 + (torch.rand(n, generator=g) - 0.5) * 1.0
+    p["_scales"][:] = torch.log(0.6 + 1.0 * torch.rand(n, 3, generator=g))
+    p["_opacities"][:] = -4.5 + torch.rand(n, generator=g)
+    with torch.no_grad():
+        o = render_path({k: v.double() for k, v in p.items()}, vm.double(), Ks.double(), W, H, sky=None, grid_slots=None,
+                        guidance_factor=None)
+        out = render_fused({k: v.cuda() for k, v in p.items()}, vm.cuda(), Ks.cuda(), W, H, sky=None, grid_slots=None,
+                           bil_sizes=(), sh_degree=3, near_plane=0.1)
+    n_vis = int((o["info"]["radii"][0] > 0).sum())
+    assert n_vis > 4096                                   # queue (4092 entries) and sort capacity (4096) both exceeded
+    offs = out["info"]["tile_offsets"].long()
+    assert int((offs[1:] - offs[:-1]).max()) > 4096
+    assert out["info"]["n_isect"] == int(out["info"]["tiles_touched"].sum())
+    keep = (~o["ambiguous"])[..., None].cuda()
+    for k in ("rgb_gaussians", "opacity"):
+        assert ((out[k].view(1, H, W, -1) - o[k].float().cuda()).abs() * keep).max() < 2e-5, k
