@@ -113,6 +113,10 @@ BDS_D f32x2 sub2(f32x2 a, f32x2 b) {
 
 // fire-and-forget fp32 reduction into global memory (RED.ADD.F32)
 BDS_D void red_add(float* p, float v) { atomicAdd(p, v); }
+// four consecutive floats, 16-byte aligned, in one reduction (RED.E.ADD.F32x4)
+BDS_D void red_add_v4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
 #endif  // __CUDACC__
 
 }  // namespace bds

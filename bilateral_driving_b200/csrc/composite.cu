@@ -326,9 +326,6 @@ struct BatchSmem {                     // per warp
   float4 vc[32];                       // per-pixel cotangent of the raw accumulators (C_r, C_g, C_b, D)
 };
 
-BDS_D void red_add_v4(float* p, float a, float b, float c, float d) {
-  asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
-}
 BDS_D float rcp_approx(float x) {
   float r;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));

@@ -342,6 +342,25 @@ struct ProjBwdParams {
   float *v_means, *v_quats, *v_scales, *v_opacities, *v_colors, *v_fdc, *v_frest, *v_viewmats, *v_means2d, *absgrad;
 };
 
+// Gradient row of the 15 higher SH coefficients of one Gaussian (45 floats, value j = b[1 + j/3] * vcol[j % 3]):
+// HEAD scalar reductions up to 16-byte alignment, then 128-bit vector reductions, then the scalar tail -
+// 13-14 requests instead of 45.
+template <int HEAD>
+BDS_D void sh_rest_red(float* fr, const float* b, const float* vcol) {
+#define BDS_SHV(j) (b[1 + (j) / 3] * vcol[(j) % 3])
+#pragma unroll
+  for (int j = 0; j < HEAD; ++j) red_add(fr + j, BDS_SHV(j));
+  constexpr int NV = (45 - HEAD) / 4;
+#pragma unroll
+  for (int q = 0; q < NV; ++q) {
+    const int j = HEAD + 4 * q;
+    red_add_v4(fr + j, BDS_SHV(j), BDS_SHV(j + 1), BDS_SHV(j + 2), BDS_SHV(j + 3));
+  }
+#pragma unroll
+  for (int j = HEAD + 4 * NV; j < 45; ++j) red_add(fr + j, BDS_SHV(j));
+#undef BDS_SHV
+}
+
 __global__ void __launch_bounds__(256) project_bwd_kernel(ProjBwdParams p) {
   int n_slots = p.counters[0];
   int slot = blockIdx.x * blockDim.x + threadIdx.x;
@@ -410,6 +429,14 @@ __global__ void __launch_bounds__(256) project_bwd_kernel(ProjBwdParams p) {
 #pragma unroll
         for (int ch = 0; ch < 3; ++ch) red_add(p.v_fdc + 3 * (size_t)n + ch, b[0] * vcol[ch]);
         float* fr = p.v_frest + (size_t)n * (p.d.sh_K - 1) * 3;
+        if (nb == 16 && p.d.sh_K == 16) {  // degree 3: the 45-float row leaves as 128-bit reductions
+          switch ((int)(((16u - (unsigned)((uintptr_t)fr & 15u)) & 15u) >> 2)) {
+            case 0: sh_rest_red<0>(fr, b, vcol); break;
+            case 1: sh_rest_red<1>(fr, b, vcol); break;
+            case 2: sh_rest_red<2>(fr, b, vcol); break;
+            default: sh_rest_red<3>(fr, b, vcol); break;
+          }
+        } else
         for (int k = 1; k < nb; ++k) {
 #pragma unroll
           for (int ch = 0; ch < 3; ++ch) red_add(fr + (k - 1) * 3 + ch, b[k] * vcol[ch]);
@@ -429,8 +456,12 @@ __global__ void __launch_bounds__(256) project_bwd_kernel(ProjBwdParams p) {
       red_add(p.v_means + 3 * (size_t)n + k, v_mu[k]);
       red_add(p.v_scales + 3 * (size_t)n + k, v_s[k]);
     }
+    if (((uintptr_t)p.v_quats & 15u) == 0) {
+      red_add_v4(p.v_quats + 4 * (size_t)n, v_q[0], v_q[1], v_q[2], v_q[3]);
+    } else {
 #pragma unroll
-    for (int k = 0; k < 4; ++k) red_add(p.v_quats + 4 * (size_t)n + k, v_q[k]);
+      for (int k = 0; k < 4; ++k) red_add(p.v_quats + 4 * (size_t)n + k, v_q[k]);
+    }
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
       vview[i * 4] = v_R[i * 3]; vview[i * 4 + 1] = v_R[i * 3 + 1]; vview[i * 4 + 2] = v_R[i * 3 + 2];
