@@ -867,6 +867,7 @@ extern "C" int bds_composite_bwd(const bds_render_desc* d, const bds_epilogue_de
   const int n_tiles = (d->row_end - d->row_begin) * p.tile_w;
   if (n_tiles == 0) return 0;
   BDS_REQUIRE(tile_offsets && out_alpha && last_ids && v_rgb && v_splats, "composite_bwd: null pointer");
+  BDS_REQUIRE(((uintptr_t)v_splats & 15u) == 0, "composite_bwd: v_splats must be 16-byte aligned (128-bit reductions)");
   if (e->mode != 0) BDS_REQUIRE(out_rgb_gauss && out_depth, "composite_bwd: modes 1/2 need rgb_gauss and depth");
   if (e->mode == 0 && e->channels == 4 && e->expected_depth)
     BDS_REQUIRE(out_depth, "composite_bwd: ED mode needs the normalised depth output (out_depth)");

@@ -194,7 +194,7 @@ int bds_composite_fwd_masked(const bds_render_desc* d, const bds_epilogue_desc* 
                              void* workspace, bds_stream_t stream);
 
 /* Backward of the above.  Cotangents: v_rgb [P,D or 3], v_rgb_gauss [P,3] (optional), v_depth [P]
- * (optional), v_alpha [P] (optional).  Outputs: v_splats [n_slots,12] ACCUMULATED (caller zeroes):
+ * (optional), v_alpha [P] (optional).  Outputs: v_splats [n_slots,12] ACCUMULATED (caller zeroes; 16-byte aligned):
  * {m_x, m_y, m_xx, m_xy, m_yy, m_0, v_r, v_g, v_b, v_depth, sum|w g_x|, sum|w g_y|} - the pixel moments of
  * w = alpha * v_alpha about the splat's mean (every 2-D gradient is linear in them; bds_project_bwd converts);
  * v_sky [P,3] optional (written); v_grids: host array like host_grids, ACCUMULATED;
