@@ -13,6 +13,7 @@ LIB_PATH = os.path.join(_HERE, os.environ.get("BDS_LIB", "libbds_b200.so"))
 MAX_LEVELS = 4
 TILE = 16
 COUNTERS_LEN = 4096  # BDS_COUNTERS_LEN (include/bds.h)
+ABI_VERSION = 2      # BDS_ABI_VERSION: 2 = moment-form gradient records, counters[BDS_COUNTERS_LEN], masked composite
 SPLAT_FLOATS = 12
 
 
@@ -67,6 +68,8 @@ def _load():
     lib = C.CDLL(LIB_PATH)
     lib.bds_last_error.restype = C.c_char_p
     lib.bds_abi_version.restype = C.c_int
+    if lib.bds_abi_version() != ABI_VERSION:
+        raise ImportError(f"{LIB_PATH} has ABI version {lib.bds_abi_version()}, this package needs {ABI_VERSION}: rebuild it")
     lib.bds_device_arch.restype = C.c_int
     if hasattr(lib, "bds_launch_count"):
         lib.bds_launch_count.restype = C.c_ulonglong

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define BDS_ABI_VERSION 1
+#define BDS_ABI_VERSION 2
 #define BDS_MAX_LEVELS 4
 #define BDS_COUNTERS_LEN 4096  /* int32 entries of the projection counters buffer */
 #define BDS_TILE 16
