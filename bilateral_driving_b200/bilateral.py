@@ -14,12 +14,11 @@ plus ``multiscale_bilateral(rgb, slots, sizes, factors)``: the fused slice + seq
 affine fields.  All arithmetic runs in ``libbds_b200.so``; there is no torch fallback.
 """
 import ctypes as C
-from typing import List, Optional, Sequence
+from typing import Sequence
 
 import torch
 from torch import nn
 
-from . import _lib
 from ._lib import BilateralDesc, check, lib, ptr, ptr_array, require_cuda, stream_ptr
 
 

@@ -6,7 +6,7 @@ the number of cameras, tile sharding otherwise (8 GPUs, 6 cameras).  Full-resolu
 no halo.  Every rank holds a full parameter replica; after the local backward ONE all-reduce (sum)
 over a flat fp32 buffer [Gaussian grads | grid grads] gives every rank the single-GPU gradient.
 """
-from typing import Iterable, List, Sequence, Tuple
+from typing import List, Sequence, Tuple
 
 import torch
 

@@ -18,9 +18,8 @@ Public entry points
 No torch/CPU fallback exists: every op raises if the tensors are not on a CUDA device.
 """
 import ctypes as C
-import math
 import weakref
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch

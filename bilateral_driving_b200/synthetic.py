@@ -6,7 +6,7 @@ device) and moved afterwards.  Parameter names mirror ``VanillaGaussians`` in th
 _features_dc [N,3], _features_rest [N,15,3]``.
 """
 import math
-from typing import Dict, List, Optional, Sequence
+from typing import Dict, List, Sequence
 
 import torch
 

@@ -1,6 +1,6 @@
 """Profiling aid: sub-warp hit statistics of the composite walk.  `make -C bilateral_driving_b200/csrc stats`
 builds libbds_b200_stats.so (-DBDS_STATS); this script selects it through BDS_LIB."""
-import ctypes as C, json, subprocess, sys, os
+import ctypes as C, json, sys, os
 os.environ.setdefault("BDS_LIB", "libbds_b200_stats.so")
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
