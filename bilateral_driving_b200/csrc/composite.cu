@@ -31,8 +31,15 @@
 
 namespace bds {
 
-constexpr int kChunk = 128;                 // records per stage
-constexpr int kStages = 3;
+constexpr int kChunk = 128;                 // backward: records per TMA stage
+#ifndef BDS_FWD_CHUNK
+#define BDS_FWD_CHUNK 128
+#endif
+#ifndef BDS_FWD_STAGES
+#define BDS_FWD_STAGES 3
+#endif
+constexpr int kFChunk = BDS_FWD_CHUNK;      // forward: records per TMA stage
+constexpr int kFStages = BDS_FWD_STAGES;    // forward: stages in flight
 constexpr int kRecBytes = 48;
 
 // ---- parameters ----------------------------------------------------------------------------------
@@ -115,25 +122,25 @@ __device__ unsigned long long g_stats[16];
 #endif
 template <int MODE>
 __global__ void __launch_bounds__(256, BDS_FWD_MINB) composite_fwd_kernel(CompParams p) {
-  __shared__ __align__(128) float4 srec[kStages][kChunk * 3];
-  __shared__ __align__(8) uint64_t bars[kStages];
+  __shared__ __align__(128) float4 srec[kFStages][kFChunk * 3];
+  __shared__ __align__(8) uint64_t bars[kFStages];
 
   const TileGeom g = tile_geom(p);
   const int lane = threadIdx.x & 31;
   const int n = g.end - g.start;
-  const int nchunks = (n + kChunk - 1) / kChunk;
+  const int nchunks = (n + kFChunk - 1) / kFChunk;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kStages; ++s) mbar_init(&bars[s], 1);
+    for (int s = 0; s < kFStages; ++s) mbar_init(&bars[s], 1);
     mbar_fence_init();
   }
   __syncthreads();
   int issued = 0;
   if (threadIdx.x == 0) {
-    for (; issued < nchunks && issued < kStages; ++issued) {
-      int cnt = min(kChunk, n - issued * kChunk);
+    for (; issued < nchunks && issued < kFStages; ++issued) {
+      int cnt = min(kFChunk, n - issued * kFChunk);
       mbar_expect_tx(&bars[issued], cnt * kRecBytes);
-      bulk_g2s(&srec[issued][0], p.recs + (size_t)(g.start + issued * kChunk) * 3, cnt * kRecBytes, &bars[issued]);
+      bulk_g2s(&srec[issued][0], p.recs + (size_t)(g.start + issued * kFChunk) * 3, cnt * kRecBytes, &bars[issued]);
     }
   }
 
@@ -155,16 +162,16 @@ __global__ void __launch_bounds__(256, BDS_FWD_MINB) composite_fwd_kernel(CompPa
 
   int waited = 0;
   for (int k = 0; k < nchunks; ++k) {
-    const int st = k % kStages;
-    mbar_wait(&bars[st], (k / kStages) & 1);
+    const int st = k % kFStages;
+    mbar_wait(&bars[st], (k / kFStages) & 1);
     waited = k + 1;
 #ifdef BDS_STATS
     int st_cA = 0, st_cB = 0, st_q0 = 0, st_q1 = 0, st_q2 = 0, st_q3 = 0;
 #endif
     if (!warp_done) {
-      const int cnt = min(kChunk, n - k * kChunk);
+      const int cnt = min(kFChunk, n - k * kFChunk);
       const float4* sr = &srec[st][0];
-      const int idx0 = g.start + k * kChunk;
+      const int idx0 = g.start + k * kFChunk;
       for (int base = 0; base < cnt && !warp_done; base += 32) {
         // lane j tests record base+j against the warp's 8x4 pixel rectangle
         int j = base + lane;
@@ -252,15 +259,15 @@ __global__ void __launch_bounds__(256, BDS_FWD_MINB) composite_fwd_kernel(CompPa
     int all_done = __syncthreads_and(warp_done ? 1 : 0);
     if (all_done) break;
     if (threadIdx.x == 0 && issued < nchunks) {
-      int cnt = min(kChunk, n - issued * kChunk);
+      int cnt = min(kFChunk, n - issued * kFChunk);
       mbar_expect_tx(&bars[st], cnt * kRecBytes);
-      bulk_g2s(&srec[st][0], p.recs + (size_t)(g.start + issued * kChunk) * 3, cnt * kRecBytes, &bars[st]);
+      bulk_g2s(&srec[st][0], p.recs + (size_t)(g.start + issued * kFChunk) * 3, cnt * kRecBytes, &bars[st]);
       ++issued;
     }
   }
   // never leave with a bulk copy still in flight into this CTA's shared memory
   if (threadIdx.x == 0) {
-    for (int k = waited; k < issued; ++k) mbar_wait(&bars[k % kStages], (k / kStages) & 1);
+    for (int k = waited; k < issued; ++k) mbar_wait(&bars[k % kFStages], (k / kFStages) & 1);
   }
 
   if (!g.inside) return;
