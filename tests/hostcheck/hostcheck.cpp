@@ -68,6 +68,11 @@ void hc_lin_src(int d, int in_size, int out_size, int* i0, int* i1, float* t) {
   *i0 = tp.i0; *i1 = tp.i1; *t = tp.t;
 }
 float hc_lattice_coord(int j, int n, int g) { return lattice_coord(j, n, g); }
+float hc_unit_lin01(int j, int n, int g) { return unit_coord(lin01(j, n), g); }  // the hoisted form the kernels use
+// value repack [GY][GX][3][L][4]: element -> parameter-layout index, and (node, z, row) -> float offset
+long hc_value_param_index(int i, int L, int GY, int GX) { return (long)bil_value_param_index(i, L, GY, GX); }
+int hc_value_offset(int node, int z, int k, int L) { return bil_value_offset(node, z, k, L); }
+int hc_node(int x, int y, int z, int L, int GX) { return bil_node(x, y, z, L, GX); }
 
 // tri set-up: returns nodes[8] and weights[8] of the trilinear stencil, and z_inside
 int hc_tri(float fx, float fy, float fz, int L, int GY, int GX, int* nodes, float* w) {

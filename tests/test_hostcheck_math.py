@@ -174,6 +174,26 @@ def test_resize_taps_and_trilinear_stencil(hc):
         assert inside == int(0 < fz < 3)
 
 
+def test_value_repack_index_maps(hc):
+    """The quad-major value repack [GY][GX][3][L][4]: the repack kernels' element -> parameter index map is a
+    bijection onto [12][L][GY][GX], the slice's (node, slab, affine row) offset addresses the same element, and
+    the hoisted lattice coordinate equals the reference form bit for bit."""
+    hc.hc_value_param_index.restype = C.c_long
+    hc.hc_unit_lin01.restype = C.c_float
+    for (L, GY, GX) in ((4, 8, 8), (8, 16, 16), (3, 5, 6), (1, 2, 2)):
+        n = 12 * L * GY * GX
+        seen = np.zeros(n, dtype=np.int32)
+        for i in range(n):
+            seen[hc.hc_value_param_index(i, L, GY, GX)] += 1
+        assert (seen == 1).all()
+        for (x, y, z, ch) in ((0, 0, 0, 0), (GX - 1, GY - 1, L - 1, 11), (GX // 2, GY // 3, L // 2, 6), (1, 0, 0, 5)):
+            node = hc.hc_node(x, y, z, L, GX)
+            off = hc.hc_value_offset(node, z, ch // 4, L) + ch % 4
+            assert hc.hc_value_param_index(off, L, GY, GX) == ((ch * L + z) * GY + y) * GX + x
+    for (j, n_, g) in ((0, 1920, 32), (5, 11, 8), (1919, 1920, 8), (540, 1080, 16), (7, 8, 2)):
+        assert hc.hc_unit_lin01(j, n_, g) == hc.hc_lattice_coord(j, n_, g)
+
+
 def test_candidate_rect_contains_every_hit_tile(hc):
     """The ellipse-bbox pruning of the tile enumeration never drops a tile the exact test accepts."""
     rng = np.random.default_rng(1)
