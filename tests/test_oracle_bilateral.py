@@ -103,3 +103,37 @@ def test_fp64_against_live_reference():
             assert (ref - ours).abs().max() < 1e-12
     finally:
         torch.set_default_dtype(torch.float32)
+
+
+def test_module_mirror_keeps_the_reference_checkpoint_contract():
+    """State-dict keys / shapes / dtypes and optimiser group names of the host mirror equal the UNMODIFIED
+    reference modules (models/modules.py:275-351, 422-593): released checkpoints load with strict=True
+    (models/trainers/base.py:737) and the YAML optimiser entries `Affine#grid{i}` keep matching (base.py:182-188)."""
+    from oracle.ref_loader import load_reference, reference_available
+
+    if not reference_available():
+        pytest.skip("reference tree not present")
+    from bilateral_driving_b200 import bilateral as ours
+
+    _, mods = load_reference()
+    sizes = [[2, 2, 1], [4, 4, 2], [8, 8, 4]]   # configs/omnire_ms_bilateral.yaml:249
+    ref = mods.MultiScaleBilateralAffineTransform("Affine", n=5, grid=sizes, device="cpu")
+    mine = ours.MultiScaleBilateralAffineTransform("Affine", n=5, grid=sizes, device="cpu")
+    sd_ref, sd_mine = ref.state_dict(), mine.state_dict()
+    assert list(sd_ref.keys()) == list(sd_mine.keys())
+    for k in sd_ref:
+        assert sd_ref[k].shape == sd_mine[k].shape and sd_ref[k].dtype == sd_mine[k].dtype, k
+        assert torch.equal(sd_ref[k], sd_mine[k]), k          # identity initialisation, luma weights
+    mine.load_state_dict(sd_ref, strict=True)
+    g_ref, g_mine = ref.get_param_groups(), mine.get_param_groups()
+    assert list(g_ref.keys()) == list(g_mine.keys())
+    for k in g_ref:
+        assert [tuple(p.shape) for p in g_ref[k]] == [tuple(p.shape) for p in g_mine[k]]
+    assert [float(w) for w in ref.tv_weight] == [float(w) for w in mine.tv_weight]
+    # single-scale module (models/modules.py:275-351)
+    r1 = mods.BilateralAffineTransform("Affine", n=3, grid_X=16, grid_Y=16, grid_W=8, device="cpu")
+    m1 = ours.BilateralAffineTransform("Affine", n=3, grid_X=16, grid_Y=16, grid_W=8, device="cpu")
+    assert list(r1.state_dict().keys()) == list(m1.state_dict().keys())
+    for k, v in r1.state_dict().items():
+        assert v.shape == m1.state_dict()[k].shape, k
+    assert list(r1.get_param_groups().keys()) == list(m1.get_param_groups().keys())
