@@ -183,10 +183,18 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"bilateral fwd+bwd, 1 cam {W}x{H}, 3-scale grids 8/16/32, CPU torch {torch.__version__}"},
+        # same workload name as the GPU arm; what a step of THIS arm covers is the bounded sample below
+        "config": {"workload": _workload_name(args.n_gauss, args.cams, W, H, args.guidance),
+                   "sample": f"bilateral fwd+bwd of ONE {W}x{H} camera image per step (the rasteriser half of the path is "
+                             f"gsplat CUDA in the reference: no CPU implementation exists), CPU torch {torch.__version__}"},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     })
+
+
+def _workload_name(n_gauss, cams, W, H, guidance):
+    return (f"configs[2]: {n_gauss} synthetic Gaussians, {cams}-cam nuScenes-shaped rig {W}x{H}, 3-scale grids 8/16/32 "
+            f"{'full-res guidance (fused)' if guidance == 'full' else 'guidance_factor=[4,4,2] (two-phase)'}, SH degree 3")
 
 
 _JSON_OUT = None
@@ -372,8 +380,7 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"configs[2]: {N} synthetic Gaussians, {Cn}-cam nuScenes-shaped rig {W}x{H}, "
-                               f"3-scale grids 8/16/32 {'full-res guidance (fused)' if args.guidance == 'full' else 'guidance_factor=[4,4,2] (two-phase)'}, SH degree 3",
+        "config": {"workload": _workload_name(N, Cn, W, H, args.guidance),
                    "parallelism": f"tile-row bands x{world}", "n_isect_rank0": I, "n_visible_rank0": Nv,
                    "l2": "inputs larger than L2 (472 MB of parameters + images per step)",
                    "composite_fwd_ms": t_fwd, "composite_bwd_ms": t_bwd},
