@@ -117,9 +117,50 @@ def ptr_array(tensors):
 
 
 def stream_ptr():
+    """Current torch stream of the current device.  The C ABI launches on the CURRENT device, so every op runs under
+    ``device_scoped`` (current device = the device of its tensors)."""
     import torch
 
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _first_cuda_device(objs):
+    import torch
+
+    for o in objs:
+        if torch.is_tensor(o):
+            if o.is_cuda:
+                return o.device
+        elif isinstance(o, (list, tuple)):
+            d = _first_cuda_device(o)
+            if d is not None:
+                return d
+    return None
+
+
+def device_scoped(fn):
+    """Decorator for the forward / backward of an autograd Function: run it with the device of its (first CUDA)
+    tensor argument as the current device, so that kernels, memsets, function attributes, the stream taken by
+    ``stream_ptr()`` and torch's own allocations all belong to the device the tensors live on (a model on cuda:1
+    without torch.cuda.set_device would otherwise launch on cuda:0)."""
+    import functools
+
+    @functools.wraps(fn)
+    def scoped(ctx, *args):
+        import torch
+
+        dev = _first_cuda_device(args)
+        if dev is None:
+            try:
+                dev = _first_cuda_device(ctx.saved_tensors)
+            except Exception:
+                dev = None
+        if dev is None:   # CPU tensors: the op itself raises BdsError (no CPU fallback)
+            return fn(ctx, *args)
+        with torch.cuda.device(dev):
+            return fn(ctx, *args)
+
+    return scoped
 
 
 def require_cuda(*tensors):

@@ -19,7 +19,7 @@ from typing import Sequence
 import torch
 from torch import nn
 
-from ._lib import BilateralDesc, check, lib, ptr, ptr_array, require_cuda, stream_ptr
+from ._lib import BilateralDesc, check, device_scoped, lib, ptr, ptr_array, require_cuda, stream_ptr
 
 
 def _workspace(desc, H, W, device):
@@ -31,8 +31,10 @@ class _MSBilateralFn(torch.autograd.Function):
     """rgb [H,W,3] + per-level grid slots [12,L,GY,GX] -> rgb_out [H,W,3] (+ affine fields)."""
 
     @staticmethod
+    @device_scoped
     def forward(ctx, rgb, sizes, factors, want_affine, *slots):
         require_cuda(rgb, *slots)
+        ctx.set_materialize_grads(False)   # unused affine-field outputs hand None to backward (100 MB per level at 1080p)
         if rgb.dim() != 3 or rgb.shape[-1] != 3:
             raise ValueError(f"rgb must be [H,W,3], got {tuple(rgb.shape)}")
         H, W, _ = rgb.shape
@@ -57,6 +59,7 @@ class _MSBilateralFn(torch.autograd.Function):
         return out
 
     @staticmethod
+    @device_scoped
     def backward(ctx, v_out, *v_affines):
         rgb_c, *slots_c = ctx.saved_tensors
         H, W, _ = rgb_c.shape
@@ -90,6 +93,7 @@ class _SliceFn(torch.autograd.Function):
     """Generic per-sample slice: xy [n,2], rgb [n,3], grid [12,L,GY,GX] -> affine [n,12]."""
 
     @staticmethod
+    @device_scoped
     def forward(ctx, grid, xy, rgb):
         require_cuda(grid, xy, rgb)
         grid_c, xy_c, rgb_c = grid.contiguous().float(), xy.contiguous().float(), rgb.contiguous().float()
@@ -102,6 +106,7 @@ class _SliceFn(torch.autograd.Function):
         return out
 
     @staticmethod
+    @device_scoped
     def backward(ctx, v_aff):
         grid_c, xy_c, rgb_c = ctx.saved_tensors
         _, L, GY, GX = grid_c.shape
@@ -116,6 +121,7 @@ class _SliceFn(torch.autograd.Function):
 
 class _TVFn(torch.autograd.Function):
     @staticmethod
+    @device_scoped
     def forward(ctx, grids, weight):
         require_cuda(grids)
         g = grids.contiguous().float()
@@ -128,6 +134,7 @@ class _TVFn(torch.autograd.Function):
         return loss
 
     @staticmethod
+    @device_scoped
     def backward(ctx, v_loss):
         (g,) = ctx.saved_tensors
         N, _, L, GY, GX = g.shape
@@ -222,10 +229,47 @@ def slice(bil_grids, xy, rgb, grid_idx):  # noqa: A001 - name mirrors the refere
 
 
 def _cam_index(image_infos) -> int:
+    """Host-side image index (modules.py:507 does ``int(image_infos["img_idx"][0][0])``: a device->host sync)."""
     assert "img_idx" in image_infos
-    if "img_idx_host" in image_infos:  # optional: avoids the device->host sync of modules.py:507
+    if "img_idx_host" in image_infos:  # optional: a caller that knows the index on the host avoids the sync
         return int(image_infos["img_idx_host"])
     return int(image_infos["img_idx"][0][0])
+
+
+def _train_slot(grids, image_infos):
+    """``grids[img_idx]`` of the training branch WITHOUT the device->host sync of modules.py:507: the slot is
+    selected on the device from the index tensor itself.  Same values and the same dense, one-hot-row gradient as
+    the reference's advanced indexing (lib_bilagrid.py:346-348)."""
+    if "img_idx_host" in image_infos:
+        return grids[int(image_infos["img_idx_host"])]
+    idx = image_infos["img_idx"]
+    if not torch.is_tensor(idx):
+        return grids[int(idx)]
+    return grids.index_select(0, idx.reshape(-1)[:1].to(device=grids.device, dtype=torch.long))[0]
+
+
+def chain_inverse_apply(affines, x):
+    """Closed form of what modules.py:474-492 gets from a batched 4x4 ``torch.inverse``: the per-pixel chain
+    ``x -> A_n(...A_1(A_0 x))`` of 3x4 affines is itself a 3x4 affine [R | t] (R = R_n...R_0); its inverse maps
+    ``y -> R^-1 (y - t)`` with R^-1 = adj(R) / det(R).  ``affines``: list of [..., 3, 4]; ``x``: [..., 3]."""
+    R = affines[0][..., :3, :3]
+    t = affines[0][..., :3, 3]
+    for A in affines[1:]:
+        Rl = A[..., :3, :3]
+        t = (Rl @ t[..., None])[..., 0] + A[..., :3, 3]
+        R = Rl @ R
+    a, b, c = R[..., 0, 0], R[..., 0, 1], R[..., 0, 2]
+    d, e, f = R[..., 1, 0], R[..., 1, 1], R[..., 1, 2]
+    g, h, i = R[..., 2, 0], R[..., 2, 1], R[..., 2, 2]
+    c00, c01, c02 = e * i - f * h, c * h - b * i, b * f - c * e
+    c10, c11, c12 = f * g - d * i, a * i - c * g, c * d - a * f
+    c20, c21, c22 = d * h - e * g, b * g - a * h, a * e - b * d
+    det = a * c00 + b * c10 + c * c20
+    y = x - t
+    y0, y1, y2 = y[..., 0], y[..., 1], y[..., 2]
+    out = torch.stack([c00 * y0 + c01 * y1 + c02 * y2, c10 * y0 + c11 * y1 + c12 * y2,
+                       c20 * y0 + c21 * y1 + c22 * y2], dim=-1)
+    return out / det[..., None]
 
 
 class BilateralAffineTransform(nn.Module):
@@ -242,20 +286,22 @@ class BilateralAffineTransform(nn.Module):
     def tv_loss(self):
         return total_variation_loss(self.bil_grids.grids)
 
-    def _slots(self, cam_idx):
+    def _slots(self, image_infos):
         if not self.in_test_set:
-            return [self.bil_grids.grids[cam_idx]]
-        near = self.training_indices_for_test[cam_idx]
+            return [_train_slot(self.bil_grids.grids, image_infos)]
+        near = self.training_indices_for_test[_cam_index(image_infos)]
         return [torch.stack([self.bil_grids.grids[i] for i in near]).mean(0)]
 
+    def level_sizes(self):
+        return [self.bil_grids.size_xyl]
+
     def forward(self, rgb, image_infos):
-        cam_idx = _cam_index(image_infos)
-        _, aff = multiscale_bilateral(rgb, self._slots(cam_idx), [self.bil_grids.size_xyl], None, True)
+        _, aff = multiscale_bilateral(rgb, self._slots(image_infos), self.level_sizes(), None, True)
         return aff[0]
 
     def transform(self, rgb, image_infos):
         """Fused forward + apply of scene_graph.py:95-98."""
-        return multiscale_bilateral(rgb, self._slots(_cam_index(image_infos)), [self.bil_grids.size_xyl], None)
+        return multiscale_bilateral(rgb, self._slots(image_infos), self.level_sizes(), None)
 
     def get_param_groups(self):
         return {self.class_prefix + "all": self.bil_grids.parameters()}
@@ -287,6 +333,7 @@ class MultiScaleBilateralAffineTransform(nn.Module):
         self.device = device
         self.in_test_set = False
         self.save_matrix = None
+        self._cycle_ctx = None
 
     def _levels(self):
         return [getattr(self, f"bil_grids{i}") for i in range(len(self.grid_size))]
@@ -298,35 +345,49 @@ class MultiScaleBilateralAffineTransform(nn.Module):
         return loss
 
     def _slots(self, image_infos):
-        cam_idx = _cam_index(image_infos)
-        if "img_idx" in image_infos and not self.in_test_set:
-            return [bg.grids[cam_idx] for bg in self._levels()]
-        near = self.training_indices_for_test[cam_idx]
+        assert "img_idx" in image_infos
+        if not self.in_test_set:
+            return [_train_slot(bg.grids, image_infos) for bg in self._levels()]
+        near = self.training_indices_for_test[_cam_index(image_infos)]
         # the mean over neighbour slices equals the slice of the mean grid (slicing is linear in the
         # grid values at fixed coordinates): modules.py:523-538
         return [torch.stack([bg.grids[i] for i in near]).mean(0) for bg in self._levels()]
 
+    def level_sizes(self):
+        return [bg.size_xyl for bg in self._levels()]
+
     def forward(self, rgb, image_infos, guidance_factor=[4, 4, 2]):  # noqa: B006 - reference signature
-        sizes = [bg.size_xyl for bg in self._levels()]
-        _, out_list = multiscale_bilateral(rgb, self._slots(image_infos), sizes, guidance_factor, True)
+        _, out_list = multiscale_bilateral(rgb, self._slots(image_infos), self.level_sizes(), guidance_factor, True)
         self.save_matrix = out_list
+        self._cycle_ctx = None
         return out_list
 
     def transform(self, rgb, image_infos, guidance_factor=[4, 4, 2]):  # noqa: B006
-        sizes = [bg.size_xyl for bg in self._levels()]
-        return multiscale_bilateral(rgb, self._slots(image_infos), sizes, guidance_factor)
+        """Fused slice + sequential apply (scene_graph.py:112-117): no affine fields are materialised.  What
+        ``inverse_loss`` would need of them is remembered as (rgb, slots, guidance_factor) and only evaluated if
+        the cycle loss is actually asked for."""
+        slots = self._slots(image_infos)
+        self.remember_for_inverse_loss(rgb, slots, guidance_factor)
+        return multiscale_bilateral(rgb, slots, self.level_sizes(), guidance_factor)
+
+    def remember_for_inverse_loss(self, rgb, slots, guidance_factor):
+        self.save_matrix = None
+        self._cycle_ctx = (rgb, list(slots), guidance_factor)
+
+    def _affine_fields(self):
+        if self.save_matrix is not None:
+            return self.save_matrix
+        if getattr(self, "_cycle_ctx", None) is None:
+            raise RuntimeError("inverse_loss called before forward/transform (modules.py:474 reads save_matrix)")
+        rgb, slots, gf = self._cycle_ctx
+        _, fields = multiscale_bilateral(rgb, slots, self.level_sizes(), gf, True)
+        return fields
 
     def inverse_loss(self, gt, render):
-        """modules.py:474-492 (cycle loss on the saved affine fields)."""
-        shape = self.save_matrix[0].shape
-        B, H, W, _, _ = shape
-        mat = torch.eye(4, device=gt.device).view(1, 1, 1, 4, 4).repeat(1, H, W, 1, 1)
-        for arr in self.save_matrix:
-            mat = affine_to_homogeneous_batch(arr) @ mat
-        inverses = torch.inverse(mat.view(-1, 4, 4)).view(B, H, W, 4, 4)
-        inverse_affine = inverses[:, :, :, :3, :].reshape(gt.shape[0], gt.shape[1], 3, 4)
-        gt_t = (inverse_affine[..., :3, :3] @ gt[..., None] + inverse_affine[..., :3, 3:])[..., 0]
-        return torch.abs(gt_t - render).mean()
+        """modules.py:474-492: mean |chain^-1(gt) - render| - the per-pixel 4x4 ``torch.inverse`` of the reference
+        replaced by the closed-form inverse of the composed 3x4 chain (``chain_inverse_apply``)."""
+        fields = [a.reshape(gt.shape[0], gt.shape[1], 3, 4) for a in self._affine_fields()]
+        return torch.abs(chain_inverse_apply(fields, gt) - render).mean()
 
     def get_param_groups(self):
         return {f"{self.class_prefix}grid{i}": bg.parameters() for i, bg in enumerate(self._levels())}

@@ -31,11 +31,12 @@ void set_error(const char* fmt, ...);
     }                                 \
   } while (0)
 
-extern unsigned long long g_launches;  // kernels launched by this library (statistics only)
+extern unsigned long long g_launches;  // kernels launched by this library (statistics only; relaxed atomic:
+                                       // the entry points are re-entrant across host threads / streams)
 }  // namespace bds
 #define BDS_CHECK_LAUNCH()      \
   do {                          \
-    ++bds::g_launches;          \
+    __atomic_fetch_add(&bds::g_launches, 1ull, __ATOMIC_RELAXED); \
     BDS_CHECK_CUDA(cudaGetLastError()); \
   } while (0)
 namespace bds {

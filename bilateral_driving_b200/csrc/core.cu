@@ -23,4 +23,4 @@ extern "C" int bds_device_arch(void) {
   BDS_CHECK_CUDA(cudaGetDeviceProperties(&prop, dev));
   return prop.major * 10 + prop.minor;
 }
-extern "C" unsigned long long bds_launch_count(void) { return bds::g_launches; }
+extern "C" unsigned long long bds_launch_count(void) { return __atomic_load_n(&bds::g_launches, __ATOMIC_RELAXED); }

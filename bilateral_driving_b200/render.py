@@ -24,8 +24,8 @@ from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
 
-from ._lib import (COUNTERS_LEN, TILE, BdsError, BilateralDesc, EpilogueDesc, RenderDesc, check, lib, ptr, ptr_array,
-                   require_cuda, stream_ptr)
+from ._lib import (COUNTERS_LEN, TILE, BdsError, BilateralDesc, EpilogueDesc, RenderDesc, check, device_scoped, lib, ptr,
+                   ptr_array, require_cuda, stream_ptr)
 
 NULL = C.c_void_p(0)
 
@@ -131,10 +131,14 @@ class _RenderFn(torch.autograd.Function):
     Outputs: out_rgb, out_rgb_gauss, out_depth, out_alpha, means2d (dense or empty), radii."""
 
     @staticmethod
+    @device_scoped
     def forward(ctx, cfg: RenderCfg, holder: dict, means, quats, scales, opacities, colors, fdc, frest, viewmats,
                 Ks, backgrounds, sky, *grids):
         require_cuda(means, quats, scales, opacities, colors, fdc, frest, viewmats, Ks, backgrounds, sky, *grids)
         dev = means.device
+        # unused outputs hand None (not a zero tensor) to backward: v_rgb_gauss / v_depth / v_alpha / the [C,N,2]
+        # means2d cotangent are optional in the C ABI
+        ctx.set_materialize_grads(False)
         f32 = dict(device=dev, dtype=torch.float32)
         i32 = dict(device=dev, dtype=torch.int32)
         cont = lambda t: None if t is None else t.contiguous().float()  # noqa: E731
@@ -222,6 +226,7 @@ class _RenderFn(torch.autograd.Function):
                 out_depth if out_depth is not None else torch.empty(0, **f32), out_alpha, m2d, radii)
 
     @staticmethod
+    @device_scoped
     def backward(ctx, v_rgb, v_rgbg, v_depth, v_alpha, v_means2d_extra, _v_radii):
         cfg, d, e = ctx.cfg, ctx.d, ctx.e
         (means, quats, scales, opacities, colors, fdc, frest, viewmats, Ks, backgrounds, sky, splats, counters,
@@ -395,32 +400,42 @@ def rasterize_masked(info, gaussian_mask):
     [C,H,W,1])`` like ``rasterization``.
     """
     c = info["_bds_cache"] if isinstance(info, dict) and "_bds_cache" in info else info
-    cfg, d, e = c["cfg"], c["d"], c["e"]
-    if cfg.mode != 0:
-        raise NotImplementedError("rasterize_masked re-renders gsplat-shaped outputs (mode 0)")
+    cfg, d = c["cfg"], c["d"]
     if not gaussian_mask.is_cuda:
         raise BdsError("bds operators run on CUDA tensors only (no CPU fallback exists)")
     N, Cn, P = c["N"], c["Cn"], c["P"]
     if gaussian_mask.numel() != N:
         raise ValueError(f"gaussian_mask has {gaussian_mask.numel()} entries for {N} Gaussians")
+    # the sorted lists do not depend on the epilogue of the render that produced them: a cache of a fused
+    # (mode 1 / 2) render is re-composited with the plain gsplat epilogue the reference's render_fn returns
+    if cfg.mode == 0:
+        e, channels, bg = c["e"], cfg.channels, c["backgrounds"]
+    else:
+        e, channels, bg = EpilogueDesc(), 4, None
+        e.mode, e.channels, e.expected_depth = 0, 4, 1
     dev = gaussian_mask.device
-    keep = (gaussian_mask.reshape(-1) != 0).to(torch.uint8).contiguous()
-    slot_keep = torch.empty(max(c["n_slots"], 1), device=dev, dtype=torch.uint8)
-    st = stream_ptr()
-    check(lib.bds_slot_keep(C.byref(d), ptr(c["splats"]), ptr(c["counters"]), C.c_int32(c["n_slots"]), ptr(keep),
-                            ptr(slot_keep), st), "bds_slot_keep")
-    f32 = dict(device=dev, dtype=torch.float32)
-    out_rgb = torch.empty(P, cfg.channels, **f32)
-    out_alpha = torch.empty(P, **f32)
-    last_ids = torch.empty(P, device=dev, dtype=torch.int32)
-    check(lib.bds_composite_fwd_masked(C.byref(d), C.byref(e), ptr(c["sorted_splats"]), ptr(c["tile_offsets"]),
-                                       ptr(slot_keep), ptr(c["backgrounds"]), NULL, NULL, ptr(out_rgb), NULL, NULL,
-                                       ptr(out_alpha), ptr(last_ids), NULL, st), "bds_composite_fwd_masked")
-    return out_rgb.view(Cn, cfg.height, cfg.width, cfg.channels), out_alpha.view(Cn, cfg.height, cfg.width, 1)
+    with torch.cuda.device(dev):
+        keep = (gaussian_mask.reshape(-1) != 0).to(torch.uint8).contiguous()
+        slot_keep = torch.empty(max(c["n_slots"], 1), device=dev, dtype=torch.uint8)
+        st = stream_ptr()
+        check(lib.bds_slot_keep(C.byref(d), ptr(c["splats"]), ptr(c["counters"]), C.c_int32(c["n_slots"]), ptr(keep),
+                                ptr(slot_keep), st), "bds_slot_keep")
+        f32 = dict(device=dev, dtype=torch.float32)
+        out_rgb = torch.empty(P, channels, **f32)
+        out_alpha = torch.empty(P, **f32)
+        last_ids = torch.empty(P, device=dev, dtype=torch.int32)
+        check(lib.bds_composite_fwd_masked(C.byref(d), C.byref(e), ptr(c["sorted_splats"]), ptr(c["tile_offsets"]),
+                                           ptr(slot_keep), ptr(bg), NULL, NULL, ptr(out_rgb), NULL, NULL,
+                                           ptr(out_alpha), ptr(last_ids), NULL, st), "bds_composite_fwd_masked")
+    rows = P // cfg.width
+    if rows == Cn * cfg.height:
+        return out_rgb.view(Cn, cfg.height, cfg.width, channels), out_alpha.view(Cn, cfg.height, cfg.width, 1)
+    return out_rgb.view(rows, cfg.width, channels), out_alpha.view(rows, cfg.width, 1)   # a band of stacked pixel rows
 
 
 class _SHFn(torch.autograd.Function):
     @staticmethod
+    @device_scoped
     def forward(ctx, degree, dirs, coeffs):
         require_cuda(dirs, coeffs)
         d2 = dirs.reshape(-1, 3).contiguous().float()
@@ -433,6 +448,7 @@ class _SHFn(torch.autograd.Function):
         return out.view(*dirs.shape[:-1], 3)
 
     @staticmethod
+    @device_scoped
     def backward(ctx, v_out):
         d2, c2 = ctx.saved_tensors
         K = c2.shape[1]
@@ -446,6 +462,8 @@ class _SHFn(torch.autograd.Function):
 
 def spherical_harmonics(degrees_to_use: int, dirs, coeffs, masks=None):
     """gsplat.cuda._wrapper.spherical_harmonics: dirs [...,3], coeffs [...,K,3] -> [...,3]."""
+    if not 0 <= degrees_to_use <= 3:
+        raise NotImplementedError(f"SH degree {degrees_to_use}: bands 0..3 are built")
     assert (degrees_to_use + 1) ** 2 <= coeffs.shape[-2], coeffs.shape
     assert dirs.shape[:-1] == coeffs.shape[:-2], (dirs.shape, coeffs.shape)
     assert dirs.shape[-1] == 3 and coeffs.shape[-1] == 3
@@ -456,9 +474,10 @@ def spherical_harmonics(degrees_to_use: int, dirs, coeffs, masks=None):
 
 
 def num_sh_bases(degree: int) -> int:
-    """gsplat.cuda_legacy._wrapper.num_sh_bases."""
-    if degree > 4:
-        raise ValueError("degree <= 4")
+    """gsplat.cuda_legacy._wrapper.num_sh_bases.  The kernels evaluate bands 0..3 (the reference's ``sh_degree: 3``,
+    configs/omnire_ms_bilateral.yaml:69); degree 4, which gsplat would accept, is refused here as everywhere else."""
+    if not 0 <= degree <= 3:
+        raise NotImplementedError(f"SH degree {degree}: bands 0..3 are built (reference config sh_degree: 3)")
     return (degree + 1) ** 2
 
 
@@ -532,6 +551,7 @@ class _PhotoLossFn(torch.autograd.Function):
     writes the cotangents (the benchmark step's loss)."""
 
     @staticmethod
+    @device_scoped
     def forward(ctx, rgb, gt, depth, alpha, lambda_d, lambda_a, count, unit_cotangent):
         require_cuda(rgb, gt, depth, alpha)
         rgb_c, gt_c = rgb.contiguous(), gt.contiguous()

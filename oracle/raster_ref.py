@@ -124,9 +124,12 @@ def depth_order(depths):
 
 
 def composite(means2d, conics, opacities, colors, depths, radii, width, height, background=None,
-              margin=1e-5, row_range=None):
+              margin=1e-5, row_range=None, abs_acc=None):
     """One camera.  colors [N,D].  Returns render [H,W,D], alpha [H,W], ambiguous [H,W] bool,
-    n_isect (int).  ``row_range`` = (tile_row_begin, tile_row_end) restricts the tiles rendered."""
+    n_isect (int).  ``row_range`` = (tile_row_begin, tile_row_end) restricts the tiles rendered.
+    ``abs_acc`` [N,2]: filled DURING backward with gsplat's ``absgrad`` = sum over pixels of |per-pixel
+    contribution to v_means2d|, which plain autograd (a signed sum) cannot give: the
+    per-(pixel, Gaussian) cotangent of the expanded means is caught by a tensor hook before it is reduced."""
     dt = means2d.dtype
     D = colors.shape[-1]
     tw = (width + TILE - 1) // TILE
@@ -158,8 +161,14 @@ def composite(means2d, conics, opacities, colors, depths, radii, width, height, 
                 mu = means2d[ids]
                 con = conics[ids]
                 op = opacities[ids]
-                dx = mu[None, :, 0] - px.reshape(-1, 1)
-                dy = mu[None, :, 1] - py.reshape(-1, 1)
+                mu_e = mu[None, :, :].expand(P, -1, -1)
+                if abs_acc is not None and mu_e.requires_grad:
+                    def _catch(g, ids=ids):
+                        abs_acc.index_add_(0, ids, g.detach().abs().sum(0))
+
+                    mu_e.register_hook(_catch)
+                dx = mu_e[:, :, 0] - px.reshape(-1, 1)
+                dy = mu_e[:, :, 1] - py.reshape(-1, 1)
                 sigma = 0.5 * (con[None, :, 0] * dx * dx + con[None, :, 2] * dy * dy) + con[None, :, 1] * dx * dy
                 araw = op[None, :] * torch.exp(-sigma)
                 alpha = torch.clamp(araw, max=ALPHA_MAX)
@@ -208,15 +217,20 @@ def composite(means2d, conics, opacities, colors, depths, radii, width, height, 
 
 def rasterization(means, quats, scales, opacities, colors, viewmats, Ks, width, height,
                   near_plane=0.01, far_plane=1e10, radius_clip=0.0, eps2d=0.3, backgrounds=None,
-                  render_mode="RGB", rasterize_mode="classic", margin=1e-5, row_range=None):
-    """gsplat-shaped entry: colors [N,3] or [C,N,3]; returns renders [C,H,W,D], alphas [C,H,W,1], info."""
+                  render_mode="RGB", rasterize_mode="classic", margin=1e-5, row_range=None, absgrad=False):
+    """gsplat-shaped entry: colors [N,3] or [C,N,3]; returns renders [C,H,W,D], alphas [C,H,W,1], info.
+    ``absgrad=True``: ``info["absgrad"]`` [C,N,2] is filled during backward (see ``composite``)."""
     assert render_mode in ("RGB", "D", "ED", "RGB+D", "RGB+ED")
     C = viewmats.shape[0]
     renders, alphas, ambs = [], [], []
     info = dict(radii=[], means2d=[], depths=[], conics=[], n_isect=[], ambiguous_gauss=[])
+    abs_all = torch.zeros(C, means.shape[0], 2, dtype=means.dtype) if absgrad else None
+    prs = [project(means, quats, scales, viewmats[c], Ks[c], width, height, eps2d, near_plane, far_plane, radius_clip,
+                   margin) for c in range(C)]
+    # info["means2d"] is a graph tensor UPSTREAM of the images, as in gsplat (base.py:430 calls retain_grad() on it)
+    means2d_all = torch.stack([pr["means2d"] for pr in prs])
     for c in range(C):
-        pr = project(means, quats, scales, viewmats[c], Ks[c], width, height, eps2d, near_plane,
-                     far_plane, radius_clip, margin)
+        pr = dict(prs[c], means2d=means2d_all[c])
         col = colors[c] if colors.dim() == 3 else colors
         op = opacities
         if rasterize_mode == "antialiased":
@@ -233,7 +247,7 @@ def rasterization(means, quats, scales, opacities, colors, viewmats, Ks, width, 
             if render_mode in ("RGB+D", "RGB+ED"):
                 bg = torch.cat([bg, torch.zeros(1, dtype=bg.dtype)])
         r, a, m, ni = composite(pr["means2d"], pr["conics"], op, feat, pr["depths"], pr["radii"],
-                                width, height, bg, margin, row_range)
+                                width, height, bg, margin, row_range, abs_acc=None if abs_all is None else abs_all[c])
         # a rounding-ambiguous Gaussian may gain / lose boundary tiles: flag the tiles in
         # rect(radius + 1) \ rect(radius - 1)
         if pr["ambiguous"].any():
@@ -255,8 +269,11 @@ def rasterization(means, quats, scales, opacities, colors, viewmats, Ks, width, 
             info[k].append(pr[k])
         info["n_isect"].append(ni)
         info["ambiguous_gauss"].append(pr["ambiguous"])
-    for k in ("radii", "means2d", "depths", "conics", "ambiguous_gauss"):
+    for k in ("radii", "depths", "conics", "ambiguous_gauss"):
         info[k] = torch.stack(info[k])
+    info["means2d"] = means2d_all
     info["ambiguous"] = torch.stack(ambs)
     info["width"], info["height"] = width, height
+    if abs_all is not None:
+        info["absgrad"] = abs_all
     return torch.stack(renders), torch.stack(alphas), info

@@ -1,59 +1,72 @@
-"""Import the UNMODIFIED reference bilateral code from /root/reference (this container only).
+"""Import the UNMODIFIED reference code of the hot path.  TEST INFRASTRUCTURE (see oracle/__init__.py).
 
-TEST INFRASTRUCTURE (see oracle/__init__.py).  Used by ``oracle/make_golden.py`` to mint
-the committed fixtures in ``tests/golden/`` and by the CPU tests that are skipped when
-``/root/reference`` is absent (it does not exist on the GPU box).
+Source tree, first that exists:
+* ``/root/reference/project``        (the build container), or
+* ``oracle/_ref/project``            (byte-for-byte copies made by ``oracle/build_ref.py``; git-ignored, travels to
+                                      the GPU box with the snapshot - ``/root/reference`` does not exist there).
 
-The reference imports three packages that are not installed here; none of them is touched
-by the bilateral path, so they are replaced by empty stubs:
+Used by ``oracle/make_golden.py`` to mint the committed fixtures in ``tests/golden/``, by the tests that compare
+with the live reference (skipped when neither tree exists), and by ``bench.py``'s CPU legs (``cpu_baseline`` /
+``--impl reference``), which time the reference's own bilateral module on the host cores.
 
-* ``tensorly``      - ``lib_bilagrid.py:48,53`` (``tl.set_backend`` at import time only)
-* ``pytorch3d``     - ``models/modules.py:9``  (``knn_points``; VoxelDeformer only)
-* ``nvdiffrast``    - ``models/modules.py:10`` (``dr.texture``; EnvLight only)
+Packages the reference imports that are not installed here are replaced by the stand-ins of ``oracle/ref_stubs.py``.
 """
+import importlib
 import os
 import sys
-import types
+
+from . import ref_stubs
 
 REFERENCE_ROOT = os.environ.get("BDS_REFERENCE_ROOT", "/root/reference")
-_PROJECT = os.path.join(REFERENCE_ROOT, "project")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_CANDIDATES = (os.path.join(REFERENCE_ROOT, "project"), os.path.join(_HERE, "_ref", "project"))
+
+
+def project_root():
+    for p in _CANDIDATES:
+        if os.path.isfile(os.path.join(p, "bilateral", "lib_bilagrid.py")):
+            return p
+    return None
 
 
 def reference_available() -> bool:
-    return os.path.isfile(os.path.join(_PROJECT, "bilateral", "lib_bilagrid.py"))
+    return project_root() is not None
 
 
-def _stub(name, **attrs):
-    if name in sys.modules:
-        return sys.modules[name]
-    m = types.ModuleType(name)
-    m.__dict__.update(attrs)
-    sys.modules[name] = m
-    return m
+def reference_kind() -> str:
+    """"reference" = /root/reference itself, "_ref" = the copies under oracle/_ref."""
+    p = project_root()
+    if p is None:
+        return "absent"
+    return "reference" if p == _CANDIDATES[0] else "_ref"
 
 
-def _not_available(*_a, **_k):  # pragma: no cover
-    raise RuntimeError("stubbed third-party function called; not on the bilateral path")
+def _prepare():
+    root = project_root()
+    if root is None:
+        raise FileNotFoundError(f"reference not found under {REFERENCE_ROOT} nor oracle/_ref (run python -m oracle.build_ref)")
+    ref_stubs.install()
+    if root not in sys.path:
+        sys.path.insert(0, root)
+    return root
 
 
 def load_reference():
     """Returns (lib_bilagrid module, models.modules module) of the reference."""
-    if not reference_available():
-        raise FileNotFoundError(f"reference not found under {REFERENCE_ROOT}")
-    _stub("tensorly", set_backend=lambda *_a, **_k: None)
-    _stub("tensorly.decomposition", parafac=_not_available)
-    p3d = _stub("pytorch3d")
-    p3d.ops = _stub("pytorch3d.ops", knn_points=_not_available)
-    p3d.transforms = _stub("pytorch3d.transforms", matrix_to_quaternion=_not_available)
-    nvd = _stub("nvdiffrast")
-    nvd.torch = _stub("nvdiffrast.torch", texture=_not_available)
-    if _PROJECT not in sys.path:
-        sys.path.insert(0, _PROJECT)
-    import importlib
-
+    _prepare()
     lib = importlib.import_module("bilateral.lib_bilagrid")
     mods = importlib.import_module("models.modules")
     return lib, mods
+
+
+def load_reference_trainers(gsplat_pkg_dir=None):
+    """Returns the reference's ``models.trainers.scene_graph`` module (``MultiTrainer``; ``BasicTrainer`` is its
+    base).  ``models/gaussians/basics.py:12-15`` imports ``gsplat``: ``gsplat_pkg_dir`` is put first on ``sys.path``
+    for it (``<repo>/shim`` = the sm_100a renderer, the import seam; ``<repo>/oracle/gsplat_cpu`` = the CPU oracle)."""
+    _prepare()
+    if gsplat_pkg_dir is not None and gsplat_pkg_dir not in sys.path:
+        sys.path.insert(0, gsplat_pkg_dir)
+    return importlib.import_module("models.trainers.scene_graph")
 
 
 def reference_apply_chain(rgb, affine_list):

@@ -1,0 +1,195 @@
+"""The drop-in trainer against the reference's UNMODIFIED trainer code.
+
+Reference arm: ``models.trainers.scene_graph.MultiTrainer`` + ``models.modules.MultiScaleBilateralAffineTransform``
+imported from the reference tree (``/root/reference/project`` or its byte-for-byte copies under ``oracle/_ref``),
+running on the CPU with the oracle as ``gsplat``.  Checked arm: ``FusedMultiTrainer`` + this package's Affine module
+with the same parameters.
+
+* CPU test (``-m "not gpu"``): the kernel-backed entry points are replaced by their oracle restatements, so what is
+  checked is the trainer's host logic - the output dictionary, ``loss_dict`` (``affine_loss`` present and equal to the
+  reference's), every parameter gradient, the densification taps, the per-class eval renders.
+* GPU test (``-m gpu``): the same comparison with the real sm_100a kernels on the fused arm.
+"""
+import pytest
+import torch
+
+import trainer_harness as TH
+from oracle.ref_loader import reference_available
+
+pytestmark = pytest.mark.skipif(not reference_available(), reason="needs the reference tree or oracle/_ref")
+
+
+def _reference_arm(w1, single=False):
+    sg = TH.load_scene_graph()
+    cfg = TH.make_cfg(TH.REF_SINGLE if single else TH.REF_MS, w1=w1, single=single)
+    tr = TH.build_trainer(sg.MultiTrainer, cfg, torch.device("cpu"))
+    TH.init_scene(tr, "cpu")
+    return tr
+
+
+def _fused_arm(ref_trainer, device, w1, single=False, guidance_factor="default"):
+    TH.load_scene_graph()
+    import bilateral_driving_b200.trainer as T
+
+    cfg = TH.make_cfg(TH.OUR_SINGLE if single else TH.OUR_MS, w1=w1, single=single)
+    cfg.trainer.type = "bilateral_driving_b200.trainer.FusedMultiTrainer"
+    tr = TH.build_trainer(T.FusedMultiTrainer, cfg, torch.device(device))
+    for m in tr.models.values():
+        m.to(device)
+    TH.copy_models(ref_trainer, tr, device)
+    if guidance_factor != "default":
+        tr.guidance_factor = guidance_factor
+    return tr
+
+
+def _step(tr, image_infos, cam_infos, fix_reference_bug=False):
+    tr.set_train()
+    tr.preprocess_per_train_step(tr.step)
+    for p in TH.all_params(tr).values():
+        p.grad = None
+    outputs = tr(image_infos, cam_infos)
+    tr.update_visibility_filter()
+    if fix_reference_bug:
+        # the published MultiTrainer.forward never sets outputs["original_rgb"] although compute_losses reads it
+        # (base.py:628-631): the first step of every ms-bilateral config raises KeyError
+        with pytest.raises(KeyError):
+            tr.compute_losses(outputs, image_infos, cam_infos)
+        outputs["original_rgb"] = outputs["rgb_gaussians"] + outputs["rgb_sky"] * (1.0 - outputs["opacity"])  # base.py:496
+    loss_dict = tr.compute_losses(outputs, image_infos, cam_infos)
+    sum(loss_dict.values()).backward()
+    return outputs, loss_dict
+
+
+def _patch_cpu(monkeypatch):
+    import bilateral_driving_b200.bilateral as BL
+    import bilateral_driving_b200.render as R
+
+    monkeypatch.setattr(R, "render_fused", TH.oracle_render_fused)
+    monkeypatch.setattr(BL, "multiscale_bilateral", TH.oracle_multiscale_bilateral)
+    monkeypatch.setattr(BL, "total_variation_loss", TH.oracle_tv)
+
+
+def _compare(ref, fused, o_ref, o_fu, l_ref, l_fu, tol_img, tol_loss, tol_grad, keep=None):
+    dev = o_fu["rgb"].device
+    k = None if keep is None else keep.to(dev)[..., None]
+    for key in ("rgb", "rgb_gaussians", "opacity", "rgb_sky", "rgb_sky_blend", "original_rgb"):
+        assert key in o_fu, key
+        d = (o_fu[key] - o_ref[key].to(dev)).abs()
+        assert float((d if k is None else d * k).max()) < tol_img, key
+    d = (o_fu["depth"] - o_ref["depth"].to(dev)).abs() / o_ref["depth"].to(dev).abs().clamp(min=1.0)
+    assert float((d if k is None else d * k).max()) < 2 * tol_img
+    assert set(l_fu) == set(l_ref), (sorted(l_fu), sorted(l_ref))
+    assert "affine_loss" in l_fu
+    for key in l_ref:
+        a, b = float(l_fu[key]), float(l_ref[key])
+        assert abs(a - b) <= tol_loss * max(1.0, abs(b)), (key, a, b)
+    pr, pf = TH.all_params(ref), TH.all_params(fused)
+    assert set(pr) == set(pf)
+    for name in pr:
+        gr, gf = pr[name].grad, pf[name].grad
+        assert (gr is None) == (gf is None), name
+        if gr is None:
+            continue
+        scale = float(gr.abs().max().clamp(min=1e-12))
+        assert float((gf.cpu() - gr).abs().max()) / scale < tol_grad, name
+    # densification taps (base.py:279-297): values, not just shapes
+    ir, iff = ref.info, fused.info
+    assert int((iff["radii"].cpu() != ir["radii"]).sum()) <= 2
+    for attr in ("grad", "absgrad"):
+        a, b = getattr(iff["means2d"], attr), getattr(ir["means2d"], attr)
+        assert a is not None and b is not None and a.shape == b.shape, attr
+        assert float((a.cpu() - b).abs().max()) / float(b.abs().max().clamp(min=1e-12)) < tol_grad, attr
+    assert int(iff["width"]) == int(ir["width"]) and int(iff["height"]) == int(ir["height"])
+
+
+@pytest.mark.parametrize("w1", [0.0, 0.5])
+def test_fused_trainer_host_logic_against_reference_trainer(monkeypatch, w1):
+    """CPU: FusedMultiTrainer.forward / compute_losses against the reference's own BasicTrainer.compute_losses /
+    MultiTrainer.forward on the same parameters (default guidance_factor=[4,4,2])."""
+    _patch_cpu(monkeypatch)
+    ref = _reference_arm(w1)
+    fused = _fused_arm(ref, "cpu", w1)
+    image_infos, cam_infos = TH.make_batch("cpu")
+    o_ref, l_ref = _step(ref, image_infos, cam_infos, fix_reference_bug=True)
+    o_fu, l_fu = _step(fused, image_infos, cam_infos)
+    # the reference's expression, spelled out: affine.w * tv_loss() + affine.w1 * inverse_loss(gt, original_rgb)
+    aff = ref.models["Affine"]
+    mask = (1.0 - image_infos["egocar_masks"]).float()[..., None]
+    expect = 0.01 * aff.tv_loss() + w1 * aff.inverse_loss(image_infos["pixels"] * mask, o_ref["original_rgb"] * mask)
+    assert abs(float(l_fu["affine_loss"]) - float(expect)) < 1e-6 * max(1.0, abs(float(expect)))
+    assert float(l_fu["affine_loss"]) != 0.0
+    _compare(ref, fused, o_ref, o_fu, l_ref, l_fu, tol_img=1e-6, tol_loss=1e-6, tol_grad=1e-4)
+    # the type string is back in place after compute_losses
+    assert fused.model_config.Affine.type == TH.OUR_MS
+    # eval: per-class and dynamic-only renders (scene_graph.py:296-313)
+    ref.set_eval(); fused.set_eval()
+    with torch.no_grad():
+        e_ref, e_fu = ref(image_infos, cam_infos), fused(image_infos, cam_infos)
+    assert set(e_ref) | {"original_rgb"} == set(e_fu)
+    for key in ("Background_rgb", "Background_opacity", "Background_depth", "Dynamic_rgb", "Dynamic_opacity"):
+        assert float((e_fu[key] - e_ref[key]).abs().max()) < 1e-6, key
+
+
+def test_single_grid_affine_type_also_gets_its_tv_loss(monkeypatch):
+    """base.py:589-593: the BilateralAffineTransform branch (TV only)."""
+    _patch_cpu(monkeypatch)
+    ref = _reference_arm(0.0, single=True)
+    fused = _fused_arm(ref, "cpu", 0.0, single=True)
+    image_infos, cam_infos = TH.make_batch("cpu")
+    o_ref, l_ref = _step(ref, image_infos, cam_infos)
+    o_fu, l_fu = _step(fused, image_infos, cam_infos)
+    o_ref["original_rgb"] = o_fu["original_rgb"]   # not produced by the reference on this branch (and not read)
+    _compare(ref, fused, o_ref, o_fu, l_ref, l_fu, tol_img=1e-6, tol_loss=1e-6, tol_grad=1e-4)
+
+
+def test_chain_inverse_closed_form_matches_torch_inverse():
+    """modules.py:474-492 composes 4x4 homogeneous matrices and calls torch.inverse per pixel."""
+    from bilateral_driving_b200.bilateral import affine_to_homogeneous_batch, chain_inverse_apply
+
+    g = torch.Generator().manual_seed(0)
+    H, W = 9, 7
+    fields = [torch.eye(3, 4).expand(1, H, W, 3, 4) + 0.2 * torch.randn(1, H, W, 3, 4, generator=g) for _ in range(3)]
+    gt = torch.rand(H, W, 3, generator=g)
+    mat = torch.eye(4).view(1, 1, 1, 4, 4).repeat(1, H, W, 1, 1)
+    for arr in fields:
+        mat = affine_to_homogeneous_batch(arr) @ mat
+    inv = torch.inverse(mat.view(-1, 4, 4)).view(1, H, W, 4, 4)[:, :, :, :3, :].reshape(H, W, 3, 4)
+    want = (inv[..., :3, :3] @ gt[..., None] + inv[..., :3, 3:])[..., 0]
+    got = chain_inverse_apply([f.reshape(H, W, 3, 4) for f in fields], gt)
+    assert float((got - want).abs().max()) < 1e-4
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("guidance", ["default", None])
+def test_fused_trainer_on_gpu_against_reference_trainer(guidance):
+    """GPU: the drop-in trainer with the real kernels (composite mode 1 + low-res bilateral kernels for the default
+    guidance_factor=[4,4,2]; composite mode 2 for None) against the reference's trainer on the CPU oracle."""
+    ref = _reference_arm(0.5)
+    if guidance is None:
+        # the reference trainer cannot be asked for guidance_factor=None (scene_graph.py:113 does not pass it):
+        # give the reference module that default for this comparison
+        aff = ref.models["Affine"]
+        orig = aff.forward
+        aff.forward = lambda rgb, infos, guidance_factor=None: orig(rgb, infos, guidance_factor=None)
+    fused = _fused_arm(ref, "cuda", 0.5, guidance_factor=guidance)
+    image_infos, cam_infos = TH.make_batch("cpu")
+    g_infos, g_cam = TH.make_batch("cuda")
+    o_ref, l_ref = _step(ref, image_infos, cam_infos, fix_reference_bug=True)
+    o_fu, l_fu = _step(fused, g_infos, g_cam)
+    keep = ~ref.info["ambiguous"][0]
+    _compare(ref, fused, o_ref, o_fu, l_ref, l_fu, tol_img=2e-5, tol_loss=2e-4, tol_grad=2e-3, keep=keep)
+    assert "_bds_cache" in fused.info and fused.info["_bds_cache"] is not None
+    # eval: masked re-renders reuse the sorted lists of the fused render
+    from bilateral_driving_b200 import _lib
+
+    ref.set_eval(); fused.set_eval()
+    with torch.no_grad():
+        e_ref = ref(image_infos, cam_infos)
+        n0 = _lib.lib.bds_launch_count()
+        e_fu = fused(g_infos, g_cam)
+        torch.cuda.synchronize()
+        launches = _lib.lib.bds_launch_count() - n0
+    keep_g = keep.cuda()[..., None]
+    for key in ("rgb", "Background_rgb", "Background_opacity", "Dynamic_rgb", "Dynamic_opacity"):
+        assert float(((e_fu[key] - e_ref[key].cuda()).abs() * keep_g).max()) < 2e-5, key
+    assert launches < 40   # one pipeline + two masked composites, not three rasterizations
