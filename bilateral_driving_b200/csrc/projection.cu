@@ -482,6 +482,61 @@ __global__ void __launch_bounds__(256) project_bwd_kernel(ProjBwdParams p) {
   }
 }
 
+// Cotangents a user of the gsplat info tensors puts on means2d / depths / conics (v_*_extra) for Gaussians that gsplat
+// calls visible (radii > 0) but that own NO splat record here (their alpha >= 1/255 footprint misses every tile of the
+// band, so the exact binning never emitted them): project_bwd_kernel walks the records and cannot see them.
+__global__ void __launch_bounds__(256) project_bwd_extras_kernel(ProjBwdParams p, const int32_t* __restrict__ radii,
+                                                                 const int32_t* __restrict__ slot_of) {
+  const int64_t total = (int64_t)p.d.n_gauss * p.d.n_cams;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool active = idx < total && radii[idx] > 0 && slot_of[idx] < 0;
+  float vview[12];
+#pragma unroll
+  for (int k = 0; k < 12; ++k) vview[k] = 0.f;
+  const int N = p.d.n_gauss;
+  const int c = idx < total ? (int)(idx / N) : 0;
+  if (active) {
+    const int n = (int)(idx - (int64_t)c * N);
+    float vmx = 0.f, vmy = 0.f, vz = 0.f, va = 0.f, vb = 0.f, vc = 0.f;
+    if (p.v_means2d_extra) { vmx = p.v_means2d_extra[2 * idx]; vmy = p.v_means2d_extra[2 * idx + 1]; }
+    if (p.v_depths_extra) vz = p.v_depths_extra[idx];
+    if (p.v_conics_extra) { va = p.v_conics_extra[3 * idx]; vb = p.v_conics_extra[3 * idx + 1]; vc = p.v_conics_extra[3 * idx + 2]; }
+    CamIntr cam;
+    load_cam(p.viewmats, p.Ks, c, cam);
+    float mu[3] = {p.means[3 * (size_t)n], p.means[3 * (size_t)n + 1], p.means[3 * (size_t)n + 2]};
+    float q[4] = {p.quats[4 * (size_t)n], p.quats[4 * (size_t)n + 1], p.quats[4 * (size_t)n + 2], p.quats[4 * (size_t)n + 3]};
+    float s[3] = {p.scales[3 * (size_t)n], p.scales[3 * (size_t)n + 1], p.scales[3 * (size_t)n + 2]};
+    if (p.d.raw_params) { s[0] = __expf(s[0]); s[1] = __expf(s[1]); s[2] = __expf(s[2]); }
+    float v_mu[3] = {0.f, 0.f, 0.f}, v_q[4] = {0.f, 0.f, 0.f, 0.f}, v_s[3] = {0.f, 0.f, 0.f}, v_R[9], v_t[3];
+    project_gaussian_vjp(mu, q, s, cam, p.d.width, p.d.height, p.d.eps2d, vmx, vmy, vz, va, vb, vc, 0.f, v_mu, v_q, v_s,
+                         v_R, v_t);
+    if (p.d.raw_params) { v_s[0] *= s[0]; v_s[1] *= s[1]; v_s[2] *= s[2]; }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      red_add(p.v_means + 3 * (size_t)n + k, v_mu[k]);
+      red_add(p.v_scales + 3 * (size_t)n + k, v_s[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) red_add(p.v_quats + 4 * (size_t)n + k, v_q[k]);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      vview[i * 4] = v_R[i * 3]; vview[i * 4 + 1] = v_R[i * 3 + 1]; vview[i * 4 + 2] = v_R[i * 3 + 2];
+      vview[i * 4 + 3] = v_t[i];
+    }
+  }
+  if (p.v_viewmats && __any_sync(0xffffffffu, active)) {
+    // consecutive idx share the camera except where a warp straddles a camera boundary
+    for (int cam_i = __shfl_sync(0xffffffffu, c, 0); cam_i <= __shfl_sync(0xffffffffu, c, 31); ++cam_i) {
+      const bool mine = active && c == cam_i;
+#pragma unroll
+      for (int k = 0; k < 12; ++k) {
+        float v = warp_sum(mine ? vview[k] : 0.f);
+        if ((threadIdx.x & 31) == 0 && v != 0.f) red_add(p.v_viewmats + 16 * cam_i + k, v);
+      }
+    }
+  }
+}
+
 // stand-alone SH ---------------------------------------------------------------------------------
 __global__ void sh_fwd_kernel(int n, int degree, int K, const float* __restrict__ dirs,
                               const float* __restrict__ coeffs, float* __restrict__ out) {
@@ -628,6 +683,26 @@ extern "C" int bds_project_bwd(const bds_render_desc* d, const float* means, con
   // the slot count lives on the device; launch over the worst case (every (cam, gauss) visible) and
   // let threads beyond counters[0] exit - the grid is cheap next to an extra host sync
   project_bwd_kernel<<<ceil_div(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  BDS_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int bds_project_bwd_extras(const bds_render_desc* d, const float* means, const float* quats,
+                                      const float* scales, const float* viewmats, const float* Ks, const int32_t* radii,
+                                      const int32_t* slot_of, const float* v_means2d_extra, const float* v_depths_extra,
+                                      const float* v_conics_extra, float* v_means, float* v_quats, float* v_scales,
+                                      float* v_viewmats, bds_stream_t stream) {
+  if (int rc = check_render_desc(d)) return rc;
+  int64_t total = (int64_t)d->n_gauss * d->n_cams;
+  if (total == 0 || !(v_means2d_extra || v_depths_extra || v_conics_extra)) return 0;
+  BDS_REQUIRE(means && quats && scales && viewmats && Ks && radii && slot_of, "project_bwd_extras: null input pointer");
+  BDS_REQUIRE(v_means && v_quats && v_scales, "project_bwd_extras: null output pointer");
+  ProjBwdParams p{};
+  p.d = *d;
+  p.means = means; p.quats = quats; p.scales = scales; p.viewmats = viewmats; p.Ks = Ks;
+  p.v_means2d_extra = v_means2d_extra; p.v_depths_extra = v_depths_extra; p.v_conics_extra = v_conics_extra;
+  p.v_means = v_means; p.v_quats = v_quats; p.v_scales = v_scales; p.v_viewmats = v_viewmats;
+  project_bwd_extras_kernel<<<ceil_div(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(p, radii, slot_of);
   BDS_CHECK_LAUNCH();
   return 0;
 }

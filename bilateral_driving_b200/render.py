@@ -166,6 +166,9 @@ class _RenderFn(torch.autograd.Function):
             means2d = depths = conics = None
         comps = torch.zeros(Cn, N, **f32) if (cfg.antialiased and cfg.dense_info) else None
         tiles_touched = torch.empty(Cn, N, **i32)
+        # record index of every (camera, Gaussian), -1 = none: only kept when the gsplat info tensors are exposed (a
+        # user cotangent on them must also reach visible Gaussians that own no record: bds_project_bwd_extras)
+        slot_of = torch.empty(Cn, N, **i32) if cfg.dense_info else None
         tile_counts = torch.empty(n_band_tiles + 1, **i32)
         counters = torch.zeros(COUNTERS_LEN, **i32)   # [0] records, [1] overflow flag, [2..] queue of very large splats
         cap = cfg.splat_capacity or max(Cn * N, 1)
@@ -175,7 +178,7 @@ class _RenderFn(torch.autograd.Function):
             check(lib.bds_project_fwd(C.byref(d), ptr(means), ptr(quats), ptr(scales), ptr(opacities), ptr(colors),
                                       colors_per_cam, ptr(fdc), ptr(frest), ptr(viewmats), ptr(Ks), ptr(radii),
                                       ptr(means2d), ptr(depths), ptr(conics), ptr(comps), ptr(tiles_touched),
-                                      ptr(tile_counts), ptr(splats), C.c_int32(cap), NULL, ptr(counters), st),
+                                      ptr(tile_counts), ptr(splats), C.c_int32(cap), ptr(slot_of), ptr(counters), st),
                   "bds_project_fwd")
         stats = torch.zeros(1, device=dev, dtype=torch.int64)
         tile_offsets = torch.empty(n_band_tiles + 1, **i32)
@@ -214,7 +217,8 @@ class _RenderFn(torch.autograd.Function):
         ctx.has = dict(colors=colors is not None, sky=sky is not None, bg=backgrounds is not None)
         ctx.save_for_backward(means, quats, scales, opacities, colors, fdc, frest, viewmats, Ks, backgrounds, sky,
                               splats, counters, sorted_splats, tile_offsets, out_rgbg, out_depth, out_alpha, last_ids,
-                              out_rgb if (cfg.mode == 0 and cfg.channels == 4 and cfg.expected_depth) else None, *grids)
+                              out_rgb if (cfg.mode == 0 and cfg.channels == 4 and cfg.expected_depth) else None,
+                              radii, slot_of, *grids)
         holder.update(n_isect=n_isect, n_visible=n_slots, depths=depths, conics=conics, tiles_touched=tiles_touched,
                       tile_offsets=tile_offsets, compensations=comps, sorted_splats=sorted_splats, last_ids=last_ids,
                       # what rasterize_masked() needs to composite again over the same sorted lists
@@ -230,7 +234,8 @@ class _RenderFn(torch.autograd.Function):
     def backward(ctx, v_rgb, v_rgbg, v_depth, v_alpha, v_means2d_extra, _v_radii):
         cfg, d, e = ctx.cfg, ctx.d, ctx.e
         (means, quats, scales, opacities, colors, fdc, frest, viewmats, Ks, backgrounds, sky, splats, counters,
-         sorted_splats, tile_offsets, out_rgbg, out_depth, out_alpha, last_ids, out_rgb_ed, *grids) = ctx.saved_tensors
+         sorted_splats, tile_offsets, out_rgbg, out_depth, out_alpha, last_ids, out_rgb_ed, radii, slot_of,
+         *grids) = ctx.saved_tensors
         dev = means.device
         f32 = dict(device=dev, dtype=torch.float32)
         N, Cn = means.shape[0], viewmats.shape[0]
@@ -296,6 +301,10 @@ class _RenderFn(torch.autograd.Function):
                                       ptr(counters), ptr(v_splats), ptr(extra), NULL, NULL, ptr(v_means), ptr(v_quats),
                                       ptr(v_scales), ptr(v_opac), ptr(v_colors), ptr(v_fdc), ptr(v_frest), ptr(v_view),
                                       ptr(v_m2d), ptr(absg), st), "bds_project_bwd")
+            if extra is not None and slot_of is not None:
+                check(lib.bds_project_bwd_extras(C.byref(d), ptr(means), ptr(quats), ptr(scales), ptr(viewmats), ptr(Ks),
+                                                 ptr(radii), ptr(slot_of), ptr(extra), NULL, NULL, ptr(v_means),
+                                                 ptr(v_quats), ptr(v_scales), ptr(v_view), st), "bds_project_bwd_extras")
         # densification taps (base.py:279-297 reads info["means2d"].grad / .absgrad)
         ref = ctx.holder.get("means2d_ref")
         m2d = ref() if ref is not None else None

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define BDS_ABI_VERSION 2
+#define BDS_ABI_VERSION 3
 #define BDS_MAX_LEVELS 4
 #define BDS_COUNTERS_LEN 4096  /* int32 entries of the projection counters buffer */
 #define BDS_TILE 16
@@ -221,6 +221,16 @@ int bds_project_bwd(const bds_render_desc* d, const float* means, const float* q
                     const float* v_conics_extra, float* v_means, float* v_quats, float* v_scales,
                     float* v_opacities, float* v_colors, float* v_features_dc, float* v_features_rest,
                     float* v_viewmats, float* v_means2d, float* absgrad, bds_stream_t stream);
+
+/* Companion of bds_project_bwd for the optional dense extras only: a Gaussian that gsplat calls visible
+ * (radii > 0) but whose alpha >= 1/255 footprint misses every tile of the band owns no splat record here
+ * (slot_of < 0), so the record walk of bds_project_bwd never sees a cotangent a user of the gsplat info tensors
+ * put on its means2d / depths / conics.  This entry adds exactly those contributions (ACCUMULATED into the same
+ * outputs).  radii, slot_of [C,N] int32 as written by bds_project_fwd.  No-op when all three extras are NULL. */
+int bds_project_bwd_extras(const bds_render_desc* d, const float* means, const float* quats, const float* scales,
+                           const float* viewmats, const float* Ks, const int32_t* radii, const int32_t* slot_of,
+                           const float* v_means2d_extra, const float* v_depths_extra, const float* v_conics_extra,
+                           float* v_means, float* v_quats, float* v_scales, float* v_viewmats, bds_stream_t stream);
 
 /* Fused photometric loss used by the benchmark step: mean((rgb-gt)^2) +
  * lambda_d*mean(depth) + lambda_a*mean(alpha); writes the cotangents and ACCUMULATES the loss. */
