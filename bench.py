@@ -115,42 +115,102 @@ class ClockSampler:
 
 
 def cpu_threads() -> int:
-    """Threads for the CPU legs: torch's indexing kernels peak at 32 threads on the 128-core hosts of this pool
-    (probe scripts/cpu_threads_probe.py: 8/16/32/64/128 threads -> 0.54/0.61/0.68/0.43/0.08 Mpix/s), so the
-    fastest setting is used and reported in ``cores``."""
-    return max(1, min(os.cpu_count() or 1, 32))
+    """Threads for the CPU legs: every host core, stated in ``cores``."""
+    return max(1, os.cpu_count() or 1)
 
 
-def cpu_bilateral_baseline(rgb_in_cpu, grids_cpu, repeats=2):
-    """The reference's pure-PyTorch bilateral path (oracle port of modules.py:505-584 +
-    scene_graph.py:112-117, guidance_factor=None = the semantics the fused kernel implements), fwd+bwd
-    of sum(out*G) on the host cores.  Returns (Mpix/s, seconds per iteration, threads)."""
+def _reference_bilateral_step(H, W, grids_cpu, rgb_in, G, guidance_factor, kind_box):
+    """One fwd+bwd of the reference's pure-PyTorch bilateral path on the host cores: the reference's OWN
+    ``models.modules.MultiScaleBilateralAffineTransform`` + the apply loop of scene_graph.py:112-117, imported from
+    oracle/_ref (byte-for-byte copies, oracle/build_ref.py) or /root/reference; the oracle port only if neither
+    exists.  Returns a closure that runs one timed iteration."""
     import torch
 
+    from oracle import ref_loader
+
+    sizes = [[g.shape[3], g.shape[2], g.shape[1]] for g in grids_cpu]   # (grid_X, grid_Y, grid_W)
+    if ref_loader.reference_available():
+        _, mods = ref_loader.load_reference()
+        kind_box["kind"] = "reference"
+        kind_box["source"] = ref_loader.reference_kind()
+        m = mods.MultiScaleBilateralAffineTransform("Affine", n=1, grid=sizes, device="cpu")
+        for i, g in enumerate(grids_cpu):
+            getattr(m, f"bil_grids{i}").grids.data.copy_(g[None])
+        info = {"img_idx": torch.zeros(H, W, dtype=torch.long)}
+
+        def run():
+            rgb = rgb_in.clone().requires_grad_(True)
+            for p_ in m.parameters():
+                p_.grad = None
+            out = ref_loader.reference_apply_chain(rgb, m(rgb, info, guidance_factor=guidance_factor))
+            (out * G).sum().backward()
+        return run
     from oracle import bilateral_ref as B
 
-    torch.set_num_threads(cpu_threads())
-    H, W, _ = rgb_in_cpu.shape
-    g = torch.Generator(); g.manual_seed(2)
-    G = torch.randn(H, W, 3, generator=g)
-    best = None
-    for it in range(repeats + 1):
-        rgb = rgb_in_cpu.clone().requires_grad_(True)
+    kind_box["kind"] = "port"
+    kind_box["source"] = "oracle/bilateral_ref.py (oracle/_ref absent)"
+
+    def run_port():
+        rgb = rgb_in.clone().requires_grad_(True)
         grids = [x.clone().requires_grad_(True) for x in grids_cpu]
-        t0 = time.perf_counter()
-        out = B.multiscale_forward(grids, rgb, None)
-        (out * G).sum().backward()
-        dt = time.perf_counter() - t0
-        if it > 0:
-            best = dt if best is None else min(best, dt)
-    return H * W / best / 1e6, best, torch.get_num_threads()
+        (B.multiscale_forward(grids, rgb, guidance_factor) * G).sum().backward()
+    return run_port
+
+
+def cpu_reference_timings(H, W, grids_cpu, warmup=1, repeats=5, repeats_fullres=3):
+    """Times the CPU reference for BOTH guidance modes: ``guidance_factor=None`` (the
+    semantics of the fused kernel = the benchmark workload) and the reference's default ``[4,4,2]``.  Returns a dict
+    with per-mode lists of seconds, the thread count and what was timed."""
+    import torch
+
+    torch.set_num_threads(cpu_threads())
+    g = torch.Generator(); g.manual_seed(17)
+    rgb_in = torch.rand(H, W, 3, generator=g)
+    G = torch.randn(H, W, 3, generator=g)
+    res = {"threads": torch.get_num_threads(), "torch": torch.__version__}
+    for tag, gf, reps in (("none", None, repeats_fullres), ("f442", [4, 4, 2], repeats)):
+        box = {}
+        run = _reference_bilateral_step(H, W, grids_cpu, rgb_in, G, gf, box)
+        times = []
+        for it in range(warmup + reps):
+            t0 = time.perf_counter()
+            run()
+            dt = time.perf_counter() - t0
+            if it >= warmup:
+                times.append(dt)
+        res[tag] = times
+        res.update(box)
+    return res
+
+
+def _cpu_model_name():
+    try:
+        for ln in open("/proc/cpuinfo"):
+            if ln.startswith("model name"):
+                return ln.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown CPU"
+
+
+def _cpu_baseline_block(H, W, t):
+    best_none, best_442 = min(t["none"]), min(t["f442"])
+    v = H * W / best_none / 1e6
+    return {
+        "value": v, "unit": UNIT, "cores": t["threads"], "kind": t["kind"], "source": t["source"],
+        "guidance_442_value": H * W / best_442 / 1e6,
+        "sample": (f"the reference's own MultiScaleBilateralAffineTransform + apply (bilateral half of the path; the "
+                   f"rasteriser half is gsplat CUDA, no CPU implementation exists) fwd+bwd of sum(out*G) on ONE {W}x{H} "
+                   f"image: value = guidance_factor=None (the workload's semantics), best of {len(t['none'])} after 1 "
+                   f"warm-up = {best_none:.2f} s; guidance_442_value = reference default [4,4,2], best of "
+                   f"{len(t['f442'])} = {best_442:.2f} s; {_cpu_model_name()}, {t['threads']} threads, torch {t['torch']}")}
 
 
 def run_reference(args):
-    """Reference arm: the reference has NO CPU (or any own) implementation of the rasteriser half
-    (it is gsplat CUDA, a pip dependency); its own code on this path is the pure-PyTorch bilateral
-    module, which is what runs here on the host cores (oracle port - /root/reference does not exist
-    on the GPU box).  Each step = fwd+bwd of one 1920x1080 camera image."""
+    """Reference arm: the reference has NO CPU (or any own) implementation of the rasteriser half (it is gsplat CUDA,
+    a pip dependency); its own code on this path is the pure-PyTorch bilateral module, which is what runs here on the
+    host cores, imported unmodified from oracle/_ref (or /root/reference).  Each step = fwd+bwd of one 1920x1080
+    camera image with guidance_factor=None (the semantics of the GPU arm's workload)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -159,35 +219,34 @@ def run_reference(args):
     from bilateral_driving_b200 import synthetic as S
 
     H, W = args.height, args.width
-    g = torch.Generator(); g.manual_seed(17)
-    rgb_in = torch.rand(H, W, 3, generator=g)
     grids = [x[0] for x in S.make_grids(1)]
     torch.set_num_threads(cpu_threads())
-    from oracle import bilateral_ref as B
-
+    g = torch.Generator(); g.manual_seed(17)
+    rgb_in = torch.rand(H, W, 3, generator=g)
     Gm = torch.randn(H, W, 3, generator=g)
+    box = {}
+    gf = [4, 4, 2] if args.guidance == "lowres" else None
+    run = _reference_bilateral_step(H, W, grids, rgb_in, Gm, gf, box)
     times = []
     for it in range(args.warmup + args.steps):
-        rgb = rgb_in.clone().requires_grad_(True)
-        gr = [x.clone().requires_grad_(True) for x in grids]
         t0 = time.perf_counter()
-        (B.multiscale_forward(gr, rgb, None) * Gm).sum().backward()
+        run()
         dt = time.perf_counter() - t0
         if it >= args.warmup:
             times.append(dt)
     total = sum(times)
     val = H * W * len(times) / total / 1e6
-    sample = ("bilateral half only (the reference's rasteriser is gsplat CUDA, no CPU path exists): oracle port of "
-              "MultiScaleBilateralAffineTransform(guidance_factor=None)+apply, fwd+bwd, one 1920x1080 image per step")
+    sample = (f"bilateral half only (the reference's rasteriser is gsplat CUDA, no CPU path exists): the reference's own "
+              f"MultiScaleBilateralAffineTransform(guidance_factor={gf})+apply, fwd+bwd, one {W}x{H} image per step, "
+              f"{_cpu_model_name()}, {torch.get_num_threads()} threads, torch {torch.__version__}")
     _emit({
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         # same workload name as the GPU arm; what a step of THIS arm covers is the bounded sample below
-        "config": {"workload": _workload_name(args.n_gauss, args.cams, W, H, args.guidance),
-                   "sample": f"bilateral fwd+bwd of ONE {W}x{H} camera image per step (the rasteriser half of the path is "
-                             f"gsplat CUDA in the reference: no CPU implementation exists), CPU torch {torch.__version__}"},
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+        "config": {"workload": _workload_name(args.n_gauss, args.cams, W, H, args.guidance), "sample": sample},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": box["kind"],
+                         "source": box["source"], "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     })
 
@@ -395,14 +454,9 @@ def main():
                      "traffic_source": "ncu --set full, profiles/r01_ncu_full_key_metrics.txt" if default_workload and args.guidance in NCU_TRAFFIC_BYTES else None},
     }
     if world == 1 and not args.no_cpu_baseline:
-        # CPU baseline on the box's host cores: bounded sample = ONE camera image, 1 warm-up + 2 timed
-        rgb_in = torch.rand(H, W, 3, generator=torch.Generator().manual_seed(17))
-        v, sec, cores = cpu_bilateral_baseline(rgb_in, [g[0] for g in grids_cpu])
-        line["cpu_baseline"] = {
-            "value": v, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"oracle port of the reference's pure-PyTorch bilateral path (guidance_factor=None) fwd+bwd on one "
-                      f"{W}x{H} image, best of 2 after 1 warm-up, {sec:.2f} s/iter; the rasteriser half has no CPU "
-                      f"implementation in the reference (gsplat CUDA)"}
+        # CPU baseline on the box's host cores: bounded sample = ONE camera image, both guidance modes
+        t = cpu_reference_timings(H, W, [g[0] for g in grids_cpu])
+        line["cpu_baseline"] = _cpu_baseline_block(H, W, t)
     _emit(line)
     if world > 1:
         dist.destroy_process_group()
