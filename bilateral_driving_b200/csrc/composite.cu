@@ -409,7 +409,7 @@ BDS_D void flush_batch(const BatchSmem* bs, int nb, float rx0, float ry0, float*
 
 constexpr size_t kBwdSmemRec = (size_t)kBStages * kChunk * kRecBytes;
 constexpr size_t kBwdSmemWalk = kBwdSmemRec + 8 * sizeof(BatchSmem);
-constexpr size_t kBwdSmem = kBwdSmemBil > kBwdSmemWalk ? kBwdSmemBil : kBwdSmemWalk;
+constexpr size_t kBwdSmem = kPanelBytes > kBwdSmemWalk ? kPanelBytes : kBwdSmemWalk;
 
 #ifndef BDS_BWD_MINB
 #define BDS_BWD_MINB 4     // resident CTAs per SM the backward is compiled for
@@ -459,8 +459,9 @@ __global__ void __launch_bounds__(256, BDS_BWD_MINB) composite_bwd_kernel(CompPa
     }
   }
   if (MODE == 2) {
-    // chain backward (appendix A.3 of SURVEY.md); every thread takes part in the cooperative
-    // grid-gradient accumulation, pixels outside the image contribute nothing
+    // chain backward (appendix A.3 of SURVEY.md); every warp reduces the grid-node gradients of its own 8x4 pixels
+    // (warp_level_accumulate, bilateral_accum.cuh: no block barrier), pixels outside the image contribute nothing
+    WarpPanel* const pn = reinterpret_cast<WarpPanel*>(dyn_smem) + warp;
     const float x0r = fmaf(sk[0], Tfin, rg), x0g = fmaf(sk[1], Tfin, gg), x0b = fmaf(sk[2], Tfin, bg);
     const float lum = luma_of(x0r, x0g, x0b);
     const int pxc = min(g.px, p.W - 1), pyc = min(g.py, p.H - 1);
@@ -484,37 +485,35 @@ __global__ void __launch_bounds__(256, BDS_BWD_MINB) composite_bwd_kernel(CompPa
       }
     }
     float v_lum = 0.f;
-    const float tile_x01 = lin01((blockIdx.x % p.tile_w) * kTile, p.W);
-    const float tile_y01 = lin01(((p.row_begin + blockIdx.x / p.tile_w) % p.tile_h) * kTile, p.H);
 #pragma unroll
     for (int l = BDS_MAX_LEVELS - 1; l >= 0; --l) {
       if (l < p.bil.n_levels) {
-        const size_t goff = (size_t)g.cam * p.bil.L[l] * p.bil.GY[l] * p.bil.GX[l] * 12;
-        Tri t = tri_setup(unit_coord(x01, p.bil.GX[l]), unit_coord(y01, p.bil.GY[l]),
-                          luma_coord(lum, p.bil.L[l]), p.bil.L[l], p.bil.GY[l], p.bil.GX[l]);
-        float Al[12], dAdz[12], vAff[12];
+        const int Ll = p.bil.L[l], GYl = p.bil.GY[l], GXl = p.bil.GX[l];
+        const size_t goff = (size_t)g.cam * Ll * GYl * GXl * 12;
+        Tri t = tri_setup(unit_coord(x01, GXl), unit_coord(y01, GYl), luma_coord(lum, Ll), Ll, GYl, GXl);
+        float Al[12], dAdz[12];
         tri_fetch<true>(p.bil.grid_cl[l] + goff, t, Al, dAdz);
-#pragma unroll
-        for (int k = 0; k < 12; ++k) vAff[k] = 0.f;
-        float nr, ng, nb;
-        affine_apply_bwd(Al, xs[l][0], xs[l][1], xs[l][2], gr, gg2, gb, vAff, nr, ng, nb);
-        gr = nr; gg2 = ng; gb = nb;
-        if (t.z_inside) {
-          float sdot = 0.f;
-#pragma unroll
-          for (int k = 0; k < 12; ++k) sdot = fmaf(vAff[k], dAdz[k], sdot);
-          v_lum += sdot * (float)(p.bil.L[l] - 1);
+        const float xr = xs[l][0], xg = xs[l][1], xb = xs[l][2];
+        if (t.z_inside) {   // guidance gradient: <g (x) [x; 1], dA/dfz> (L - 1)
+          const float d0 = fmaf(dAdz[0], xr, fmaf(dAdz[1], xg, fmaf(dAdz[2], xb, dAdz[3])));
+          const float d1 = fmaf(dAdz[4], xr, fmaf(dAdz[5], xg, fmaf(dAdz[6], xb, dAdz[7])));
+          const float d2 = fmaf(dAdz[8], xr, fmaf(dAdz[9], xg, fmaf(dAdz[10], xb, dAdz[11])));
+          v_lum = fmaf(fmaf(gr, d0, fmaf(gg2, d1, gb * d2)), (float)(Ll - 1), v_lum);
         }
 #ifndef BDS_DIAG_NO_ACCUM   // timing experiments only (scripts/gpu_variants.sh): results are wrong without it
-        level_grad_accumulate(reinterpret_cast<float*>(dyn_smem), t, vAff, g.inside, tile_x01, tile_y01,
-                              p.bil.L[l], p.bil.GY[l], p.bil.GX[l], p.bil.v_grid_cl[l] + goff);
+        warp_level_accumulate(pn, t, g.inside, gr, gg2, gb, xr, xg, xb, Ll, GYl, GXl, p.bil.v_grid_cl[l] + goff);
 #else
-        if (vAff[0] == 123.456f) p.bil.v_grid_cl[l][goff] = vAff[5] + vAff[11];
+        if (gr == 123.456f) p.bil.v_grid_cl[l][goff] = gr + xr;
 #endif
+        // cotangent of the level input: A[:, :3]^T g
+        const float nr = Al[0] * gr + Al[4] * gg2 + Al[8] * gb;
+        const float ng = Al[1] * gr + Al[5] * gg2 + Al[9] * gb;
+        const float nb = Al[2] * gr + Al[6] * gg2 + Al[10] * gb;
+        gr = nr; gg2 = ng; gb = nb;
       }
     }
     gr += v_lum * kLumaR; gg2 += v_lum * kLumaG; gb += v_lum * kLumaB;
-    // the staging / window bytes are about to be overwritten by TMA (async proxy): order the
+    // the panel bytes are about to be overwritten by TMA (async proxy): order the
     // generic-proxy accesses above before it (the __syncthreads below publishes it block-wide)
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -547,8 +546,8 @@ __global__ void __launch_bounds__(256, BDS_BWD_MINB) composite_bwd_kernel(CompPa
   // this warp's deferred-reduction panel (beyond the record stages; the bilateral prologue is done with
   // the bytes it shared with them)
   BatchSmem* bs = reinterpret_cast<BatchSmem*>(dyn_smem + kBwdSmemRec) + warp;
-  bs->vc[lane] = make_float4(vC[0], vC[1], vC[2], vC[3]);
-  __syncthreads();
+  __syncthreads();   // (mode 2) the prologue's shared memory is free: panels / record stages may be written
+  bs->vc[lane] = make_float4(vC[0], vC[1], vC[2], vC[3]);   // read by this warp only (flush_batch syncs the warp)
   int block_last = -1;
 #pragma unroll
   for (int w = 0; w < 8; ++w) block_last = max(block_last, s_last[w]);
