@@ -31,7 +31,10 @@
 
 namespace bds {
 
-constexpr int kChunk = 128;                 // backward: records per TMA stage
+#ifndef BDS_BWD_CHUNK
+#define BDS_BWD_CHUNK 128
+#endif
+constexpr int kChunk = BDS_BWD_CHUNK;       // backward: records per TMA stage
 #ifndef BDS_FWD_CHUNK
 #define BDS_FWD_CHUNK 128
 #endif
@@ -317,7 +320,10 @@ __global__ void __launch_bounds__(256, BDS_FWD_MINB) composite_fwd_kernel(CompPa
 //     {m_x, m_y, m_xx, m_xy, m_yy, m_0, v_r, v_g, v_b, v_depth, sum|w g_x|, sum|w g_y|}
 // with m_ab = sum_p w_p dx_p^a dy_p^b, (dx, dy) = mean2d - pixel centre, g = (2a' dx + b' dy, b' dx + 2c' dy).
 // project_bwd_kernel turns the moments into v_mean2d / v_conic / v_opacity (all linear in them).
-constexpr int kBStages = 2;            // backward: TMA stages of kChunk records
+#ifndef BDS_BWD_STAGES
+#define BDS_BWD_STAGES 2
+#endif
+constexpr int kBStages = BDS_BWD_STAGES;   // backward: TMA stages of kChunk records
 #ifndef BDS_BATCH
 #define BDS_BATCH 16
 #endif
@@ -409,7 +415,8 @@ BDS_D void flush_batch(const BatchSmem* bs, int nb, float rx0, float ry0, float*
 
 constexpr size_t kBwdSmemRec = (size_t)kBStages * kChunk * kRecBytes;
 constexpr size_t kBwdSmemWalk = kBwdSmemRec + 8 * sizeof(BatchSmem);
-constexpr size_t kBwdSmem = kPanelBytes > kBwdSmemWalk ? kPanelBytes : kBwdSmemWalk;
+constexpr size_t kBwdSmemBilPark = kPanelBytes + (size_t)(BDS_MAX_LEVELS - 1) * 3 * 256 * sizeof(float4);   // panels + parked levels
+constexpr size_t kBwdSmem = kBwdSmemBilPark > kBwdSmemWalk ? kBwdSmemBilPark : kBwdSmemWalk;
 
 #ifndef BDS_BWD_MINB
 #define BDS_BWD_MINB 4     // resident CTAs per SM the backward is compiled for
@@ -418,7 +425,8 @@ template <int MODE>
 __global__ void __launch_bounds__(256, BDS_BWD_MINB) composite_bwd_kernel(CompParams p) {
   extern __shared__ __align__(128) unsigned char dyn_smem[];
   float4 (*srec)[kChunk * 3] = reinterpret_cast<float4 (*)[kChunk * 3]>(dyn_smem);
-  __shared__ __align__(8) uint64_t bars[kBStages];
+  __shared__ __align__(8) uint64_t bars[kBStages];    // stage filled (TMA complete_tx)
+  __shared__ __align__(8) uint64_t freed[kBStages];   // stage consumed by all eight warps
   __shared__ int s_last[8];
 
   const TileGeom g = tile_geom(p);
@@ -466,6 +474,10 @@ __global__ void __launch_bounds__(256, BDS_BWD_MINB) composite_bwd_kernel(CompPa
     const float lum = luma_of(x0r, x0g, x0b);
     const int pxc = min(g.px, p.W - 1), pyc = min(g.py, p.H - 1);
     const float x01 = lin01(pxc, p.W), y01 = lin01(pyc, p.H);   // one IEEE division per axis, not per level
+    // Forward order first: levels 0 .. n-2 are fetched ONCE (values and slab differences); what the backward order
+    // needs of them - the 3x3 part of A_l (for A_l^T g) and d_l = dA_l/dfz [x_l; 1] (for the guidance gradient) - is
+    // parked in shared memory (12 floats per level and thread) instead of being fetched a second time.
+    float4* const park = reinterpret_cast<float4*>(dyn_smem + kPanelBytes) + threadIdx.x;   // [level][3][256]
     float xs[BDS_MAX_LEVELS][3];
     {
       float r = x0r, gq = x0g, b = x0b;
@@ -473,12 +485,18 @@ __global__ void __launch_bounds__(256, BDS_BWD_MINB) composite_bwd_kernel(CompPa
       for (int l = 0; l < BDS_MAX_LEVELS; ++l) {
         if (l < p.bil.n_levels) {
           xs[l][0] = r; xs[l][1] = gq; xs[l][2] = b;
-          if (l + 1 < p.bil.n_levels) {   // the last level's output is not an input of anything
+          if (l + 1 < p.bil.n_levels) {   // the last level is fetched in the backward loop
             const float* grid = p.bil.grid_cl[l] + (size_t)g.cam * p.bil.L[l] * p.bil.GY[l] * p.bil.GX[l] * 12;
             Tri t = tri_setup(unit_coord(x01, p.bil.GX[l]), unit_coord(y01, p.bil.GY[l]),
                               luma_coord(lum, p.bil.L[l]), p.bil.L[l], p.bil.GY[l], p.bil.GX[l]);
-            float Al[12];
-            tri_fetch<false>(grid, t, Al, nullptr);
+            float Al[12], dAdz[12];
+            tri_fetch<true>(grid, t, Al, dAdz);
+            const float d0 = fmaf(dAdz[0], r, fmaf(dAdz[1], gq, fmaf(dAdz[2], b, dAdz[3])));
+            const float d1 = fmaf(dAdz[4], r, fmaf(dAdz[5], gq, fmaf(dAdz[6], b, dAdz[7])));
+            const float d2 = fmaf(dAdz[8], r, fmaf(dAdz[9], gq, fmaf(dAdz[10], b, dAdz[11])));
+            park[(l * 3 + 0) * 256] = make_float4(Al[0], Al[1], Al[2], d0);
+            park[(l * 3 + 1) * 256] = make_float4(Al[4], Al[5], Al[6], d1);
+            park[(l * 3 + 2) * 256] = make_float4(Al[8], Al[9], Al[10], d2);
             affine_apply(Al, r, gq, b);
           }
         }
@@ -491,24 +509,33 @@ __global__ void __launch_bounds__(256, BDS_BWD_MINB) composite_bwd_kernel(CompPa
         const int Ll = p.bil.L[l], GYl = p.bil.GY[l], GXl = p.bil.GX[l];
         const size_t goff = (size_t)g.cam * Ll * GYl * GXl * 12;
         Tri t = tri_setup(unit_coord(x01, GXl), unit_coord(y01, GYl), luma_coord(lum, Ll), Ll, GYl, GXl);
-        float Al[12], dAdz[12];
-        tri_fetch<true>(p.bil.grid_cl[l] + goff, t, Al, dAdz);
         const float xr = xs[l][0], xg = xs[l][1], xb = xs[l][2];
-        if (t.z_inside) {   // guidance gradient: <g (x) [x; 1], dA/dfz> (L - 1)
-          const float d0 = fmaf(dAdz[0], xr, fmaf(dAdz[1], xg, fmaf(dAdz[2], xb, dAdz[3])));
-          const float d1 = fmaf(dAdz[4], xr, fmaf(dAdz[5], xg, fmaf(dAdz[6], xb, dAdz[7])));
-          const float d2 = fmaf(dAdz[8], xr, fmaf(dAdz[9], xg, fmaf(dAdz[10], xb, dAdz[11])));
-          v_lum = fmaf(fmaf(gr, d0, fmaf(gg2, d1, gb * d2)), (float)(Ll - 1), v_lum);
+        float R[9], d0, d1, d2;   // 3x3 part of A_l, dA_l/dfz [x_l; 1]
+        if (l + 1 == p.bil.n_levels) {
+          float Al[12], dAdz[12];
+          tri_fetch<true>(p.bil.grid_cl[l] + goff, t, Al, dAdz);
+          d0 = fmaf(dAdz[0], xr, fmaf(dAdz[1], xg, fmaf(dAdz[2], xb, dAdz[3])));
+          d1 = fmaf(dAdz[4], xr, fmaf(dAdz[5], xg, fmaf(dAdz[6], xb, dAdz[7])));
+          d2 = fmaf(dAdz[8], xr, fmaf(dAdz[9], xg, fmaf(dAdz[10], xb, dAdz[11])));
+          R[0] = Al[0]; R[1] = Al[1]; R[2] = Al[2]; R[3] = Al[4]; R[4] = Al[5]; R[5] = Al[6];
+          R[6] = Al[8]; R[7] = Al[9]; R[8] = Al[10];
+        } else {
+          const float4 q0 = park[(l * 3 + 0) * 256], q1 = park[(l * 3 + 1) * 256], q2 = park[(l * 3 + 2) * 256];
+          R[0] = q0.x; R[1] = q0.y; R[2] = q0.z; d0 = q0.w;
+          R[3] = q1.x; R[4] = q1.y; R[5] = q1.z; d1 = q1.w;
+          R[6] = q2.x; R[7] = q2.y; R[8] = q2.z; d2 = q2.w;
         }
+        if (t.z_inside)   // guidance gradient: <g (x) [x; 1], dA/dfz> (L - 1)
+          v_lum = fmaf(fmaf(gr, d0, fmaf(gg2, d1, gb * d2)), (float)(Ll - 1), v_lum);
 #ifndef BDS_DIAG_NO_ACCUM   // timing experiments only (scripts/gpu_variants.sh): results are wrong without it
         warp_level_accumulate(pn, t, g.inside, gr, gg2, gb, xr, xg, xb, Ll, GYl, GXl, p.bil.v_grid_cl[l] + goff);
 #else
         if (gr == 123.456f) p.bil.v_grid_cl[l][goff] = gr + xr;
 #endif
         // cotangent of the level input: A[:, :3]^T g
-        const float nr = Al[0] * gr + Al[4] * gg2 + Al[8] * gb;
-        const float ng = Al[1] * gr + Al[5] * gg2 + Al[9] * gb;
-        const float nb = Al[2] * gr + Al[6] * gg2 + Al[10] * gb;
+        const float nr = R[0] * gr + R[3] * gg2 + R[6] * gb;
+        const float ng = R[1] * gr + R[4] * gg2 + R[7] * gb;
+        const float nb = R[2] * gr + R[5] * gg2 + R[8] * gb;
         gr = nr; gg2 = ng; gb = nb;
       }
     }
@@ -540,7 +567,7 @@ __global__ void __launch_bounds__(256, BDS_BWD_MINB) composite_bwd_kernel(CompPa
   for (int o = 16; o > 0; o >>= 1) wl = max(wl, __shfl_xor_sync(kFull, wl, o));
   if (lane == 0) s_last[warp] = wl;
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kBStages; ++s) mbar_init(&bars[s], 1);
+    for (int s = 0; s < kBStages; ++s) { mbar_init(&bars[s], 1); mbar_init(&freed[s], 8); }
     mbar_fence_init();
   }
   // this warp's deferred-reduction panel (beyond the record stages; the bilateral prologue is done with
@@ -653,13 +680,17 @@ __global__ void __launch_bounds__(256, BDS_BWD_MINB) composite_bwd_kernel(CompPa
         }
       }
     }
-    __syncthreads();
-    if (threadIdx.x == 0 && issued < nchunks) {
-      int kk = nchunks - 1 - issued;
-      int c2 = min(kChunk, n - kk * kChunk);
+    // consumer release: the warp is done with stage st.  No block barrier - the other warps run ahead by up to
+    // kBStages - 1 chunks; the refill of the stage (walk index q + kBStages) is issued by lane 0 of warp q % 8 once
+    // all eight warps have released it
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&freed[st]);
+    if (q + kBStages < nchunks && warp == (q & 7) && lane == 0) {
+      mbar_wait(&freed[st], (q / kBStages) & 1);
+      const int kk = nchunks - 1 - (q + kBStages);
+      const int c2 = min(kChunk, n - kk * kChunk);
       mbar_expect_tx(&bars[st], c2 * kRecBytes);
       bulk_g2s(&srec[st][0], p.recs + (size_t)(g.start + kk * kChunk) * 3, c2 * kRecBytes, &bars[st]);
-      ++issued;
     }
   }
   if (nb > 0) flush_batch(bs, nb, rxmin, rymin, p.v_splats);
