@@ -126,15 +126,22 @@ __device__ unsigned long long g_stats[16];
 template <int MODE>
 __global__ void __launch_bounds__(256, BDS_FWD_MINB) composite_fwd_kernel(CompParams p) {
   __shared__ __align__(128) float4 srec[kFStages][kFChunk * 3];
-  __shared__ __align__(8) uint64_t bars[kFStages];
+  __shared__ __align__(8) uint64_t bars[kFStages];    // stage filled (TMA complete_tx)
+  __shared__ __align__(8) uint64_t freed[kFStages];   // stage consumed by all eight warps
+  __shared__ int s_done_warps;                        // warps whose 32 pixels are all saturated
+  __shared__ int s_stop;                              // first chunk that will NOT be loaded (block-wide early exit)
+  __shared__ int s_decided;                           // refill decisions are taken in chunk order (no holes)
 
   const TileGeom g = tile_geom(p);
-  const int lane = threadIdx.x & 31;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int n = g.end - g.start;
   const int nchunks = (n + kFChunk - 1) / kFChunk;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kFStages; ++s) mbar_init(&bars[s], 1);
+    for (int s = 0; s < kFStages; ++s) { mbar_init(&bars[s], 1); mbar_init(&freed[s], 8); }
+    s_done_warps = 0;
+    s_stop = nchunks;
+    s_decided = 0;
     mbar_fence_init();
   }
   __syncthreads();
@@ -163,11 +170,22 @@ __global__ void __launch_bounds__(256, BDS_FWD_MINB) composite_fwd_kernel(CompPa
   float emin = g.inside ? -kLog2_255 : INFINITY;
   bool warp_done = __all_sync(kFull, !g.inside);
 
-  int waited = 0;
+  // No block barrier in the loop: a warp releases a stage when it is done with it (mbarrier `freed`) and runs ahead by
+  // up to kFStages - 1 chunks; lane 0 of warp k % 8 refills the stage with chunk k + kFStages once all eight warps
+  // have released it - unless every warp has reported its pixels saturated, in which case it lowers s_stop instead
+  // and the block leaves after the chunks already in flight (the block-wide early exit).
+  bool counted_done = false;
   for (int k = 0; k < nchunks; ++k) {
     const int st = k % kFStages;
-    mbar_wait(&bars[st], (k / kFStages) & 1);
-    waited = k + 1;
+    {   // wait for chunk k, or learn that it will never be loaded
+      bool stop = false;
+      for (unsigned it = 0;; ++it) {
+        if (mbar_try_wait(&bars[st], (k / kFStages) & 1)) break;
+        if (k >= *reinterpret_cast<volatile int*>(&s_stop)) { stop = true; break; }
+        if (it > (1u << 24)) __trap();   // a byte-count mismatch would otherwise hang the GPU
+      }
+      if (__any_sync(kFull, stop)) break;
+    }
 #ifdef BDS_STATS
     int st_cA = 0, st_cB = 0, st_q0 = 0, st_q1 = 0, st_q2 = 0, st_q3 = 0;
 #endif
@@ -258,20 +276,32 @@ __global__ void __launch_bounds__(256, BDS_FWD_MINB) composite_fwd_kernel(CompPa
       atomicAdd(&g_stats[5], (unsigned long long)max(max(st_q0, st_q1), max(st_q2, st_q3)));
     }
 #endif
-    // every warp is past stage st: it may be refilled; also the block-wide early exit
-    int all_done = __syncthreads_and(warp_done ? 1 : 0);
-    if (all_done) break;
-    if (threadIdx.x == 0 && issued < nchunks) {
-      int cnt = min(kFChunk, n - issued * kFChunk);
-      mbar_expect_tx(&bars[st], cnt * kRecBytes);
-      bulk_g2s(&srec[st][0], p.recs + (size_t)(g.start + issued * kFChunk) * 3, cnt * kRecBytes, &bars[st]);
-      ++issued;
+    if (warp_done && !counted_done) {
+      counted_done = true;
+      if (lane == 0) atomicAdd(&s_done_warps, 1);
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&freed[st]);   // release: orders the counter update above before the refill decision
+    if (k + kFStages < nchunks && warp == (k & 7) && lane == 0) {
+      mbar_wait(&freed[st], (k / kFStages) & 1);
+      for (unsigned it = 0; *reinterpret_cast<volatile int*>(&s_decided) != k; ++it)   // the decision for chunk k - 1 first
+        if (it > (1u << 24)) __trap();
+      if (*reinterpret_cast<volatile int*>(&s_stop) == nchunks) {   // nobody has stopped the loads yet
+        if (*reinterpret_cast<volatile int*>(&s_done_warps) == 8) {
+          *reinterpret_cast<volatile int*>(&s_stop) = k + kFStages;
+        } else {
+          const int kk = k + kFStages;
+          const int cnt = min(kFChunk, n - kk * kFChunk);
+          mbar_expect_tx(&bars[st], cnt * kRecBytes);
+          bulk_g2s(&srec[st][0], p.recs + (size_t)(g.start + kk * kFChunk) * 3, cnt * kRecBytes, &bars[st]);
+        }
+      }
+      __threadfence_block();
+      *reinterpret_cast<volatile int*>(&s_decided) = k + 1;
     }
   }
-  // never leave with a bulk copy still in flight into this CTA's shared memory
-  if (threadIdx.x == 0) {
-    for (int k = waited; k < issued; ++k) mbar_wait(&bars[k % kFStages], (k / kFStages) & 1);
-  }
+  // every chunk that was loaded has been waited for by every warp (a warp only leaves at a chunk >= s_stop): no bulk
+  // copy is in flight into this CTA's shared memory when it exits
 
   if (!g.inside) return;
 #if BDS_FWD_MINB <= 4
