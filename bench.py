@@ -50,6 +50,9 @@ def parse():
     ap.add_argument("--height", type=int, default=1080)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--breakdown", action="store_true", help="print the per-phase CUDA-event times of rank 0 to stderr")
+    ap.add_argument("--grad-exchange", default="splats", choices=["splats", "dense"],
+                    help="N > 1: splats = all-gather the per-splat gradient records and run the projection backward over "
+                         "all of them on every rank (default); dense = all-reduce the dense 236 B x N parameter gradients")
     ap.add_argument("--guidance", default="full", choices=["full", "lowres"],
                     help="full: guidance_factor=None fused in the composite kernel (headline); lowres: the reference's "
                          "default [4,4,2] = composite mode 1 + stand-alone low-res bilateral kernels")
@@ -332,7 +335,8 @@ def main():
         slots = [[u[c] for u in per_cam] if c in cams else None for c in range(Cn)]
         out = render.render_fused(params, vmx, Ksx, W, H, sky=sky, grid_slots=slots, bil_sizes=sizes, sh_degree=3,
                                   near_plane=0.1, row_begin=rb, row_end=re, absgrad=True, dense_info=False,
-                                  guidance_factor=(4, 4, 2) if args.guidance == "lowres" else None)
+                                  guidance_factor=(4, 4, 2) if args.guidance == "lowres" else None,
+                                  exchange_group=True if (world > 1 and args.grad_exchange == "splats") else None)
         if gt_ready is not None:  # the GT image copy ran on a side stream, overlapped with the render
             torch.cuda.current_stream().wait_event(gt_ready)
         loss = render.photometric_loss(out["rgb"], gt, out["depth"], out["opacity"], LAMBDA_D, LAMBDA_A, count=total_px,
@@ -342,7 +346,10 @@ def main():
                 loss = loss + total_variation_loss(g, TV_W * 0.5 * (sizes[lvl][0] * sizes[lvl][1] * sizes[lvl][2]) ** 0.5)
         loss.backward()
         with render._timed("allreduce"):
-            allreduce_grads([t.grad for t in leaves], flat=out["info"].get("grad_flat"))
+            if out["info"].get("grads_are_global"):   # the Gaussian gradients are already the job's: grids only
+                allreduce_grads([t.grad for t in grids])
+            else:
+                allreduce_grads([t.grad for t in leaves], flat=out["info"].get("grad_flat"))
         info_box.update(n_isect=out["info"]["n_isect"], n_visible=out["info"]["n_visible"])
         return loss
 
@@ -440,7 +447,8 @@ def main():
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": _workload_name(N, Cn, W, H, args.guidance),
-                   "parallelism": f"tile-row bands x{world}", "n_isect_rank0": I, "n_visible_rank0": Nv,
+                   "parallelism": f"tile-row bands x{world}" + ("" if world == 1 else f", gradient exchange: {args.grad_exchange}"),
+                   "n_isect_rank0": I, "n_visible_rank0": Nv,
                    "l2": "inputs larger than L2 (472 MB of parameters + images per step)",
                    "composite_fwd_ms": t_fwd, "composite_bwd_ms": t_bwd},
         "e2e": {"value": e2e_v, "unit": UNIT, "h2d_bytes_per_step": gt_host.numel() * 4 + vm.numel() * 4 + Ks.numel() * 4,

@@ -6,7 +6,7 @@ the number of cameras, tile sharding otherwise (8 GPUs, 6 cameras).  Full-resolu
 no halo.  Every rank holds a full parameter replica; after the local backward ONE all-reduce (sum)
 over a flat fp32 buffer [Gaussian grads | grid grads] gives every rank the single-GPU gradient.
 """
-from typing import List, Sequence, Tuple
+from typing import List, Optional, Sequence, Tuple
 
 import torch
 
@@ -68,3 +68,50 @@ def allreduce_grads(tensors: Sequence[torch.Tensor], group=None, flat: torch.Ten
         n = g.numel()
         g.copy_(flat[off:off + n].view_as(g))
         off += n
+
+
+# ---- gradient exchange in SPLAT space ---------------------------------------------------------------------------------
+# The dense parameter gradient of the Gaussians is 236 B x N per rank (472 MB at 2 M Gaussians) and its all-reduce is
+# the fixed cost that bounds strong scaling.  What a rank's backward actually produces is far smaller: one 48-byte
+# gradient record (the pixel moments of composite_bwd) per splat VISIBLE in its band, next to the 48-byte forward
+# record of that splat.  Every parameter gradient is a linear function of those records (project_bwd), so instead of
+# reducing 472 MB the ranks ALL-GATHER the records (96 B x visible splats, about 4 x less data and one direction
+# instead of reduce-scatter + all-gather) and each rank runs the projection backward over all of them.  A splat that
+# reaches two bands simply appears twice, with partial moments: the projection backward is linear in them.
+def gather_splat_counts(n_local: int, device, group=None) -> Tuple[List[int], torch.Tensor]:
+    """All ranks' record counts: a host list (sizes the gather buffers) and the device total (int32[1], what
+    bds_project_bwd reads as counters[0])."""
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    mine = torch.tensor([n_local], device=device, dtype=torch.int64)
+    every = torch.empty(world, device=device, dtype=torch.int64)
+    dist.all_gather_into_tensor(every, mine, group=group)
+    return [int(v) for v in every.tolist()], every.sum().to(torch.int32).reshape(1)
+
+
+def allgather_rows(local: torch.Tensor, counts: Sequence[int], group=None) -> torch.Tensor:
+    """Concatenation over ranks of the first counts[r] rows of every rank's ``local`` ([>= counts[rank], K])."""
+    import torch.distributed as dist
+
+    rank = dist.get_rank(group)
+    K = local.shape[1]
+    total = int(sum(counts))
+    out = torch.empty(max(total, 1), K, device=local.device, dtype=local.dtype)
+    mine = local[:counts[rank]]
+    if dist.get_backend(group) == "nccl":
+        # uneven all-gather: NCCL runs it as one grouped launch, every rank writes straight into its slice
+        pieces = list(out[:total].split(list(counts)))
+        dist.all_gather(pieces, mine.contiguous(), group=group)
+        return out
+    # portable path (gloo: equal sizes only): pad to the longest piece, then compact
+    m = max(max(counts), 1)
+    padded = torch.zeros(m, K, device=local.device, dtype=local.dtype)
+    padded[:counts[rank]] = mine
+    every = [torch.empty_like(padded) for _ in counts]
+    dist.all_gather(every, padded, group=group)
+    off = 0
+    for r, c in enumerate(counts):
+        out[off:off + c] = every[r][:c]
+        off += c
+    return out

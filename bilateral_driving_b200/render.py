@@ -74,6 +74,10 @@ class RenderCfg:
     absgrad: bool = False
     dense_info: bool = True    # write gsplat-shaped means2d / depths / conics
     splat_capacity: Optional[int] = None
+    # multi-GPU (dist.py): exchange the per-splat gradient records instead of all-reducing the dense parameter
+    # gradients - the backward all-gathers them over this process group (True = the default group) and runs the
+    # projection backward over every rank's records, so the returned Gaussian gradients are already the job's
+    exchange_group: object = None
 
     def tiles(self):
         return (self.width + TILE - 1) // TILE, (self.height + TILE - 1) // TILE
@@ -193,6 +197,14 @@ class _RenderFn(torch.autograd.Function):
         n_isect, n_slots, overflow = int(h_stats[0]), int(h_counters[0]), int(h_counters[1])
         if overflow:
             raise BdsError(f"splat capacity {cap} exceeded ({n_slots} visible splats); raise RenderCfg.splat_capacity")
+        ctx.exchange = None
+        if cfg.exchange_group is not None:
+            from . import dist as D
+            if cfg.dense_info:
+                raise BdsError("exchange_group needs dense_info=False (the dense densification taps are per rank)")
+            grp = None if cfg.exchange_group is True else cfg.exchange_group
+            counts, total_dev = D.gather_splat_counts(n_slots, dev, grp)
+            ctx.exchange = (grp, counts, total_dev)
         sorted_splats = torch.empty(max(n_isect, 1), 12, **f32)
         ws1 = torch.empty(int(lib.bds_bin_sort_workspace_bytes(C.byref(d), C.c_int64(n_isect))), device=dev,
                           dtype=torch.uint8)
@@ -288,6 +300,17 @@ class _RenderFn(torch.autograd.Function):
         v_means, v_quats, v_scales, v_opac = views["means"], views["quats"], views["scales"], views["opac"]
         v_colors, v_fdc, v_frest = views.get("colors"), views.get("fdc"), views.get("frest")
         ctx.holder["grad_flat"] = flat
+        rec_fwd, rec_bwd, n_counter = splats, v_splats, counters
+        if ctx.exchange is not None:
+            # every rank's (forward record, gradient record) pairs; the projection backward below then produces the
+            # gradient of the WHOLE job on every rank (no dense all-reduce of the Gaussian gradients afterwards)
+            from . import dist as D
+            grp, counts, total_dev = ctx.exchange
+            with _timed("exchange"):
+                rec_fwd = D.allgather_rows(splats, counts, grp)
+                rec_bwd = D.allgather_rows(v_splats, counts, grp)
+            n_counter = total_dev
+            ctx.holder["grads_are_global"] = True
         v_view = torch.zeros_like(viewmats) if need[9] else None
         want_taps = cfg.dense_info
         v_m2d = torch.zeros(Cn, N, 2, **f32) if want_taps else None
@@ -296,11 +319,20 @@ class _RenderFn(torch.autograd.Function):
         if v_means2d_extra is not None and v_means2d_extra.numel() > 0:
             extra = v_means2d_extra.contiguous().float()
         with _timed("project_bwd"):
-            check(lib.bds_project_bwd(C.byref(d), ptr(means), ptr(quats), ptr(scales), ptr(opacities), ptr(colors),
-                                      ctx.colors_per_cam, ptr(fdc), ptr(frest), ptr(viewmats), ptr(Ks), ptr(splats),
-                                      ptr(counters), ptr(v_splats), ptr(extra), NULL, NULL, ptr(v_means), ptr(v_quats),
-                                      ptr(v_scales), ptr(v_opac), ptr(v_colors), ptr(v_fdc), ptr(v_frest), ptr(v_view),
-                                      ptr(v_m2d), ptr(absg), st), "bds_project_bwd")
+            # bds_project_bwd launches one thread per possible record of ONE rank (C x N); the gathered records of all
+            # ranks normally fit (a splat is repeated only where it reaches two bands), else they go in several calls
+            pieces = [(rec_fwd, rec_bwd, n_counter)]
+            if ctx.exchange is not None and sum(ctx.exchange[1]) > Cn * N:
+                tot, step_n = sum(ctx.exchange[1]), Cn * N
+                pieces = [(rec_fwd[o:o + step_n], rec_bwd[o:o + step_n],
+                           torch.tensor([min(step_n, tot - o)], device=dev, dtype=torch.int32))
+                          for o in range(0, tot, step_n)]
+            for pf, pb, pc in pieces:
+                check(lib.bds_project_bwd(C.byref(d), ptr(means), ptr(quats), ptr(scales), ptr(opacities), ptr(colors),
+                                          ctx.colors_per_cam, ptr(fdc), ptr(frest), ptr(viewmats), ptr(Ks), ptr(pf),
+                                          ptr(pc), ptr(pb), ptr(extra), NULL, NULL, ptr(v_means), ptr(v_quats),
+                                          ptr(v_scales), ptr(v_opac), ptr(v_colors), ptr(v_fdc), ptr(v_frest), ptr(v_view),
+                                          ptr(v_m2d), ptr(absg), st), "bds_project_bwd")
             if extra is not None and slot_of is not None:
                 check(lib.bds_project_bwd_extras(C.byref(d), ptr(means), ptr(quats), ptr(scales), ptr(viewmats), ptr(Ks),
                                                  ptr(radii), ptr(slot_of), ptr(extra), NULL, NULL, ptr(v_means),
@@ -505,7 +537,7 @@ def render_fused(params: Dict[str, torch.Tensor], viewmats, Ks, width: int, heig
                  grid_slots: Optional[Sequence[Sequence[torch.Tensor]]] = None, bil_sizes=(), sh_degree: int = 3,
                  near_plane: float = 0.1, far_plane: float = 1e10, radius_clip: float = 0.0, absgrad: bool = True,
                  row_begin: int = 0, row_end: int = -1, activated: bool = False, dense_info: bool = False,
-                 antialiased: bool = False, guidance_factor=None):
+                 antialiased: bool = False, guidance_factor=None, exchange_group=None):
     """One fused pass of the hot path for C cameras.
 
     ``params``: ``_means [N,3], _scales (log) [N,3], _quats [N,4], _opacities (logit) [N] or [N,1],
@@ -517,6 +549,9 @@ def render_fused(params: Dict[str, torch.Tensor], viewmats, Ks, width: int, heig
     kernel stops after the glue (mode 1) and the low-resolution-guidance kernels of ``bilateral.py`` finish the
     chain per camera (the low-res guidance of a pixel needs neighbours outside its tile).  Requires whole
     cameras in the band.
+    ``exchange_group`` (multi-GPU band sharding, dist.py): a process group (True = the default one) over which the
+    backward all-gathers the per-splat gradient records, so that the Gaussian gradients it returns are the WHOLE
+    job's on every rank (``info["grads_are_global"]``) and only the grid gradients remain to be all-reduced.
     Returns dict(rgb, rgb_gaussians, depth, opacity [band pixels ...], radii, info).
     """
     Cn = viewmats.shape[0]
@@ -525,7 +560,8 @@ def render_fused(params: Dict[str, torch.Tensor], viewmats, Ks, width: int, heig
     cfg = RenderCfg(width=width, height=height, near_plane=near_plane, far_plane=far_plane, radius_clip=radius_clip,
                     antialiased=antialiased, row_begin=row_begin, row_end=row_end, raw_params=not activated,
                     sh_degree=-1 if activated else sh_degree, mode=mode, channels=4, expected_depth=True,
-                    bil_sizes=tuple(tuple(s) for s in bil_sizes), absgrad=absgrad, dense_info=dense_info)
+                    bil_sizes=tuple(tuple(s) for s in bil_sizes), absgrad=absgrad, dense_info=dense_info,
+                    exchange_group=exchange_group)
     grids: List[Optional[torch.Tensor]] = []
     if mode == 2:
         assert len(grid_slots) == Cn and all(len(g) == len(bil_sizes) for g in grid_slots if g is not None)

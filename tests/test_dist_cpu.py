@@ -77,3 +77,32 @@ def test_allreduce_is_noop_without_process_group():
     t = torch.ones(3)
     allreduce_grads([t])
     assert torch.equal(t, torch.ones(3))
+
+
+def _exchange_worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from bilateral_driving_b200.dist import allgather_rows, gather_splat_counts
+
+        n_local = [5, 0, 3][rank]
+        local = torch.full((8, 12), float(rank)) + torch.arange(8)[:, None] * 0.01   # capacity 8, first n_local rows valid
+        counts, total = gather_splat_counts(n_local, torch.device("cpu"))
+        out = allgather_rows(local, counts)
+        ret[rank] = (counts, int(total), out[:sum(counts)].clone())
+    finally:
+        dist.destroy_process_group()
+
+
+def test_splat_record_exchange_gathers_uneven_pieces():
+    """dist.gather_splat_counts / allgather_rows (the splat-space gradient exchange) over gloo, world size 3, with an
+    empty rank: every rank ends with the concatenation of the valid rows of all ranks, in rank order."""
+    world = 3
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_exchange_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
+    for r in range(world):
+        counts, total, out = ret[r]
+        assert counts == [5, 0, 3] and total == 8 and out.shape == (8, 12)
+        assert torch.allclose(out[:5, 0], 0.0 + torch.arange(5) * 0.01) and torch.allclose(out[5:, 0], 2.0 + torch.arange(3) * 0.01)
