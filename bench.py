@@ -50,9 +50,11 @@ def parse():
     ap.add_argument("--height", type=int, default=1080)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--breakdown", action="store_true", help="print the per-phase CUDA-event times of rank 0 to stderr")
-    ap.add_argument("--grad-exchange", default="splats", choices=["splats", "dense"],
-                    help="N > 1: splats = all-gather the per-splat gradient records and run the projection backward over "
-                         "all of them on every rank (default); dense = all-reduce the dense 236 B x N parameter gradients")
+    ap.add_argument("--grad-exchange", default="dense", choices=["splats", "dense"],
+                    help="N > 1: dense = ONE all-reduce of the flat 236 B x N parameter gradient (default: NCCL runs it as "
+                         "NVLS in-switch reduction, 1.2 ms at 8 GPUs); splats = all-gather the per-splat gradient records "
+                         "and run the projection backward over all of them on every rank (less data, but the uneven "
+                         "all-gather measured slower: 3.89 vs 3.04 ms/step at 8 GPUs, profiles/r02_bench_n8_*.json)")
     ap.add_argument("--guidance", default="full", choices=["full", "lowres"],
                     help="full: guidance_factor=None fused in the composite kernel (headline); lowres: the reference's "
                          "default [4,4,2] = composite mode 1 + stand-alone low-res bilateral kernels")
