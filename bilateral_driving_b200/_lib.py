@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, os.environ.get("BDS_LIB", "libbds_b200.so"))
 MAX_LEVELS = 4
 TILE = 16
 COUNTERS_LEN = 4096  # BDS_COUNTERS_LEN (include/bds.h)
-ABI_VERSION = 3      # BDS_ABI_VERSION: 3 = + bds_project_bwd_extras (2: moment-form gradient records, masked composite)
+ABI_VERSION = 4      # BDS_ABI_VERSION: 4 = + bds_densify_stats; 3 = + bds_project_bwd_extras; 2 = moment-form gradient records
 SPLAT_FLOATS = 12
 
 
@@ -92,7 +92,7 @@ ABI_SYMBOLS = (
     "bds_bin_count_workspace_bytes", "bds_bin_count", "bds_bin_sort_workspace_bytes", "bds_bin_sort",
     "bds_composite_workspace_bytes", "bds_composite_fwd", "bds_composite_bwd",
     "bds_slot_keep", "bds_composite_fwd_masked",
-    "bds_loss_fwd_bwd",
+    "bds_loss_fwd_bwd", "bds_densify_stats",
 )
 
 

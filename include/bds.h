@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define BDS_ABI_VERSION 3
+#define BDS_ABI_VERSION 4
 #define BDS_MAX_LEVELS 4
 #define BDS_COUNTERS_LEN 4096  /* int32 entries of the projection counters buffer */
 #define BDS_TILE 16
@@ -231,6 +231,17 @@ int bds_project_bwd_extras(const bds_render_desc* d, const float* means, const f
                            const float* viewmats, const float* Ks, const int32_t* radii, const int32_t* slot_of,
                            const float* v_means2d_extra, const float* v_depths_extra, const float* v_conics_extra,
                            float* v_means, float* v_quats, float* v_scales, float* v_viewmats, bds_stream_t stream);
+
+/* Densification statistics of one step in one launch.  Replaces VanillaGaussians.after_train
+ * (models/gaussians/vanilla.py:163-191) as called by BasicTrainer.postprocess_per_train_step (base.py:279-297):
+ * radii [n] int32 (info["radii"] of the step's camera), xys_grad [n,2] (info["means2d"].absgrad or .grad; scaled here
+ * by scale_x / scale_y - pass 1 when the caller already applied base.py:285-286), last_size = max(W, H).
+ * first != 0 (the statistics were reset to None, vanilla.py:172-175): xys_grad_norm = |xys_grad| for EVERY Gaussian,
+ * vis_counts = 1; else for visible Gaussians (radii > 0): xys_grad_norm += |xys_grad|, vis_counts += 1.
+ * Always for visible Gaussians: max_2dsize = max(max_2dsize, radii / last_size).  All three [n] fp32, updated in place. */
+int bds_densify_stats(int64_t n, const int32_t* radii, const float* xys_grad, float scale_x, float scale_y,
+                      float last_size, int first, float* xys_grad_norm, float* vis_counts, float* max_2dsize,
+                      bds_stream_t stream);
 
 /* Fused photometric loss used by the benchmark step: mean((rgb-gt)^2) +
  * lambda_d*mean(depth) + lambda_a*mean(alpha); writes the cotangents and ACCUMULATES the loss. */

@@ -27,11 +27,12 @@ def _reference_arm(w1, single=False):
     return tr
 
 
-def _fused_arm(ref_trainer, device, w1, single=False, guidance_factor="default"):
+def _fused_arm(ref_trainer, device, w1, single=False, guidance_factor="default", fused_gaussians=False):
     TH.load_scene_graph()
     import bilateral_driving_b200.trainer as T
 
-    cfg = TH.make_cfg(TH.OUR_SINGLE if single else TH.OUR_MS, w1=w1, single=single)
+    bg = "bilateral_driving_b200.gaussians.FusedVanillaGaussians" if fused_gaussians else "models.gaussians.VanillaGaussians"
+    cfg = TH.make_cfg(TH.OUR_SINGLE if single else TH.OUR_MS, w1=w1, single=single, background_type=bg)
     cfg.trainer.type = "bilateral_driving_b200.trainer.FusedMultiTrainer"
     tr = TH.build_trainer(T.FusedMultiTrainer, cfg, torch.device(device))
     for m in tr.models.values():
@@ -171,7 +172,7 @@ def test_fused_trainer_on_gpu_against_reference_trainer(guidance):
         aff = ref.models["Affine"]
         orig = aff.forward
         aff.forward = lambda rgb, infos, guidance_factor=None: orig(rgb, infos, guidance_factor=None)
-    fused = _fused_arm(ref, "cuda", 0.5, guidance_factor=guidance)
+    fused = _fused_arm(ref, "cuda", 0.5, guidance_factor=guidance, fused_gaussians=True)
     image_infos, cam_infos = TH.make_batch("cpu")
     g_infos, g_cam = TH.make_batch("cuda")
     o_ref, l_ref = _step(ref, image_infos, cam_infos, fix_reference_bug=True)
@@ -179,6 +180,20 @@ def test_fused_trainer_on_gpu_against_reference_trainer(guidance):
     keep = ~ref.info["ambiguous"][0]
     _compare(ref, fused, o_ref, o_fu, l_ref, l_fu, tol_img=2e-5, tol_loss=2e-4, tol_grad=2e-3, keep=keep)
     assert "_bds_cache" in fused.info and fused.info["_bds_cache"] is not None
+    # densification bookkeeping (base.py:279-297 -> vanilla.py:151-191): the reference's after_train on the CPU against
+    # FusedVanillaGaussians.after_train (one bds_densify_stats launch), first step (statistics None) and a second one
+    for tr in (ref, fused):
+        tr.initialize_optimizer()
+    for rep in range(2):
+        ref.postprocess_per_train_step(ref.step)
+        fused.postprocess_per_train_step(fused.step)
+        a, b = ref.models["Background"], fused.models["Background"]
+        assert type(b).__name__ == "FusedVanillaGaussians"
+        for name in ("xys_grad_norm", "vis_counts", "max_2Dsize"):
+            want, got = getattr(a, name), getattr(b, name).cpu()
+            assert want.shape == got.shape, name
+            assert float((got - want).abs().max()) <= 2e-3 * float(want.abs().max().clamp(min=1e-12)), (name, rep)
+        assert float(b.vis_counts.max()) == rep + 1.0
     # eval: masked re-renders reuse the sorted lists of the fused render
     from bilateral_driving_b200 import _lib
 

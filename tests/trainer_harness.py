@@ -47,7 +47,7 @@ def load_scene_graph():
     return load_reference_trainers(os.path.join(ROOT, "oracle", "gsplat_seam"))
 
 
-def make_cfg(affine_type, w1=0.0, grid=None, single=False):
+def make_cfg(affine_type, w1=0.0, grid=None, single=False, background_type="models.gaussians.VanillaGaussians"):
     from oracle.ref_stubs import Cfg
 
     lr = dict(lr=6.0e-4, lr_final=3e-5, warmup_steps=1000, lr_pre_warmup=0)
@@ -74,7 +74,7 @@ def make_cfg(affine_type, w1=0.0, grid=None, single=False):
                 cull_alpha_thresh=0.005, cull_scale_thresh=0.5, cull_screen_size=0.15, split_screen_size=0.05,
                 stop_screen_size_at=4000, stop_split_at=15000, sh_degree=3)),
         model=dict(
-            Background=dict(type="models.gaussians.VanillaGaussians", reg=dict(sharp_shape_reg=None)),
+            Background=dict(type=background_type, reg=dict(sharp_shape_reg=None)),
             Sky=dict(type="trainer_harness.GradientSky", params=dict(), optim=dict(all=dict(lr=0.01))),
             Affine=affine,
             CamPose=dict(type="models.modules.CameraOptModule", optim=dict(all=dict(lr=1e-5, weight_decay=1e-6))))))
@@ -91,7 +91,7 @@ def build_trainer(cls, cfg, device):
     return trainer
 
 
-def init_scene(trainer, device, n=1500, sh_step=3000):
+def init_scene(trainer, device, n=1500, sh_step=3001):   # 3001: SH degree 3, and not a refinement step (% 100)
     """Same synthetic Gaussians as the rasteriser golden scene; grids perturbed off identity; CamPose off zero."""
     from bilateral_driving_b200 import synthetic as S
 
