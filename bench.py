@@ -299,7 +299,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     from bilateral_driving_b200 import _lib, render, synthetic as S
-    from bilateral_driving_b200.bilateral import total_variation_loss
+    from bilateral_driving_b200.bilateral import total_variation_loss_levels
     from bilateral_driving_b200.dist import allreduce_grads, band_for_rank, band_pixel_rows, cameras_in_band
 
     N, Cn, W, H = args.n_gauss, args.cams, args.width, args.height
@@ -343,9 +343,9 @@ def main():
             torch.cuda.current_stream().wait_event(gt_ready)
         loss = render.photometric_loss(out["rgb"], gt, out["depth"], out["opacity"], LAMBDA_D, LAMBDA_A, count=total_px,
                                        unit_cotangent=True)
-        if rank == 0:  # TV over all image slots: computed once per job, not per band
-            for lvl, g in enumerate(grids):
-                loss = loss + total_variation_loss(g, TV_W * 0.5 * (sizes[lvl][0] * sizes[lvl][1] * sizes[lvl][2]) ** 0.5)
+        if rank == 0:  # TV over all image slots (all levels in one launch): computed once per job, not per band
+            loss = loss + total_variation_loss_levels(
+                grids, [TV_W * 0.5 * (sx * sy * sl) ** 0.5 for sx, sy, sl in sizes])
         loss.backward()
         with render._timed("allreduce"):
             if out["info"].get("grads_are_global"):   # the Gaussian gradients are already the job's: grids only

@@ -86,7 +86,7 @@ lib = _load()
 ABI_SYMBOLS = (
     "bds_last_error", "bds_abi_version", "bds_device_arch", "bds_launch_count",
     "bds_bilateral_workspace_bytes", "bds_bilateral_fwd", "bds_bilateral_bwd",
-    "bds_bilagrid_slice_fwd", "bds_bilagrid_slice_bwd", "bds_tv_fwd_bwd",
+    "bds_bilagrid_slice_fwd", "bds_bilagrid_slice_bwd", "bds_tv_fwd_bwd", "bds_tv_levels_fwd_bwd",
     "bds_sh_fwd", "bds_sh_bwd",
     "bds_project_fwd", "bds_project_bwd", "bds_project_bwd_extras",
     "bds_bin_count_workspace_bytes", "bds_bin_count", "bds_bin_sort_workspace_bytes", "bds_bin_sort",

@@ -120,38 +120,49 @@ class _SliceFn(torch.autograd.Function):
 
 
 class _TVFn(torch.autograd.Function):
+    """sum_l weight_l * tv(grids_l) for any number of levels in ONE launch, which also writes the gradients (unit
+    cotangent); the backward only scales them by the upstream cotangent (which stays on the device)."""
+
     @staticmethod
     @device_scoped
-    def forward(ctx, grids, weight):
-        require_cuda(grids)
-        g = grids.contiguous().float()
-        N, _, L, GY, GX = g.shape
-        loss = torch.zeros((), device=g.device, dtype=torch.float32)
-        check(lib.bds_tv_fwd_bwd(ptr(g), N, L, GY, GX, C.c_float(weight), C.c_float(0.0), ptr(loss), C.c_void_p(0),
-                                 stream_ptr()), "bds_tv_fwd_bwd")
-        ctx.save_for_backward(g)
-        ctx.weight = weight
+    def forward(ctx, weights, *grids):
+        require_cuda(*grids)
+        gs = [g.contiguous().float() for g in grids]
+        n = len(gs)
+        loss = torch.zeros((), device=gs[0].device, dtype=torch.float32)
+        need = [g.requires_grad for g in grids]
+        v_gs = [torch.zeros_like(g) if nd else None for g, nd in zip(gs, need)]
+        arr = lambda vals, ct: (ct * n)(*vals)  # noqa: E731
+        check(lib.bds_tv_levels_fwd_bwd(n, ptr_array(gs), arr([g.shape[0] for g in gs], C.c_int),
+                                        arr([g.shape[2] for g in gs], C.c_int), arr([g.shape[3] for g in gs], C.c_int),
+                                        arr([g.shape[4] for g in gs], C.c_int), arr([float(w) for w in weights], C.c_float),
+                                        C.c_float(1.0), ptr(loss), ptr_array(v_gs), stream_ptr()), "bds_tv_levels_fwd_bwd")
+        ctx.v_gs = v_gs
         return loss
 
     @staticmethod
     @device_scoped
     def backward(ctx, v_loss):
-        (g,) = ctx.saved_tensors
-        N, _, L, GY, GX = g.shape
-        v_g = torch.zeros_like(g)
-        scratch = torch.zeros((), device=g.device, dtype=torch.float32)
-        # the upstream cotangent stays on the device (reading it here would stall the host at the very start of the
-        # backward, before the long kernels are queued): unit cotangent in the kernel, scaled afterwards
-        check(lib.bds_tv_fwd_bwd(ptr(g), N, L, GY, GX, C.c_float(ctx.weight), C.c_float(1.0),
-                                 ptr(scratch), ptr(v_g), stream_ptr()), "bds_tv_fwd_bwd")
-        return v_g.mul_(v_loss.to(v_g.dtype)), None
+        live = [v for v in ctx.v_gs if v is not None]
+        if live:
+            torch._foreach_mul_(live, v_loss.to(live[0].dtype))
+        return (None, *ctx.v_gs)
 
 
 def total_variation_loss(x, weight: float = 1.0):
     """lib_bilagrid.py:152-168 for x of shape (B, 12, L, GY, GX)."""
     if x.dim() != 5 or x.shape[1] != 12:
         raise ValueError("total_variation_loss expects a (B,12,L,H,W) bilateral grid tensor")
-    return _TVFn.apply(x, float(weight))
+    return _TVFn.apply((float(weight),), x)
+
+
+def total_variation_loss_levels(grids, weights):
+    """sum_l weights[l] * total_variation_loss(grids[l]) in one launch (modules.py:466-472)."""
+    grids = list(grids)
+    for x in grids:
+        if x.dim() != 5 or x.shape[1] != 12:
+            raise ValueError("total_variation_loss expects (B,12,L,H,W) bilateral grid tensors")
+    return _TVFn.apply(tuple(float(w) for w in weights), *grids)
 
 
 def color_affine_transform(affine_mats, rgb):
@@ -339,10 +350,7 @@ class MultiScaleBilateralAffineTransform(nn.Module):
         return [getattr(self, f"bil_grids{i}") for i in range(len(self.grid_size))]
 
     def tv_loss(self):
-        loss = 0
-        for i, bg in enumerate(self._levels()):
-            loss = loss + total_variation_loss(bg.grids, self.tv_weight[i])
-        return loss
+        return total_variation_loss_levels([bg.grids for bg in self._levels()], self.tv_weight)
 
     def _slots(self, image_infos):
         assert "img_idx" in image_infos

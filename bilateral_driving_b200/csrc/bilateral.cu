@@ -372,13 +372,22 @@ __global__ void slice_generic_bwd_kernel(const float* __restrict__ grid, int L, 
 
 // TV loss (lib_bilagrid.py:152-168): sum over the 3 spatial axes of mean squared forward
 // differences, divided by the batch size N.  One thread per element; block reduction; one atomic.
-__global__ void __launch_bounds__(256) tv_kernel(const float* __restrict__ g, int N, int L, int GY, int GX,
-                                                 float weight, float v_loss, float* __restrict__ loss,
-                                                 float* __restrict__ v_g) {
+// All levels of a multi-scale module (modules.py:466-472) go in ONE launch: blockIdx.y = level.
+struct TvLevels {
+  const float* g[BDS_MAX_LEVELS];
+  float* v_g[BDS_MAX_LEVELS];
+  int N[BDS_MAX_LEVELS], L[BDS_MAX_LEVELS], GY[BDS_MAX_LEVELS], GX[BDS_MAX_LEVELS];
+  float weight[BDS_MAX_LEVELS];
+};
+__global__ void __launch_bounds__(256) tv_kernel(TvLevels lv, float v_loss, float* __restrict__ loss) {
+  const int l = blockIdx.y;
+  const float* __restrict__ g = lv.g[l];
+  float* __restrict__ v_g = lv.v_g[l];
+  const int N = lv.N[l], L = lv.L[l], GY = lv.GY[l], GX = lv.GX[l];
+  const float weight = lv.weight[l];
   size_t total = (size_t)N * 12 * L * GY * GX;
-  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   float acc = 0.f;
-  if (idx < total) {
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
     int x = idx % GX;
     size_t r = idx / GX;
     int y = r % GY;
@@ -389,15 +398,15 @@ __global__ void __launch_bounds__(256) tv_kernel(const float* __restrict__ g, in
     float cz = fmaxf(12.f * (L - 1) * GY * GX, 1.f), cy = fmaxf(12.f * L * (GY - 1) * GX, 1.f),
           cx = fmaxf(12.f * L * GY * (GX - 1), 1.f);
     float sN = weight / (float)N;
-    float grad = 0.f;
-    if (x + 1 < GX) { float d = g[idx + 1] - v; acc += d * d / cx; grad -= 2.f * d / cx; }
+    float grad = 0.f, a = 0.f;
+    if (x + 1 < GX) { float d = g[idx + 1] - v; a += d * d / cx; grad -= 2.f * d / cx; }
     if (x > 0) { float d = v - g[idx - 1]; grad += 2.f * d / cx; }
-    if (y + 1 < GY) { float d = g[idx + GX] - v; acc += d * d / cy; grad -= 2.f * d / cy; }
+    if (y + 1 < GY) { float d = g[idx + GX] - v; a += d * d / cy; grad -= 2.f * d / cy; }
     if (y > 0) { float d = v - g[idx - GX]; grad += 2.f * d / cy; }
     size_t sz = (size_t)GY * GX;
-    if (z + 1 < L) { float d = g[idx + sz] - v; acc += d * d / cz; grad -= 2.f * d / cz; }
+    if (z + 1 < L) { float d = g[idx + sz] - v; a += d * d / cz; grad -= 2.f * d / cz; }
     if (z > 0) { float d = v - g[idx - sz]; grad += 2.f * d / cz; }
-    acc *= sN;
+    acc += a * sN;
     if (v_g) v_g[idx] += v_loss * sN * grad;
   }
   __shared__ float red[8];
@@ -569,8 +578,31 @@ extern "C" int bds_tv_fwd_bwd(const float* grids, int N, int L, int GY, int GX, 
   BDS_REQUIRE(N >= 1 && L >= 1 && GY >= 1 && GX >= 1, "tv: bad sizes");
   BDS_REQUIRE(grids && loss, "tv: null pointer");
   size_t total = (size_t)N * 12 * L * GY * GX;
-  tv_kernel<<<ceil_div((int64_t)total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(grids, N, L, GY, GX, weight, v_loss,
-                                                                                        loss, v_grids);
+  TvLevels lv{};
+  lv.g[0] = grids; lv.v_g[0] = v_grids; lv.N[0] = N; lv.L[0] = L; lv.GY[0] = GY; lv.GX[0] = GX; lv.weight[0] = weight;
+  tv_kernel<<<dim3(ceil_div((int64_t)total, 256), 1), 256, 0, static_cast<cudaStream_t>(stream)>>>(lv, v_loss, loss);
+  BDS_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int bds_tv_levels_fwd_bwd(int n_levels, const float* const* host_grids, const int* N, const int* L,
+                                     const int* GY, const int* GX, const float* weights, float v_loss, float* loss,
+                                     float* const* host_v_grids, bds_stream_t stream) {
+  BDS_REQUIRE(n_levels >= 1 && n_levels <= BDS_MAX_LEVELS, "tv_levels: 1..%d levels", BDS_MAX_LEVELS);
+  BDS_REQUIRE(host_grids && N && L && GY && GX && weights && loss, "tv_levels: null pointer");
+  TvLevels lv{};
+  size_t most = 0;
+  for (int l = 0; l < n_levels; ++l) {
+    BDS_REQUIRE(host_grids[l] && N[l] >= 1 && L[l] >= 1 && GY[l] >= 1 && GX[l] >= 1, "tv_levels: bad level %d", l);
+    lv.g[l] = host_grids[l]; lv.v_g[l] = host_v_grids ? host_v_grids[l] : nullptr;
+    lv.N[l] = N[l]; lv.L[l] = L[l]; lv.GY[l] = GY[l]; lv.GX[l] = GX[l]; lv.weight[l] = weights[l];
+    size_t total = (size_t)N[l] * 12 * L[l] * GY[l] * GX[l];
+    most = total > most ? total : most;
+  }
+  // blockIdx.y = level; the x extent covers the largest level (grid-stride loop, smaller levels leave early)
+  int bx = ceil_div((int64_t)most, 256);
+  if (bx > 148 * 16) bx = 148 * 16;
+  tv_kernel<<<dim3(bx, n_levels), 256, 0, static_cast<cudaStream_t>(stream)>>>(lv, v_loss, loss);
   BDS_CHECK_LAUNCH();
   return 0;
 }

@@ -83,6 +83,13 @@ int bds_bilagrid_slice_bwd(const float* grid, int L, int GY, int GX, int n, cons
 int bds_tv_fwd_bwd(const float* grids, int N, int L, int GY, int GX, float weight, float v_loss,
                    float* loss, float* v_grids, bds_stream_t stream);
 
+/* The same for ALL levels of a multi-scale module in ONE launch (modules.py:466-472 loops over the levels):
+ * loss += sum_l weights[l] * tv(grids[l]); host_grids / host_v_grids: host arrays of n_levels device pointers
+ * (v_grids may be NULL = loss only, or hold NULLs); N, L, GY, GX, weights: host arrays of n_levels entries. */
+int bds_tv_levels_fwd_bwd(int n_levels, const float* const* host_grids, const int* N, const int* L, const int* GY,
+                          const int* GX, const float* weights, float v_loss, float* loss, float* const* host_v_grids,
+                          bds_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * Spherical harmonics.  Replaces gsplat.cuda._wrapper.spherical_harmonics as called at
  * models/gaussians/vanilla.py:383-389 (import seam models/gaussians/basics.py:15).

@@ -68,6 +68,7 @@ def _patch_cpu(monkeypatch):
     monkeypatch.setattr(R, "render_fused", TH.oracle_render_fused)
     monkeypatch.setattr(BL, "multiscale_bilateral", TH.oracle_multiscale_bilateral)
     monkeypatch.setattr(BL, "total_variation_loss", TH.oracle_tv)
+    monkeypatch.setattr(BL, "total_variation_loss_levels", TH.oracle_tv_levels)
 
 
 def _compare(ref, fused, o_ref, o_fu, l_ref, l_fu, tol_img, tol_loss, tol_grad, keep=None):

@@ -194,3 +194,7 @@ def oracle_tv(x, weight=1.0):
     from oracle import bilateral_ref as B
 
     return weight * B.total_variation_loss(x)
+
+
+def oracle_tv_levels(grids, weights):
+    return sum(oracle_tv(g, w) for g, w in zip(grids, weights))
