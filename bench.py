@@ -32,10 +32,22 @@ if ROOT not in sys.path:
 METRIC = "fwd+bwd Mpix/s at 2M Gaussians, 6x1080p; achieved HBM GB/s vs B200 peak"
 UNIT = "Mpix/s"
 LAMBDA_D, LAMBDA_A, TV_W = 0.01, 0.05, 1.0
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the roofline kernel on the default workload
-# (2 M Gaussians, 6 x 1920x1080, N=1), from the `ncu --set full` capture summarised in
-# profiles/r01_ncu_full_key_metrics.txt (0.674020 GB read + 0.425888 GB written).  Reported only for that workload.
-NCU_TRAFFIC_BYTES = {"full": 674_020_000 + 425_887_744}
+
+
+def ncu_profile_numbers(kernel_key):
+    """DRAM traffic and executed warp-instructions of ONE launch of the roofline kernel on the default workload, from
+    the committed parser output of the round's `ncu --set full` capture (scripts/ncu_traffic.py ->
+    profiles/ncu_traffic.json).  None when the file or the kernel is missing."""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        doc = json.load(open(path))
+        for name, k in doc["kernels"].items():
+            if kernel_key in name:
+                return {"traffic": k["dram_bytes_read"] + k["dram_bytes_write"], "warp_instructions": k["warp_instructions"],
+                        "source": f"profiles/ncu_traffic.json <- {doc.get('source', '')}"}
+    except Exception:
+        pass
+    return None
 
 
 def parse():
@@ -249,15 +261,18 @@ def run_reference(args):
         "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         # same workload name as the GPU arm; what a step of THIS arm covers is the bounded sample below
-        "config": {"workload": _workload_name(args.n_gauss, args.cams, W, H, args.guidance), "sample": sample},
+        "config": {"workload": _workload_name(args.n_gauss, args.cams, W, H, args.guidance, args.gpus), "sample": sample},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": box["kind"],
                          "source": box["source"], "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     })
 
 
-def _workload_name(n_gauss, cams, W, H, guidance):
-    return (f"configs[2]: {n_gauss} synthetic Gaussians, {cams}-cam nuScenes-shaped rig {W}x{H}, 3-scale grids 8/16/32 "
+def _workload_name(n_gauss, cams, W, H, guidance, world=1):
+    """BASELINE.json config the run corresponds to."""
+    idx = {(500_000, 1): 1, (2_000_000, 6): 2 if world == 1 else 3, (8_000_000, 6): 4}.get((n_gauss, cams))
+    tag = f"configs[{idx}]" if idx is not None and (W, H) == (1920, 1080) else "custom"
+    return (f"{tag}: {n_gauss} synthetic Gaussians, {cams}-cam nuScenes-shaped rig {W}x{H}, 3-scale grids 8/16/32 "
             f"{'full-res guidance (fused)' if guidance == 'full' else 'guidance_factor=[4,4,2] (two-phase)'}, SH degree 3")
 
 
@@ -448,7 +463,8 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": _workload_name(N, Cn, W, H, args.guidance),
+        "config": {"workload": _workload_name(N, Cn, W, H, args.guidance, world),
+                   "gsplat": "not installed on the B200 box (profiles/r02_gsplat_probe.txt): no GPU reference comparator",
                    "parallelism": f"tile-row bands x{world}" + ("" if world == 1 else f", gradient exchange: {args.grad_exchange}"),
                    "n_isect_rank0": I, "n_visible_rank0": Nv,
                    "l2": "inputs larger than L2 (472 MB of parameters + images per step)",
@@ -457,12 +473,27 @@ def main():
                 "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"bound": "hbm", "kernel": "composite_fwd_kernel<2> (fused composite + glue + bilateral)" if args.guidance == "full" else "composite_fwd_kernel<1> (composite + glue)",
-                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
-                     "algorithmic_bytes": b_fwd,
-                     "traffic": NCU_TRAFFIC_BYTES.get(args.guidance) if default_workload else None,
-                     "traffic_source": "ncu --set full, profiles/r01_ncu_full_key_metrics.txt" if default_workload and args.guidance in NCU_TRAFFIC_BYTES else None},
     }
+    kernel_key = "composite_fwd_kernel<2>" if args.guidance == "full" else "composite_fwd_kernel<1>"
+    prof = ncu_profile_numbers(kernel_key) if default_workload else None
+    line["roofline"] = {
+        "bound": "hbm",
+        "kernel": ("composite_fwd_kernel<2> (fused composite + glue + bilateral)" if args.guidance == "full"
+                   else "composite_fwd_kernel<1> (composite + glue)"),
+        "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
+        "algorithmic_bytes": b_fwd,
+        "traffic": prof["traffic"] if prof else None, "traffic_source": prof["source"] if prof else None,
+    }
+    if prof and t_fwd > 0:
+        # SURVEY 8d caveat: the kernel is bound by instruction issue, not by HBM - its second roofline is the issue
+        # ceiling: one warp-instruction per clock per SM sub-partition (148 SMs x 4) at the SM clock sampled in this run
+        mhz = (clocks or {}).get("sm_mhz") or (clocks or {}).get("sm_max_mhz") or 1965.0
+        issue_peak = 148 * 4 * mhz * 1e6
+        issue_ach = prof["warp_instructions"] / (t_fwd * 1e-3)
+        line["roofline"]["secondary"] = {
+            "bound": "issue", "achieved": issue_ach / 1e9, "peak": issue_peak / 1e9, "unit": "G warp-instr/s",
+            "frac": issue_ach / issue_peak, "warp_instructions_per_launch": prof["warp_instructions"],
+            "source": prof["source"] + "; peak = 148 SMs x 4 schedulers x sampled SM clock"}
     if world == 1 and not args.no_cpu_baseline:
         # CPU baseline on the box's host cores: bounded sample = ONE camera image, both guidance modes
         t = cpu_reference_timings(H, W, [g[0] for g in grids_cpu])
