@@ -114,66 +114,125 @@ BDS_D void fused_chain_fwd(const FusedBil& b, int cam, int H, int W, int i, int 
   }
 }
 
-#ifdef BDS_STATS
-__device__ unsigned long long g_stats[16];
-#endif
 // =================================================================================================
 // forward
 // =================================================================================================
+// One CTA of 128 threads per 16x16 tile: 4 warps x (8x8 pixels), TWO pixels per lane - (x, y) and (x, y + 4).  What a
+// (warp, record) evaluation pays once - the bit iteration over the rectangle test's survivors, three 128-bit
+// broadcast loads of the record, the loop control - is shared by 64 pixels instead of 32, and the per-pixel arithmetic
+// of the two pixels runs as packed fp32x2 instructions (FFMA2 / FMUL2 / FADD2) with the record operand shared.
+constexpr int kFwdThreads = 128;
+constexpr int kFwdWarps = kFwdThreads / 32;
 #ifndef BDS_FWD_MINB
-#define BDS_FWD_MINB 5     // resident CTAs per SM the forward is compiled for (register cap 65536 / (256 * MINB))
+#define BDS_FWD_MINB 8     // resident CTAs per SM the forward is compiled for (register cap 65536 / (128 * MINB) = 64)
 #endif
+
+struct TileGeom2 {
+  int cam, px, py0, py1;    // the lane's two pixels: (px, py0) and (px, py1 = py0 + 4)
+  bool in0, in1;
+  int64_t pix0, pix1;       // indices into band-pixel arrays
+  float wx0, wy0;           // origin (pixel index) of the warp's 8x8 rectangle
+  int start, end;           // record range of the tile
+};
+
+BDS_D TileGeom2 tile_geom2(const CompParams& p) {
+  TileGeom2 g;
+  const int t = blockIdx.x;
+  const int grow = p.row_begin + t / p.tile_w;
+  const int tx = t - (t / p.tile_w) * p.tile_w;
+  g.cam = grow / p.tile_h;
+  const int ty = grow - g.cam * p.tile_h;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int sx = (warp & 1) * 8, sy = (warp >> 1) * 8;
+  g.px = tx * kTile + sx + (lane & 7);
+  g.py0 = ty * kTile + sy + (lane >> 3);
+  g.py1 = g.py0 + 4;
+  g.wx0 = (float)(tx * kTile + sx);
+  g.wy0 = (float)(ty * kTile + sy);
+  g.in0 = g.px < p.W && g.py0 < p.H;
+  g.in1 = g.px < p.W && g.py1 < p.H;
+  g.pix0 = ((int64_t)g.cam * p.H + g.py0 - p.pix_row0) * p.W + g.px;
+  g.pix1 = g.pix0 + 4 * (int64_t)p.W;
+  g.start = p.tile_offsets[t];
+  g.end = p.tile_offsets[t + 1];
+  return g;
+}
+
+// per-pixel epilogue: gsplat outputs (mode 0) or the reference glue (+ the bilateral chain)
 template <int MODE>
-__global__ void __launch_bounds__(256, BDS_FWD_MINB) composite_fwd_kernel(CompParams p) {
+BDS_D void fwd_epilogue(const CompParams& p, int cam, int64_t pix, int px, int py, float T, float cr, float cg, float cb,
+                        float cd, int last) {
+  const float A = 1.f - T;
+  p.last_ids[pix] = last;
+  p.out_alpha[pix] = A;
+  if (MODE == 0) {
+    float bgv[4] = {0.f, 0.f, 0.f, 0.f};
+    if (p.backgrounds)
+      for (int c = 0; c < p.channels; ++c) bgv[c] = p.backgrounds[cam * p.channels + c];
+    float o[4] = {cr + T * bgv[0], cg + T * bgv[1], cb + T * bgv[2], cd + T * bgv[3]};
+    if (p.channels == 4 && p.expected_depth) o[3] = o[3] / fmaxf(A, 1e-10f);
+    for (int c = 0; c < p.channels; ++c) p.out_rgb[pix * p.channels + c] = o[c];
+  } else {
+    float rg = fminf(cr, 1.f), gg = fminf(cg, 1.f), bg = fminf(cb, 1.f);  // base.py:417
+    p.out_rgbg[pix * 3] = rg; p.out_rgbg[pix * 3 + 1] = gg; p.out_rgbg[pix * 3 + 2] = bg;
+    p.out_depth[pix] = cd / fmaxf(A, 1e-10f);                             // RGB+ED
+    float r = rg, gr = gg, b = bg;
+    if (p.sky) {                                                          // scene_graph.py:293
+      r = fmaf(p.sky[pix * 3], T, r);
+      gr = fmaf(p.sky[pix * 3 + 1], T, gr);
+      b = fmaf(p.sky[pix * 3 + 2], T, b);
+    }
+    if (MODE == 2) fused_chain_fwd(p.bil, cam, p.H, p.W, py, px, r, gr, b, luma_of(r, gr, b));
+    p.out_rgb[pix * 3] = r; p.out_rgb[pix * 3 + 1] = gr; p.out_rgb[pix * 3 + 2] = b;
+  }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kFwdThreads, BDS_FWD_MINB) composite_fwd_kernel(CompParams p) {
   __shared__ __align__(128) float4 srec[kFStages][kFChunk * 3];
   __shared__ __align__(8) uint64_t bars[kFStages];    // stage filled (TMA complete_tx)
-  __shared__ __align__(8) uint64_t freed[kFStages];   // stage consumed by all eight warps
-  __shared__ int s_done_warps;                        // warps whose 32 pixels are all saturated
+  __shared__ __align__(8) uint64_t freed[kFStages];   // stage consumed by all warps
+  __shared__ int s_done_warps;                        // warps whose 64 pixels are all saturated
   __shared__ int s_stop;                              // first chunk that will NOT be loaded (block-wide early exit)
   __shared__ int s_decided;                           // refill decisions are taken in chunk order (no holes)
 
-  const TileGeom g = tile_geom(p);
+  const TileGeom2 g = tile_geom2(p);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int n = g.end - g.start;
   const int nchunks = (n + kFChunk - 1) / kFChunk;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kFStages; ++s) { mbar_init(&bars[s], 1); mbar_init(&freed[s], 8); }
+    for (int s = 0; s < kFStages; ++s) { mbar_init(&bars[s], 1); mbar_init(&freed[s], kFwdWarps); }
     s_done_warps = 0;
     s_stop = nchunks;
     s_decided = 0;
     mbar_fence_init();
   }
   __syncthreads();
-  int issued = 0;
   if (threadIdx.x == 0) {
-    for (; issued < nchunks && issued < kFStages; ++issued) {
-      int cnt = min(kFChunk, n - issued * kFChunk);
-      mbar_expect_tx(&bars[issued], cnt * kRecBytes);
-      bulk_g2s(&srec[issued][0], p.recs + (size_t)(g.start + issued * kFChunk) * 3, cnt * kRecBytes, &bars[issued]);
+    for (int k = 0; k < nchunks && k < kFStages; ++k) {
+      int cnt = min(kFChunk, n - k * kFChunk);
+      mbar_expect_tx(&bars[k], cnt * kRecBytes);
+      bulk_g2s(&srec[k][0], p.recs + (size_t)(g.start + k * kFChunk) * 3, cnt * kRecBytes, &bars[k]);
     }
   }
 
-  const float pxf = (float)g.px + 0.5f, pyf = (float)g.py + 0.5f;
-  const float rxmin = g.wx0 + 0.5f, rxmax = g.wx0 + 7.5f, rymin = g.wy0 + 0.5f, rymax = g.wy0 + 3.5f;
-  float T = 1.f;
-#if BDS_FWD_MINB <= 4
-  f32x2 crg = pk2(0.f, 0.f), cbd = crg;   // (C_r, C_g), (C_b, D) accumulated with packed fp32x2 FMAs
-#else
-  // under the 51-register cap of 5 CTAs/SM ptxas does not keep 64-bit accumulators in place (it copies them
-  // every iteration): scalar FMAs there
-  float cr = 0.f, cg = 0.f, cb = 0.f, cd = 0.f;
-#endif
-  int last = -1;
+  const float pxf = (float)g.px + 0.5f;
+  const f32x2 pyf2 = pk2((float)g.py0 + 0.5f, (float)g.py1 + 0.5f);
+  const float rxmin = g.wx0 + 0.5f, rxmax = g.wx0 + 7.5f, rymin = g.wy0 + 0.5f, rymax = g.wy0 + 7.5f;
+  const f32x2 one2 = pk2(1.f, 1.f);
+  f32x2 T2 = one2;                                         // transmittance of the two pixels
+  f32x2 cr2 = pk2(0.f, 0.f), cg2 = cr2, cb2 = cr2, cd2 = cr2;   // (pixel 0, pixel 1) per channel
+  int last0 = -1, last1 = -1;
   // alpha >= 1/255  <=>  e >= -log2(255); a saturated (or outside) pixel raises its threshold to +inf, so
   // "done" costs no extra test in the blend loop
-  float emin = g.inside ? -kLog2_255 : INFINITY;
-  bool warp_done = __all_sync(kFull, !g.inside);
+  float emin0 = g.in0 ? -kLog2_255 : INFINITY, emin1 = g.in1 ? -kLog2_255 : INFINITY;
+  bool warp_done = __all_sync(kFull, !g.in0 && !g.in1);
 
   // No block barrier in the loop: a warp releases a stage when it is done with it (mbarrier `freed`) and runs ahead by
-  // up to kFStages - 1 chunks; lane 0 of warp k % 8 refills the stage with chunk k + kFStages once all eight warps
-  // have released it - unless every warp has reported its pixels saturated, in which case it lowers s_stop instead
-  // and the block leaves after the chunks already in flight (the block-wide early exit).
+  // up to kFStages - 1 chunks; lane 0 of warp k % 4 refills the stage with chunk k + kFStages once all warps have
+  // released it - unless every warp has reported its pixels saturated, in which case it lowers s_stop instead and the
+  // block leaves after the chunks already in flight (the block-wide early exit).
   bool counted_done = false;
   for (int k = 0; k < nchunks; ++k) {
     const int st = k % kFStages;
@@ -186,108 +245,73 @@ __global__ void __launch_bounds__(256, BDS_FWD_MINB) composite_fwd_kernel(CompPa
       }
       if (__any_sync(kFull, stop)) break;
     }
-#ifdef BDS_STATS
-    int st_cA = 0, st_cB = 0, st_q0 = 0, st_q1 = 0, st_q2 = 0, st_q3 = 0;
-#endif
     if (!warp_done) {
       const int cnt = min(kFChunk, n - k * kFChunk);
       const float4* sr = &srec[st][0];
       const int idx0 = g.start + k * kFChunk;
       for (int base = 0; base < cnt && !warp_done; base += 32) {
-        // lane j tests record base+j against the warp's 8x4 pixel rectangle
-        int j = base + lane;
+        // lane j tests record base+j against the warp's 8x8 pixel rectangle
+        const int j = base + lane;
         bool hit = false;
         if (j < cnt) {
-          float4 r0 = sr[j * 3], r1 = sr[j * 3 + 1], r2 = sr[j * 3 + 2];
-          float s = min_sigma_rect(r0.x, r0.y, r0.z, r0.w, r1.x, rxmin, rxmax, rymin, rymax);
+          const float4 r0 = sr[j * 3], r1 = sr[j * 3 + 1], r2 = sr[j * 3 + 2];
+          const float s = min_sigma_rect(r0.x, r0.y, r0.z, r0.w, r1.x, rxmin, rxmax, rymin, rymax);
           hit = !(s > r2.w + (kLog2_255 + kCullMargin));
           // a masked-out splat is a splat of opacity 0: it fails the alpha >= 1/255 test on every pixel
           if (p.slot_keep && hit) hit = p.slot_keep[__float_as_int(r2.z)] != 0;
         }
         unsigned m = __ballot_sync(kFull, hit);
-#ifdef BDS_STATS
-        {
-          unsigned q[4];
-          for (int qi = 0; qi < 4; ++qi) {
-            bool h = false;
-            if (j < cnt) {
-              float4 r0 = sr[j * 3], r1 = sr[j * 3 + 1], r2 = sr[j * 3 + 2];
-              float x0 = g.wx0 + (qi & 1) * 4 + 0.5f, y0 = g.wy0 + (qi >> 1) * 2 + 0.5f;
-              float s = min_sigma_rect(r0.x, r0.y, r0.z, r0.w, r1.x, x0, x0 + 3.f, y0, y0 + 1.f);
-              h = !(s > r2.w + (kLog2_255 + kCullMargin));
-            }
-            q[qi] = __ballot_sync(kFull, h);
-          }
-          unsigned mA = q[0] | q[2], mB = q[1] | q[3];
-          int pa = __popc(mA), pb = __popc(mB);
-          int p0 = __popc(q[0]), p1 = __popc(q[1]), p2 = __popc(q[2]), p3 = __popc(q[3]);
-          st_cA += pa; st_cB += pb; st_q0 += p0; st_q1 += p1; st_q2 += p2; st_q3 += p3;
-          if (lane == 0) {
-            atomicAdd(&g_stats[0], 1ull);
-            atomicAdd(&g_stats[1], (unsigned long long)__popc(m));
-            atomicAdd(&g_stats[2], (unsigned long long)max(pa, pb));
-            atomicAdd(&g_stats[4], (unsigned long long)max(max(p0, p1), max(p2, p3)));
-            atomicAdd(&g_stats[6], (unsigned long long)(pa + pb));
-            atomicAdd(&g_stats[7], (unsigned long long)(p0 + p1 + p2 + p3));
-            atomicAdd(&g_stats[9], (unsigned long long)__popc(mA | mB));
-          }
-        }
-#endif
         while (m) {
-          int jj = base + __ffs(m) - 1;
+          const int jj = base + __ffs(m) - 1;
           m &= m - 1;
-          float4 r0 = sr[jj * 3], r1 = sr[jj * 3 + 1], r2 = sr[jj * 3 + 2];
-          float dx = r0.x - pxf, dy = r0.y - pyf;
-          // e = log2(opacity) - sigma', sigma' = a' dx^2 + b' dx dy + c' dy^2  (alpha = 2^e)
-          float e = fmaf(-dx, fmaf(r0.w, dy, r0.z * dx), r2.w);
-          e = fmaf(-(r1.x * dy), dy, e);
-          const float alpha = fminf(kAlphaMax, exp2f(e));
-          const bool ok = e >= emin && e <= r2.w;   // alpha >= 1/255 (and not saturated) and sigma' >= 0
-#ifdef BDS_STATS
-          {
-            unsigned vm = __ballot_sync(kFull, ok);
-            if (lane == 0) atomicAdd(&g_stats[8], (unsigned long long)__popc(vm));
-          }
-#endif
-          // branch-free blend step: the rectangle cull leaves records most lanes need anyway
-          const float nT = T * (1.f - alpha);
-          const bool go = ok && nT > kTStop;         // gsplat stops BEFORE adding the saturating record
-          const float vis = go ? alpha * T : 0.f;
-#if BDS_FWD_MINB <= 4
-          const f32x2 vis2 = pk2(vis, vis);
-          fma2_acc(crg, vis2, pk2(r1.z, r1.w));
-          fma2_acc(cbd, vis2, pk2(r2.x, r2.y));
-#else
-          cr = fmaf(vis, r1.z, cr);
-          cg = fmaf(vis, r1.w, cg);
-          cb = fmaf(vis, r2.x, cb);
-          cd = fmaf(vis, r2.y, cd);
-#endif
-          T = go ? nT : T;
-          last = go ? idx0 + jj : last;
-          emin = (ok && !go) ? INFINITY : emin;
+          const float4 r0 = sr[jj * 3], r1 = sr[jj * 3 + 1], r2 = sr[jj * 3 + 2];
+          // e = log2(opacity) - sigma', sigma' = a' dx^2 + b' dx dy + c' dy^2  (alpha = 2^e); dx is shared by the
+          // lane's two pixels, everything in dy runs packed
+          const float dx = r0.x - pxf;
+          const float adx = r0.z * dx;
+          const f32x2 dy2 = sub2(pk2(r0.y, r0.y), pyf2);
+          const f32x2 t2 = fma2(pk2(r0.w, r0.w), dy2, pk2(adx, adx));
+          f32x2 e2 = fma2(pk2(-dx, -dx), t2, pk2(r2.w, r2.w));
+          e2 = fma2(mul2(pk2(-r1.x, -r1.x), dy2), dy2, e2);
+          float e0, e1;
+          upk2(e2, e0, e1);
+          const float a0 = fminf(kAlphaMax, exp2f(e0)), a1 = fminf(kAlphaMax, exp2f(e1));
+          const bool ok0 = e0 >= emin0 && e0 <= r2.w;   // alpha >= 1/255 (and not saturated) and sigma' >= 0
+          const bool ok1 = e1 >= emin1 && e1 <= r2.w;
+          const f32x2 a2 = pk2(a0, a1);
+          const f32x2 nT2 = mul2(T2, sub2(one2, a2));
+          float nT0, nT1, T0, T1, v0, v1;
+          upk2(nT2, nT0, nT1);
+          upk2(T2, T0, T1);
+          const bool go0 = ok0 && nT0 > kTStop;         // gsplat stops BEFORE adding the saturating record
+          const bool go1 = ok1 && nT1 > kTStop;
+          upk2(mul2(a2, T2), v0, v1);
+          const f32x2 vis2 = pk2(go0 ? v0 : 0.f, go1 ? v1 : 0.f);
+          fma2_acc(cr2, vis2, pk2(r1.z, r1.z));
+          fma2_acc(cg2, vis2, pk2(r1.w, r1.w));
+          fma2_acc(cb2, vis2, pk2(r2.x, r2.x));
+          fma2_acc(cd2, vis2, pk2(r2.y, r2.y));
+          T2 = pk2(go0 ? nT0 : T0, go1 ? nT1 : T1);
+          last0 = go0 ? idx0 + jj : last0;
+          last1 = go1 ? idx0 + jj : last1;
+          emin0 = (ok0 && !go0) ? INFINITY : emin0;
+          emin1 = (ok1 && !go1) ? INFINITY : emin1;
         }
-        warp_done = __all_sync(kFull, emin > 0.f);
+        warp_done = __all_sync(kFull, emin0 > 0.f && emin1 > 0.f);
       }
     }
-#ifdef BDS_STATS
-    if (lane == 0) {
-      atomicAdd(&g_stats[3], (unsigned long long)max(st_cA, st_cB));
-      atomicAdd(&g_stats[5], (unsigned long long)max(max(st_q0, st_q1), max(st_q2, st_q3)));
-    }
-#endif
     if (warp_done && !counted_done) {
       counted_done = true;
       if (lane == 0) atomicAdd(&s_done_warps, 1);
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&freed[st]);   // release: orders the counter update above before the refill decision
-    if (k + kFStages < nchunks && warp == (k & 7) && lane == 0) {
+    if (k + kFStages < nchunks && warp == (k & (kFwdWarps - 1)) && lane == 0) {
       mbar_wait(&freed[st], (k / kFStages) & 1);
       for (unsigned it = 0; *reinterpret_cast<volatile int*>(&s_decided) != k; ++it)   // the decision for chunk k - 1 first
         if (it > (1u << 24)) __trap();
       if (*reinterpret_cast<volatile int*>(&s_stop) == nchunks) {   // nobody has stopped the loads yet
-        if (*reinterpret_cast<volatile int*>(&s_done_warps) == 8) {
+        if (*reinterpret_cast<volatile int*>(&s_done_warps) == kFwdWarps) {
           *reinterpret_cast<volatile int*>(&s_stop) = k + kFStages;
         } else {
           const int kk = k + kFStages;
@@ -303,35 +327,11 @@ __global__ void __launch_bounds__(256, BDS_FWD_MINB) composite_fwd_kernel(CompPa
   // every chunk that was loaded has been waited for by every warp (a warp only leaves at a chunk >= s_stop): no bulk
   // copy is in flight into this CTA's shared memory when it exits
 
-  if (!g.inside) return;
-#if BDS_FWD_MINB <= 4
-  float cr, cg, cb, cd;
-  upk2(crg, cr, cg);
-  upk2(cbd, cb, cd);
-#endif
-  const float A = 1.f - T;
-  p.last_ids[g.pix] = last;
-  p.out_alpha[g.pix] = A;
-  if (MODE == 0) {
-    float bgv[4] = {0.f, 0.f, 0.f, 0.f};
-    if (p.backgrounds)
-      for (int c = 0; c < p.channels; ++c) bgv[c] = p.backgrounds[g.cam * p.channels + c];
-    float o[4] = {cr + T * bgv[0], cg + T * bgv[1], cb + T * bgv[2], cd + T * bgv[3]};
-    if (p.channels == 4 && p.expected_depth) o[3] = o[3] / fmaxf(A, 1e-10f);
-    for (int c = 0; c < p.channels; ++c) p.out_rgb[g.pix * p.channels + c] = o[c];
-  } else {
-    float rg = fminf(cr, 1.f), gg = fminf(cg, 1.f), bg = fminf(cb, 1.f);  // base.py:417
-    p.out_rgbg[g.pix * 3] = rg; p.out_rgbg[g.pix * 3 + 1] = gg; p.out_rgbg[g.pix * 3 + 2] = bg;
-    p.out_depth[g.pix] = cd / fmaxf(A, 1e-10f);                           // RGB+ED
-    float r = rg, gr = gg, b = bg;
-    if (p.sky) {                                                          // scene_graph.py:293
-      r = fmaf(p.sky[g.pix * 3], T, r);
-      gr = fmaf(p.sky[g.pix * 3 + 1], T, gr);
-      b = fmaf(p.sky[g.pix * 3 + 2], T, b);
-    }
-    if (MODE == 2) fused_chain_fwd(p.bil, g.cam, p.H, p.W, g.py, g.px, r, gr, b, luma_of(r, gr, b));
-    p.out_rgb[g.pix * 3] = r; p.out_rgb[g.pix * 3 + 1] = gr; p.out_rgb[g.pix * 3 + 2] = b;
-  }
+  float T0, T1, r0_, r1_, g0_, g1_, b0_, b1_, d0_, d1_;
+  upk2(T2, T0, T1);
+  upk2(cr2, r0_, r1_); upk2(cg2, g0_, g1_); upk2(cb2, b0_, b1_); upk2(cd2, d0_, d1_);
+  if (g.in0) fwd_epilogue<MODE>(p, g.cam, g.pix0, g.px, g.py0, T0, r0_, g0_, b0_, d0_, last0);
+  if (g.in1) fwd_epilogue<MODE>(p, g.cam, g.pix1, g.px, g.py1, T1, r1_, g1_, b1_, d1_, last1);
 }
 
 // =================================================================================================
@@ -668,21 +668,6 @@ __global__ void __launch_bounds__(256, BDS_BWD_MINB) composite_bwd_kernel(CompPa
           float e = fmaf(-dx, fmaf(r0.w, dy, r0.z * dx), r2.w);
           e = fmaf(-(r1.x * dy), dy, e);
           const bool valid = chunk0 + jj <= last && e <= r2.w && e >= -kLog2_255;
-#ifdef BDS_STATS
-          {
-            unsigned vm = __ballot_sync(kFull, valid);
-            if (lane == 0) {
-              atomicAdd(&g_stats[10], 1ull);                                    // survivors of the rectangle cull
-              atomicAdd(&g_stats[11], vm ? 1ull : 0ull);                        // evaluations (any valid lane)
-              atomicAdd(&g_stats[12], (unsigned long long)__popc(vm));          // valid (pixel, record) pairs
-              // 4x4 halves (lanes with (lane & 7) < 4 = left) that hold a valid lane
-              unsigned left = 0x0f0f0f0fu;
-              atomicAdd(&g_stats[13], (unsigned long long)(((vm & left) != 0) + ((vm & ~left) != 0)));
-              atomicAdd(&g_stats[14], (unsigned long long)(__popc(vm) <= 2 && vm ? 1 : 0));
-              atomicAdd(&g_stats[15], (unsigned long long)(__popc(vm) <= 8 && vm ? 1 : 0));
-            }
-          }
-#endif
           if (!__any_sync(kFull, valid)) continue;
           float w = 0.f, fac = 0.f;
           if (valid) {
@@ -912,9 +897,9 @@ static int composite_fwd_impl(const bds_render_desc* d, const bds_epilogue_desc*
     if (int rc = launch_repack<false>(jobs, stream)) return rc;
   }
   switch (e->mode) {
-    case 0: composite_fwd_kernel<0><<<n_tiles, 256, 0, stream>>>(p); break;
-    case 1: composite_fwd_kernel<1><<<n_tiles, 256, 0, stream>>>(p); break;
-    default: composite_fwd_kernel<2><<<n_tiles, 256, 0, stream>>>(p); break;
+    case 0: composite_fwd_kernel<0><<<n_tiles, kFwdThreads, 0, stream>>>(p); break;
+    case 1: composite_fwd_kernel<1><<<n_tiles, kFwdThreads, 0, stream>>>(p); break;
+    default: composite_fwd_kernel<2><<<n_tiles, kFwdThreads, 0, stream>>>(p); break;
   }
   BDS_CHECK_LAUNCH();
   return 0;
@@ -1011,14 +996,3 @@ extern "C" int bds_composite_bwd(const bds_render_desc* d, const bds_epilogue_de
   return 0;
 }
 
-#ifdef BDS_STATS
-extern "C" int bds_debug_stats(unsigned long long* out, int reset) {
-  cudaDeviceSynchronize();
-  cudaMemcpyFromSymbol(out, bds::g_stats, sizeof(unsigned long long) * 16);
-  if (reset) {
-    unsigned long long z[16] = {0};
-    cudaMemcpyToSymbol(bds::g_stats, z, sizeof(z));
-  }
-  return 0;
-}
-#endif
