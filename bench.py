@@ -62,8 +62,10 @@ def parse():
     ap.add_argument("--height", type=int, default=1080)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--breakdown", action="store_true", help="print the per-phase CUDA-event times of rank 0 to stderr")
-    ap.add_argument("--grad-exchange", default="dense", choices=["splats", "dense"],
-                    help="N > 1: dense = ONE all-reduce of the flat 236 B x N parameter gradient (default: NCCL runs it as "
+    ap.add_argument("--grad-exchange", default="compact", choices=["compact", "splats", "dense"],
+                    help="N > 1: compact (default) = ONE all-reduce of the Gaussian gradients with the SH part as a colour "
+                         "cotangent per (camera, Gaussian) - 11 + 3 C floats per Gaussian instead of 59 - expanded "
+                         "afterwards; dense = ONE all-reduce of the flat 236 B x N parameter gradient (NCCL runs it as "
                          "NVLS in-switch reduction, 1.2 ms at 8 GPUs); splats = all-gather the per-splat gradient records "
                          "and run the projection backward over all of them on every rank (less data, but the uneven "
                          "all-gather measured slower: 3.89 vs 3.04 ms/step at 8 GPUs, profiles/r02_bench_n8_*.json)")
@@ -353,7 +355,8 @@ def main():
         out = render.render_fused(params, vmx, Ksx, W, H, sky=sky, grid_slots=slots, bil_sizes=sizes, sh_degree=3,
                                   near_plane=0.1, row_begin=rb, row_end=re, absgrad=True, dense_info=False,
                                   guidance_factor=(4, 4, 2) if args.guidance == "lowres" else None,
-                                  exchange_group=True if (world > 1 and args.grad_exchange == "splats") else None)
+                                  exchange_group=True if (world > 1 and args.grad_exchange != "dense") else None,
+                                  exchange_mode=args.grad_exchange if args.grad_exchange != "dense" else "splats")
         if gt_ready is not None:  # the GT image copy ran on a side stream, overlapped with the render
             torch.cuda.current_stream().wait_event(gt_ready)
         loss = render.photometric_loss(out["rgb"], gt, out["depth"], out["opacity"], LAMBDA_D, LAMBDA_A, count=total_px,

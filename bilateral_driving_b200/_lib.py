@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, os.environ.get("BDS_LIB", "libbds_b200.so"))
 MAX_LEVELS = 4
 TILE = 16
 COUNTERS_LEN = 4096  # BDS_COUNTERS_LEN (include/bds.h)
-ABI_VERSION = 4      # BDS_ABI_VERSION: 4 = + bds_densify_stats; 3 = + bds_project_bwd_extras; 2 = moment-form gradient records
+ABI_VERSION = 5      # BDS_ABI_VERSION: 5 = + compact SH gradient exchange, tv levels; 4 = + bds_densify_stats; 3 = + bds_project_bwd_extras; 2 = moment-form gradient records
 SPLAT_FLOATS = 12
 
 
@@ -88,7 +88,7 @@ ABI_SYMBOLS = (
     "bds_bilateral_workspace_bytes", "bds_bilateral_fwd", "bds_bilateral_bwd",
     "bds_bilagrid_slice_fwd", "bds_bilagrid_slice_bwd", "bds_tv_fwd_bwd", "bds_tv_levels_fwd_bwd",
     "bds_sh_fwd", "bds_sh_bwd",
-    "bds_project_fwd", "bds_project_bwd", "bds_project_bwd_extras",
+    "bds_project_fwd", "bds_project_bwd", "bds_project_bwd_extras", "bds_project_bwd_compact_sh", "bds_sh_expand_bwd",
     "bds_bin_count_workspace_bytes", "bds_bin_count", "bds_bin_sort_workspace_bytes", "bds_bin_sort",
     "bds_composite_workspace_bytes", "bds_composite_fwd", "bds_composite_bwd",
     "bds_slot_keep", "bds_composite_fwd_masked",

@@ -340,6 +340,7 @@ struct ProjBwdParams {
   const float* v_splats;
   const float *v_means2d_extra, *v_depths_extra, *v_conics_extra;
   float *v_means, *v_quats, *v_scales, *v_opacities, *v_colors, *v_fdc, *v_frest, *v_viewmats, *v_means2d, *absgrad;
+  float* v_sh_color;   // optional [C,N,3]: the SH colour cotangent per (camera, Gaussian) instead of v_fdc / v_frest
 };
 
 // Gradient row of the 15 higher SH coefficients of one Gaussian (45 floats, value j = b[1 + j/3] * vcol[j % 3]):
@@ -412,7 +413,14 @@ __global__ void __launch_bounds__(256) project_bwd_kernel(ProjBwdParams p) {
     if (p.d.raw_params) vop *= op * (1.f - op);
     red_add(p.v_opacities + n, vop);
     // colours
-    if (p.d.sh_degree >= 0) {
+    if (p.d.sh_degree >= 0 && p.v_sh_color) {
+      // compact form (multi-GPU exchange): the SH gradient of a (camera, Gaussian) pair is the outer product of the
+      // basis values of its view direction and this 3-vector; bds_sh_expand_bwd rebuilds the 48 coefficients
+      float* dst = p.v_sh_color + 3 * (size_t)idx;
+      dst[0] = (r1.z > 0.f && r1.z < 1.f) ? vr : 0.f;
+      dst[1] = (r1.w > 0.f && r1.w < 1.f) ? vg : 0.f;
+      dst[2] = (r2.x > 0.f && r2.x < 1.f) ? vbl : 0.f;
+    } else if (p.d.sh_degree >= 0) {
       float cp[3] = {-(cam.R[0] * cam.t[0] + cam.R[3] * cam.t[1] + cam.R[6] * cam.t[2]),
                      -(cam.R[1] * cam.t[0] + cam.R[4] * cam.t[1] + cam.R[7] * cam.t[2]),
                      -(cam.R[2] * cam.t[0] + cam.R[5] * cam.t[1] + cam.R[8] * cam.t[2])};
@@ -656,22 +664,24 @@ extern "C" int bds_project_fwd(const bds_render_desc* d, const float* means, con
   return 0;
 }
 
-extern "C" int bds_project_bwd(const bds_render_desc* d, const float* means, const float* quats, const float* scales,
-                               const float* opacities, const float* colors, int colors_per_cam,
-                               const float* features_dc, const float* features_rest, const float* viewmats,
-                               const float* Ks, const float* splats, const int32_t* counters, const float* v_splats,
-                               const float* v_means2d_extra, const float* v_depths_extra, const float* v_conics_extra,
-                               float* v_means, float* v_quats, float* v_scales, float* v_opacities, float* v_colors,
-                               float* v_features_dc, float* v_features_rest, float* v_viewmats, float* v_means2d,
-                               float* absgrad, bds_stream_t stream) {
+static int project_bwd_impl(const bds_render_desc* d, const float* means, const float* quats, const float* scales,
+                            const float* opacities, const float* colors, int colors_per_cam,
+                            const float* features_dc, const float* features_rest, const float* viewmats,
+                            const float* Ks, const float* splats, const int32_t* counters, const float* v_splats,
+                            const float* v_means2d_extra, const float* v_depths_extra, const float* v_conics_extra,
+                            float* v_means, float* v_quats, float* v_scales, float* v_opacities, float* v_colors,
+                            float* v_features_dc, float* v_features_rest, float* v_viewmats, float* v_means2d,
+                            float* absgrad, float* v_sh_color, bds_stream_t stream) {
   if (int rc = check_render_desc(d)) return rc;
   int64_t total = (int64_t)d->n_gauss * d->n_cams;
   if (total == 0) return 0;
   BDS_REQUIRE(means && quats && scales && opacities && viewmats && Ks && splats && counters && v_splats,
               "project_bwd: null input pointer");
   BDS_REQUIRE(v_means && v_quats && v_scales && v_opacities, "project_bwd: null output pointer");
-  if (d->sh_degree >= 0) BDS_REQUIRE(v_features_dc && (v_features_rest || d->sh_K == 1), "project_bwd: SH grads missing");
+  if (d->sh_degree >= 0 && !v_sh_color)
+    BDS_REQUIRE(v_features_dc && (v_features_rest || d->sh_K == 1), "project_bwd: SH grads missing");
   ProjBwdParams p;
+  p.v_sh_color = d->sh_degree >= 0 ? v_sh_color : nullptr;
   p.d = *d;
   p.means = means; p.quats = quats; p.scales = scales; p.opacities = opacities; p.colors = colors;
   p.fdc = features_dc; p.frest = features_rest; p.viewmats = viewmats; p.Ks = Ks; p.colors_per_cam = colors_per_cam;
@@ -683,6 +693,89 @@ extern "C" int bds_project_bwd(const bds_render_desc* d, const float* means, con
   // the slot count lives on the device; launch over the worst case (every (cam, gauss) visible) and
   // let threads beyond counters[0] exit - the grid is cheap next to an extra host sync
   project_bwd_kernel<<<ceil_div(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  BDS_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int bds_project_bwd(const bds_render_desc* d, const float* means, const float* quats, const float* scales,
+                               const float* opacities, const float* colors, int colors_per_cam,
+                               const float* features_dc, const float* features_rest, const float* viewmats,
+                               const float* Ks, const float* splats, const int32_t* counters, const float* v_splats,
+                               const float* v_means2d_extra, const float* v_depths_extra, const float* v_conics_extra,
+                               float* v_means, float* v_quats, float* v_scales, float* v_opacities, float* v_colors,
+                               float* v_features_dc, float* v_features_rest, float* v_viewmats, float* v_means2d,
+                               float* absgrad, bds_stream_t stream) {
+  return project_bwd_impl(d, means, quats, scales, opacities, colors, colors_per_cam, features_dc, features_rest, viewmats,
+                          Ks, splats, counters, v_splats, v_means2d_extra, v_depths_extra, v_conics_extra, v_means, v_quats,
+                          v_scales, v_opacities, v_colors, v_features_dc, v_features_rest, v_viewmats, v_means2d, absgrad,
+                          nullptr, stream);
+}
+
+extern "C" int bds_project_bwd_compact_sh(const bds_render_desc* d, const float* means, const float* quats,
+                                          const float* scales, const float* opacities, const float* viewmats,
+                                          const float* Ks, const float* splats, const int32_t* counters,
+                                          const float* v_splats, float* v_means, float* v_quats, float* v_scales,
+                                          float* v_opacities, float* v_sh_color, float* v_viewmats, bds_stream_t stream) {
+  BDS_REQUIRE(d && d->sh_degree >= 0 && v_sh_color, "project_bwd_compact_sh: needs the SH fast path and v_sh_color");
+  return project_bwd_impl(d, means, quats, scales, opacities, nullptr, 0, nullptr, nullptr, viewmats, Ks, splats, counters,
+                          v_splats, nullptr, nullptr, nullptr, v_means, v_quats, v_scales, v_opacities, nullptr, nullptr,
+                          nullptr, v_viewmats, nullptr, nullptr, v_sh_color, stream);
+}
+
+// v_features_dc / v_features_rest of every Gaussian from the compact per-(camera, Gaussian) colour cotangents:
+// sum over cameras of basis(view direction) (x) v_sh_color.  One thread per Gaussian, the 3 K sums in registers, one
+// plain write per coefficient (no atomics).
+__global__ void __launch_bounds__(256) sh_expand_bwd_kernel(bds_render_desc d, const float* __restrict__ means,
+                                                            const float* __restrict__ viewmats,
+                                                            const float* __restrict__ v_sh_color,
+                                                            float* __restrict__ v_fdc, float* __restrict__ v_frest) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= d.n_gauss) return;
+  const float mu[3] = {means[3 * (size_t)n], means[3 * (size_t)n + 1], means[3 * (size_t)n + 2]};
+  float acc[48];
+#pragma unroll
+  for (int k = 0; k < 48; ++k) acc[k] = 0.f;
+  int nb = (d.sh_degree + 1) * (d.sh_degree + 1);
+  if (nb > d.sh_K) nb = d.sh_K;
+  for (int c = 0; c < d.n_cams; ++c) {
+    const float* vc = v_sh_color + 3 * ((size_t)c * d.n_gauss + n);
+    const float v0 = vc[0], v1 = vc[1], v2 = vc[2];
+    if (v0 == 0.f && v1 == 0.f && v2 == 0.f) continue;
+    const float* V = viewmats + 16 * c;   // camera position = -R^T t
+    const float cx = -(V[0] * V[3] + V[4] * V[7] + V[8] * V[11]);
+    const float cy = -(V[1] * V[3] + V[5] * V[7] + V[9] * V[11]);
+    const float cz = -(V[2] * V[3] + V[6] * V[7] + V[10] * V[11]);
+    const float dx = mu[0] - cx, dy = mu[1] - cy, dz = mu[2] - cz;
+    const float inv = rsqrtf(dx * dx + dy * dy + dz * dz);
+    float b[16];
+    sh_basis(d.sh_degree, dx * inv, dy * inv, dz * inv, b);
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      if (k < nb) {
+        acc[3 * k] = fmaf(b[k], v0, acc[3 * k]);
+        acc[3 * k + 1] = fmaf(b[k], v1, acc[3 * k + 1]);
+        acc[3 * k + 2] = fmaf(b[k], v2, acc[3 * k + 2]);
+      }
+    }
+  }
+  v_fdc[3 * (size_t)n] = acc[0]; v_fdc[3 * (size_t)n + 1] = acc[1]; v_fdc[3 * (size_t)n + 2] = acc[2];
+  float* fr = v_frest + (size_t)n * (d.sh_K - 1) * 3;
+#pragma unroll
+  for (int k = 1; k < 16; ++k) {
+    if (k < d.sh_K) { fr[3 * (k - 1)] = acc[3 * k]; fr[3 * (k - 1) + 1] = acc[3 * k + 1]; fr[3 * (k - 1) + 2] = acc[3 * k + 2]; }
+  }
+}
+
+extern "C" int bds_sh_expand_bwd(const bds_render_desc* d, const float* means, const float* viewmats,
+                                 const float* v_sh_color, float* v_features_dc, float* v_features_rest,
+                                 bds_stream_t stream) {
+  if (int rc = check_render_desc(d)) return rc;
+  if (d->n_gauss == 0) return 0;
+  BDS_REQUIRE(d->sh_degree >= 0 && d->sh_K >= 1 && d->sh_K <= 16, "sh_expand_bwd: needs the SH fast path, K <= 16");
+  BDS_REQUIRE(means && viewmats && v_sh_color && v_features_dc && (v_features_rest || d->sh_K == 1),
+              "sh_expand_bwd: null pointer");
+  sh_expand_bwd_kernel<<<ceil_div(d->n_gauss, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      *d, means, viewmats, v_sh_color, v_features_dc, v_features_rest);
   BDS_CHECK_LAUNCH();
   return 0;
 }

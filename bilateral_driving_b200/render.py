@@ -78,6 +78,10 @@ class RenderCfg:
     # gradients - the backward all-gathers them over this process group (True = the default group) and runs the
     # projection backward over every rank's records, so the returned Gaussian gradients are already the job's
     exchange_group: object = None
+    # "splats": all-gather the per-splat gradient records and run the projection backward over all of them;
+    # "compact": all-reduce the Gaussian gradients with the SH part in compact form (3 floats per (camera, Gaussian)
+    # instead of 3 K per Gaussian: 11 + 3 C floats instead of 59) inside the backward, then expand it
+    exchange_mode: str = "splats"
 
     def tiles(self):
         return (self.width + TILE - 1) // TILE, (self.height + TILE - 1) // TILE
@@ -203,8 +207,13 @@ class _RenderFn(torch.autograd.Function):
             if cfg.dense_info:
                 raise BdsError("exchange_group needs dense_info=False (the dense densification taps are per rank)")
             grp = None if cfg.exchange_group is True else cfg.exchange_group
-            counts, total_dev = D.gather_splat_counts(n_slots, dev, grp)
-            ctx.exchange = (grp, counts, total_dev)
+            if cfg.exchange_mode == "compact":
+                if fdc is None or colors is not None:
+                    raise BdsError("exchange_mode='compact' needs the SH fast path (features_dc / features_rest)")
+                ctx.exchange = (grp, None, None)
+            else:
+                counts, total_dev = D.gather_splat_counts(n_slots, dev, grp)
+                ctx.exchange = (grp, counts, total_dev)
         sorted_splats = torch.empty(max(n_isect, 1), 12, **f32)
         ws1 = torch.empty(int(lib.bds_bin_sort_workspace_bytes(C.byref(d), C.c_int64(n_isect))), device=dev,
                           dtype=torch.uint8)
@@ -285,6 +294,9 @@ class _RenderFn(torch.autograd.Function):
                   "bds_composite_bwd")
         # every Gaussian-parameter gradient lives in ONE flat zero-filled buffer (one fill, and the
         # multi-GPU step all-reduces it in place: dist.allreduce_grads)
+        if ctx.exchange is not None and cfg.exchange_mode == "compact":
+            return _RenderFn._backward_compact(ctx, means, quats, scales, opacities, fdc, frest, viewmats, Ks, splats,
+                                               counters, v_splats, need, v_bg, v_sky, v_grids, st)
         parts = [("means", means), ("quats", quats), ("scales", scales), ("opac", opacities)]
         if colors is not None:
             parts.append(("colors", colors))
@@ -349,6 +361,48 @@ class _RenderFn(torch.autograd.Function):
         ctx.holder["v_splats"] = v_splats
         return (None, None, v_means, v_quats, v_scales, v_opac, v_colors, v_fdc, v_frest, v_view, None, v_bg, v_sky,
                 *v_grids)
+
+
+def _backward_compact(ctx, means, quats, scales, opacities, fdc, frest, viewmats, Ks, splats, counters, v_splats, need,
+                      v_bg, v_sky, v_grids, st):
+    """Tail of ``_RenderFn.backward`` for ``exchange_mode="compact"``: projection backward with the SH gradient as one
+    colour cotangent per (camera, Gaussian), ONE all-reduce of [means | quats | scales | opacities | that] over the
+    exchange group, then the expansion to ``_features_dc`` / ``_features_rest``.  The gradients returned are the job's."""
+    import torch.distributed as dist
+
+    cfg, d = ctx.cfg, ctx.d
+    dev = means.device
+    N, Cn = means.shape[0], viewmats.shape[0]
+    f32 = dict(device=dev, dtype=torch.float32)
+    sizes = [("means", (N, 3)), ("quats", (N, 4)), ("scales", (N, 3)), ("opac", tuple(opacities.shape)), ("shc", (Cn, N, 3))]
+    numel = [int(torch.Size(sh).numel()) for _, sh in sizes]
+    flat = torch.zeros(sum(numel), **f32)
+    views, off = {}, 0
+    for (name, sh), n_el in zip(sizes, numel):
+        views[name] = flat[off:off + n_el].view(sh)
+        off += n_el
+    v_view = torch.zeros_like(viewmats) if need[9] else None
+    with _timed("project_bwd"):
+        check(lib.bds_project_bwd_compact_sh(C.byref(d), ptr(means), ptr(quats), ptr(scales), ptr(opacities), ptr(viewmats),
+                                             ptr(Ks), ptr(splats), ptr(counters), ptr(v_splats), ptr(views["means"]),
+                                             ptr(views["quats"]), ptr(views["scales"]), ptr(views["opac"]),
+                                             ptr(views["shc"]), ptr(v_view), st), "bds_project_bwd_compact_sh")
+    grp = ctx.exchange[0]
+    with _timed("exchange"):
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=grp)
+        if v_view is not None:
+            dist.all_reduce(v_view, op=dist.ReduceOp.SUM, group=grp)
+    v_fdc, v_frest = torch.empty_like(fdc), torch.empty_like(frest)
+    with _timed("sh_expand"):
+        check(lib.bds_sh_expand_bwd(C.byref(d), ptr(means), ptr(viewmats), ptr(views["shc"]), ptr(v_fdc), ptr(v_frest), st),
+              "bds_sh_expand_bwd")
+    ctx.holder["grads_are_global"] = True
+    ctx.holder["v_splats"] = v_splats
+    return (None, None, views["means"], views["quats"], views["scales"], views["opac"], None, v_fdc, v_frest, v_view, None,
+            v_bg, v_sky, *v_grids)
+
+
+_RenderFn._backward_compact = staticmethod(_backward_compact)
 
 
 def _run(cfg: RenderCfg, means, quats, scales, opacities, colors, fdc, frest, viewmats, Ks, backgrounds, sky, grids):
@@ -537,7 +591,7 @@ def render_fused(params: Dict[str, torch.Tensor], viewmats, Ks, width: int, heig
                  grid_slots: Optional[Sequence[Sequence[torch.Tensor]]] = None, bil_sizes=(), sh_degree: int = 3,
                  near_plane: float = 0.1, far_plane: float = 1e10, radius_clip: float = 0.0, absgrad: bool = True,
                  row_begin: int = 0, row_end: int = -1, activated: bool = False, dense_info: bool = False,
-                 antialiased: bool = False, guidance_factor=None, exchange_group=None):
+                 antialiased: bool = False, guidance_factor=None, exchange_group=None, exchange_mode="splats"):
     """One fused pass of the hot path for C cameras.
 
     ``params``: ``_means [N,3], _scales (log) [N,3], _quats [N,4], _opacities (logit) [N] or [N,1],
@@ -561,7 +615,7 @@ def render_fused(params: Dict[str, torch.Tensor], viewmats, Ks, width: int, heig
                     antialiased=antialiased, row_begin=row_begin, row_end=row_end, raw_params=not activated,
                     sh_degree=-1 if activated else sh_degree, mode=mode, channels=4, expected_depth=True,
                     bil_sizes=tuple(tuple(s) for s in bil_sizes), absgrad=absgrad, dense_info=dense_info,
-                    exchange_group=exchange_group)
+                    exchange_group=exchange_group, exchange_mode=exchange_mode)
     grids: List[Optional[torch.Tensor]] = []
     if mode == 2:
         assert len(grid_slots) == Cn and all(len(g) == len(bil_sizes) for g in grid_slots if g is not None)

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define BDS_ABI_VERSION 4
+#define BDS_ABI_VERSION 5
 #define BDS_MAX_LEVELS 4
 #define BDS_COUNTERS_LEN 4096  /* int32 entries of the projection counters buffer */
 #define BDS_TILE 16
@@ -228,6 +228,20 @@ int bds_project_bwd(const bds_render_desc* d, const float* means, const float* q
                     const float* v_conics_extra, float* v_means, float* v_quats, float* v_scales,
                     float* v_opacities, float* v_colors, float* v_features_dc, float* v_features_rest,
                     float* v_viewmats, float* v_means2d, float* absgrad, bds_stream_t stream);
+
+/* Multi-GPU gradient exchange with the SH gradient in COMPACT form.  The gradient of the 3 K SH coefficients of a
+ * Gaussian is, per camera, the outer product of the K basis values of its view direction and ONE 3-vector: the colour
+ * cotangent.  bds_project_bwd_compact_sh is bds_project_bwd for the SH fast path (sh_degree >= 0) writing that 3-vector
+ * per (camera, Gaussian) into v_sh_color [C,N,3] (caller zero-fills) instead of accumulating v_features_dc / _rest; the
+ * ranks then all-reduce 11 + 3 C floats per Gaussian instead of 59, and bds_sh_expand_bwd rebuilds v_features_dc [N,3]
+ * and v_features_rest [N,K-1,3] (fully WRITTEN) from the reduced v_sh_color. */
+int bds_project_bwd_compact_sh(const bds_render_desc* d, const float* means, const float* quats, const float* scales,
+                               const float* opacities, const float* viewmats, const float* Ks, const float* splats,
+                               const int32_t* counters, const float* v_splats, float* v_means, float* v_quats,
+                               float* v_scales, float* v_opacities, float* v_sh_color, float* v_viewmats,
+                               bds_stream_t stream);
+int bds_sh_expand_bwd(const bds_render_desc* d, const float* means, const float* viewmats, const float* v_sh_color,
+                      float* v_features_dc, float* v_features_rest, bds_stream_t stream);
 
 /* Companion of bds_project_bwd for the optional dense extras only: a Gaussian that gsplat calls visible
  * (radii > 0) but whose alpha >= 1/255 footprint misses every tile of the band owns no splat record here

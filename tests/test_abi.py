@@ -6,7 +6,7 @@ import re
 def test_library_loads_and_exports_all_symbols():
     from bilateral_driving_b200 import _lib
 
-    assert _lib.lib.bds_abi_version() == _lib.ABI_VERSION == 4
+    assert _lib.lib.bds_abi_version() == _lib.ABI_VERSION == 5
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     header = open(os.path.join(root, "include", "bds.h")).read()
     declared = set(re.findall(r"\b(bds_[a-z0-9_]+)\s*\(", header))

@@ -24,7 +24,7 @@ def _inputs():
     return p, vm, Ks, W, H, grids, sky
 
 
-def _run(rank, world, group):
+def _run(rank, world, group, mode="splats"):
     from bilateral_driving_b200.dist import allreduce_grads, band_for_rank
     from bilateral_driving_b200.render import render_fused
 
@@ -35,7 +35,7 @@ def _run(rank, world, group):
     c_g = [g.cuda().requires_grad_(True) for g in grids]
     out = render_fused(c_p, vm.cuda(), Ks.cuda(), W, H, sky=None, grid_slots=[[g[c] for g in c_g] for c in range(Cn)],
                        bil_sizes=SIZES, near_plane=0.1, row_begin=rb, row_end=re, dense_info=False,
-                       exchange_group=group)
+                       exchange_group=group, exchange_mode=mode)
     r0, r1 = out["pixel_rows"]
     gen = torch.Generator().manual_seed(4)
     G = torch.randn(Cn * H, W, 3, generator=gen).cuda()
@@ -54,23 +54,26 @@ def _free_port():
     return port
 
 
-def _worker(rank, world, port, ret):
+def _worker(rank, world, port, ret, mode):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     torch.cuda.set_device(0)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        ret[rank] = _run(rank, world, True)
+        ret[rank] = _run(rank, world, True, mode)
     finally:
         dist.destroy_process_group()
 
 
-def test_exchange_of_splat_records_gives_every_rank_the_full_gradient():
+@pytest.mark.parametrize("mode", ["splats", "compact"])
+def test_exchange_of_splat_records_gives_every_rank_the_full_gradient(mode):
+    """mode "splats": all-gather of the per-splat records; mode "compact": all-reduce with the SH gradient as one colour
+    cotangent per (camera, Gaussian) + bds_sh_expand_bwd."""
     full_p, full_g = _run(0, 1, None)
     world = 2
     mgr = mp.Manager()
     ret = mgr.dict()
-    mp.spawn(_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), ret, mode), nprocs=world, join=True)
     for r in range(world):
         part_p, part_g = ret[r]
         for k in full_p:
