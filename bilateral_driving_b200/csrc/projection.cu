@@ -723,46 +723,53 @@ extern "C" int bds_project_bwd_compact_sh(const bds_render_desc* d, const float*
 }
 
 // v_features_dc / v_features_rest of every Gaussian from the compact per-(camera, Gaussian) colour cotangents:
-// sum over cameras of basis(view direction) (x) v_sh_color.  One thread per Gaussian, the 3 K sums in registers, one
-// plain write per coefficient (no atomics).
-__global__ void __launch_bounds__(256) sh_expand_bwd_kernel(bds_render_desc d, const float* __restrict__ means,
-                                                            const float* __restrict__ viewmats,
-                                                            const float* __restrict__ v_sh_color,
-                                                            float* __restrict__ v_fdc, float* __restrict__ v_frest) {
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= d.n_gauss) return;
-  const float mu[3] = {means[3 * (size_t)n], means[3 * (size_t)n + 1], means[3 * (size_t)n + 2]};
+// sum over cameras of basis(view direction) (x) v_sh_color.  One thread per Gaussian builds the 3 K sums in registers;
+// the block's rows are contiguous in v_features_rest, so they go through shared memory and leave as coalesced stores.
+constexpr int kShExpBlock = 128;
+__global__ void __launch_bounds__(kShExpBlock) sh_expand_bwd_kernel(bds_render_desc d, const float* __restrict__ means,
+                                                                   const float* __restrict__ viewmats,
+                                                                   const float* __restrict__ v_sh_color,
+                                                                   float* __restrict__ v_fdc, float* __restrict__ v_frest) {
+  __shared__ float s_out[kShExpBlock * 49];   // [thread][48] padded to 49 (conflict-free row writes)
+  const int n0 = blockIdx.x * kShExpBlock;
+  const int n = n0 + threadIdx.x;
   float acc[48];
 #pragma unroll
   for (int k = 0; k < 48; ++k) acc[k] = 0.f;
-  int nb = (d.sh_degree + 1) * (d.sh_degree + 1);
-  if (nb > d.sh_K) nb = d.sh_K;
-  for (int c = 0; c < d.n_cams; ++c) {
-    const float* vc = v_sh_color + 3 * ((size_t)c * d.n_gauss + n);
-    const float v0 = vc[0], v1 = vc[1], v2 = vc[2];
-    if (v0 == 0.f && v1 == 0.f && v2 == 0.f) continue;
-    const float* V = viewmats + 16 * c;   // camera position = -R^T t
-    const float cx = -(V[0] * V[3] + V[4] * V[7] + V[8] * V[11]);
-    const float cy = -(V[1] * V[3] + V[5] * V[7] + V[9] * V[11]);
-    const float cz = -(V[2] * V[3] + V[6] * V[7] + V[10] * V[11]);
-    const float dx = mu[0] - cx, dy = mu[1] - cy, dz = mu[2] - cz;
-    const float inv = rsqrtf(dx * dx + dy * dy + dz * dz);
-    float b[16];
-    sh_basis(d.sh_degree, dx * inv, dy * inv, dz * inv, b);
+  if (n < d.n_gauss) {
+    const float mu[3] = {means[3 * (size_t)n], means[3 * (size_t)n + 1], means[3 * (size_t)n + 2]};
+    for (int c = 0; c < d.n_cams; ++c) {
+      const float* vc = v_sh_color + 3 * ((size_t)c * d.n_gauss + n);
+      const float v0 = vc[0], v1 = vc[1], v2 = vc[2];
+      if (v0 == 0.f && v1 == 0.f && v2 == 0.f) continue;
+      const float* V = viewmats + 16 * c;   // camera position = -R^T t
+      const float cx = -(V[0] * V[3] + V[4] * V[7] + V[8] * V[11]);
+      const float cy = -(V[1] * V[3] + V[5] * V[7] + V[9] * V[11]);
+      const float cz = -(V[2] * V[3] + V[6] * V[7] + V[10] * V[11]);
+      const float dx = mu[0] - cx, dy = mu[1] - cy, dz = mu[2] - cz;
+      const float inv = rsqrtf(dx * dx + dy * dy + dz * dz);
+      float b[16];
 #pragma unroll
-    for (int k = 0; k < 16; ++k) {
-      if (k < nb) {
+      for (int k = 0; k < 16; ++k) b[k] = 0.f;     // bands above the active degree contribute nothing
+      sh_basis(d.sh_degree, dx * inv, dy * inv, dz * inv, b);
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
         acc[3 * k] = fmaf(b[k], v0, acc[3 * k]);
         acc[3 * k + 1] = fmaf(b[k], v1, acc[3 * k + 1]);
         acc[3 * k + 2] = fmaf(b[k], v2, acc[3 * k + 2]);
       }
     }
   }
-  v_fdc[3 * (size_t)n] = acc[0]; v_fdc[3 * (size_t)n + 1] = acc[1]; v_fdc[3 * (size_t)n + 2] = acc[2];
-  float* fr = v_frest + (size_t)n * (d.sh_K - 1) * 3;
 #pragma unroll
-  for (int k = 1; k < 16; ++k) {
-    if (k < d.sh_K) { fr[3 * (k - 1)] = acc[3 * k]; fr[3 * (k - 1) + 1] = acc[3 * k + 1]; fr[3 * (k - 1) + 2] = acc[3 * k + 2]; }
+  for (int k = 0; k < 48; ++k) s_out[threadIdx.x * 49 + k] = acc[k];
+  __syncthreads();
+  const int rows = min(kShExpBlock, d.n_gauss - n0);
+  const int K = d.sh_K;
+  for (int i = threadIdx.x; i < rows * 3; i += kShExpBlock) v_fdc[(size_t)n0 * 3 + i] = s_out[(i / 3) * 49 + (i % 3)];
+  const int per = (K - 1) * 3;   // floats of one row of v_features_rest
+  for (int i = threadIdx.x; i < rows * per; i += kShExpBlock) {
+    const int r = i / per, k = i - r * per;
+    v_frest[(size_t)n0 * per + i] = s_out[r * 49 + 3 + k];
   }
 }
 
@@ -774,7 +781,7 @@ extern "C" int bds_sh_expand_bwd(const bds_render_desc* d, const float* means, c
   BDS_REQUIRE(d->sh_degree >= 0 && d->sh_K >= 1 && d->sh_K <= 16, "sh_expand_bwd: needs the SH fast path, K <= 16");
   BDS_REQUIRE(means && viewmats && v_sh_color && v_features_dc && (v_features_rest || d->sh_K == 1),
               "sh_expand_bwd: null pointer");
-  sh_expand_bwd_kernel<<<ceil_div(d->n_gauss, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  sh_expand_bwd_kernel<<<ceil_div(d->n_gauss, kShExpBlock), kShExpBlock, 0, static_cast<cudaStream_t>(stream)>>>(
       *d, means, viewmats, v_sh_color, v_features_dc, v_features_rest);
   BDS_CHECK_LAUNCH();
   return 0;
