@@ -210,10 +210,12 @@ BDS_D void level_grad_accumulate(float* smem, const Tri& t, const float vAff[12]
 //      zero); two xor-shuffles fold the four rows;
 //   3. the 3x4 sum of every corner node leaves as three 128-bit vector reductions (red.global.add.v4.f32): 72 per
 //      warp and level in the common case instead of 96 scalar ones per PIXEL and level.
+// Entry of pixel (row q, column m) sits at index 9 q + m: the four rows are read at the same m by the four lane groups,
+// and a row stride of 9 entries puts them in different shared-memory banks.
 struct WarpPanel {
-  float4 x1[32];      // {x_r, x_g, x_b, 1}: level input of the pixel
-  float4 g[32];       // {g_r, g_g, g_b, -}: cotangent of the level output
-  float w[32][8];     // corner weights, index = (slab << 2) | (y << 1) | x
+  float4 x1[36];      // {x_r, x_g, x_b, 1}: level input of the pixel
+  float4 g[36];       // {g_r, g_g, g_b, -}: cotangent of the level output
+  float w[36][8];     // corner weights, index = (slab << 2) | (y << 1) | x
 };
 constexpr size_t kPanelBytes = 8 * sizeof(WarpPanel);                                  // 8 warps
 
@@ -227,9 +229,10 @@ BDS_D void warp_level_accumulate(WarpPanel* pn, const Tri& t, bool valid, float 
     const float wx0 = 1.f - t.wx1, wy0 = 1.f - t.wy1;
     const float wz0 = sv * (1.f - t.wz1), wz1 = t.dz != 0 ? sv * t.wz1 : 0.f;
     const float w00 = wx0 * wy0, w01 = t.wx1 * wy0, w10 = wx0 * t.wy1, w11 = t.wx1 * t.wy1;
-    pn->x1[lane] = valid ? make_float4(x0, x1, x2, 1.f) : make_float4(0.f, 0.f, 0.f, 0.f);
-    pn->g[lane] = valid ? make_float4(g0, g1, g2, 0.f) : make_float4(0.f, 0.f, 0.f, 0.f);
-    float4* wp = reinterpret_cast<float4*>(pn->w[lane]);
+    const int slot = lane + (lane >> 3);
+    pn->x1[slot] = valid ? make_float4(x0, x1, x2, 1.f) : make_float4(0.f, 0.f, 0.f, 0.f);
+    pn->g[slot] = valid ? make_float4(g0, g1, g2, 0.f) : make_float4(0.f, 0.f, 0.f, 0.f);
+    float4* wp = reinterpret_cast<float4*>(pn->w[slot]);
     wp[0] = make_float4(w00 * wz0, w01 * wz0, w10 * wz0, w11 * wz0);
     wp[1] = make_float4(w00 * wz1, w01 * wz1, w10 * wz1, w11 * wz1);
   }
@@ -237,9 +240,9 @@ BDS_D void warp_level_accumulate(WarpPanel* pn, const Tri& t, bool valid, float 
   unsigned leaders = __ballot_sync(kFull, valid && lane == __ffs(grp) - 1);
   __syncwarp();
   const int c = lane & 7, q = lane >> 3;               // corner node of the cell, pixel row of the 8x4 rectangle
-  const float* wf = &pn->w[8 * q][0] + c;
-  const float4* gq = pn->g + 8 * q;
-  const float4* x1q = pn->x1 + 8 * q;
+  const float* wf = &pn->w[9 * q][0] + c;
+  const float4* gq = pn->g + 9 * q;
+  const float4* x1q = pn->x1 + 9 * q;
   while (leaders) {             // uniform: one cell per round
     const int l = __ffs(leaders) - 1;
     leaders &= leaders - 1;
