@@ -112,13 +112,17 @@ __global__ void __launch_bounds__(256) apply_fwd_kernel(const float* __restrict_
 //                                 cotangents of the tile are staged in shared memory and every low-res
 //                                 pixel of the tile's footprint GATHERS its transposed-bilinear sum
 //                                 (one global reduction per (low-res pixel, channel) per tile instead of
-//                                 48 per pixel); full-res levels use level_grad_accumulate.
-//   lowres_slice_bwd_tiled_kernel low-res tile: grid-node gradients through level_grad_accumulate,
+//                                 48 per pixel); full-res levels use warp_level_accumulate12.
+//   lowres_slice_bwd_tiled_kernel low-res tile: grid-node gradients through warp_level_accumulate12,
 //                                 guidance gradient through the transposed down-sample (12 reductions
 //                                 per low-res pixel).
 // ---------------------------------------------------------------------------------------------
 constexpr int kMaxFoot = 18;  // low-res rows/cols a 16-pixel tile edge can touch (factor >= 2 -> <= 10)
+// shared memory of a tile: the cotangent stage + row sums of the transposed up-sample, or the eight per-warp panels
+constexpr size_t kBwdSmemBil = (256 * 12 + 16 * kMaxFoot * 12) * sizeof(float) > 8 * sizeof(WarpPanel12)
+                                   ? (256 * 12 + 16 * kMaxFoot * 12) * sizeof(float) : 8 * sizeof(WarpPanel12);
 static_assert((256 * 12 + 16 * kMaxFoot * 12) * sizeof(float) <= kBwdSmemBil, "cotangent stage + row sums must fit the tile's shared memory");
+static_assert(8 * sizeof(WarpPanel12) <= kBwdSmemBil, "per-warp panels must fit the tile's shared memory");
 
 __global__ void __launch_bounds__(256) apply_bwd_tiled_kernel(const float* __restrict__ rgb_in,
                                                               const float* __restrict__ v_rgb_out,
@@ -170,6 +174,7 @@ __global__ void __launch_bounds__(256) apply_bwd_tiled_kernel(const float* __res
       gr = nr; gg = ng; gb = nb;
       if (lv.factor > 1) {
         // ---- transposed bilinear up-sample as a gather over the tile's low-res footprint
+        __syncthreads();    // a full-resolution level before this one may still be reading its per-warp panels
         float* sva = smem;  // [256][12]
         {
           float4* sp = reinterpret_cast<float4*>(sva + threadIdx.x * 12);
@@ -250,7 +255,9 @@ __global__ void __launch_bounds__(256) apply_bwd_tiled_kernel(const float* __res
           for (int k = 0; k < 12; ++k) s = fmaf(vA[k], dAdz[k], s);
           v_lum += s * (float)(lv.L - 1);
         }
-        level_grad_accumulate(smem, t, vA, inside, lin01(tile_x0, ch.W), lin01(tile_y0, ch.H), lv.L, lv.GY, lv.GX, lv.v_grid_cl);
+        // per-warp reduction straight to global memory (no block barrier, bilateral_accum.cuh)
+        warp_level_accumulate12(reinterpret_cast<WarpPanel12*>(smem) + (threadIdx.x >> 5), t, inside, vA, lv.L, lv.GY, lv.GX,
+                                lv.v_grid_cl);
       }
     }
   }
@@ -303,7 +310,8 @@ __global__ void __launch_bounds__(256) lowres_slice_bwd_tiled_kernel(const float
       red_add(p11 + c, h1 * w1 * v);
     }
   }
-  level_grad_accumulate(smem, t, vA, inside, lin01(tile_x0, lv.Wd), lin01(tile_y0, lv.Hd), lv.L, lv.GY, lv.GX, lv.v_grid_cl);
+  warp_level_accumulate12(reinterpret_cast<WarpPanel12*>(smem) + (threadIdx.x >> 5), t, inside, vA, lv.L, lv.GY, lv.GX,
+                          lv.v_grid_cl);
 }
 
 // generic per-sample slice on the channel-first parameter layout (BilateralGrid.forward) ----------
