@@ -1,6 +1,6 @@
 #!/bin/bash
 # One GPU-box visit: parity tests, smoke, bench (with the per-phase breakdown), optional walk statistics.
-# Usage (from the repo root on the box):  bash scripts/gpu_check.sh [stats] [ncu]
+# Usage (from the repo root on the box):  bash scripts/gpu_check.sh [lowres] [ncu] [ncufull]
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv > gpurun_out/gpu.txt 2>&1
 timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest.log 2>&1; echo "pytest rc=$?" | tee -a gpurun_out/pytest.log
@@ -11,9 +11,6 @@ for a in "$@"; do
   if [ "$a" = "lowres" ]; then
     timeout 600 python bench.py --guidance lowres --no-cpu-baseline --breakdown > gpurun_out/bench_n1_lowres.json 2> gpurun_out/bench_n1_lowres.err
     grep "phase ms" gpurun_out/bench_n1_lowres.err; python -c "import json;d=json.load(open('gpurun_out/bench_n1_lowres.json'));print('lowres ms/step',d['ms_per_step'])"
-  fi
-  if [ "$a" = "stats" ]; then
-    timeout 600 python scripts/walk_stats.py > gpurun_out/walk_stats.json 2> gpurun_out/walk_stats.err; tail -n 1 gpurun_out/walk_stats.json
   fi
   if [ "$a" = "ncu" ]; then
     timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv \
