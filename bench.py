@@ -361,12 +361,18 @@ def main():
             torch.cuda.current_stream().wait_event(gt_ready)
         loss = render.photometric_loss(out["rgb"], gt, out["depth"], out["opacity"], LAMBDA_D, LAMBDA_A, count=total_px,
                                        unit_cotangent=True)
-        if rank == 0:  # TV over all image slots (all levels in one launch): computed once per job, not per band
-            loss = loss + total_variation_loss_levels(
-                grids, [TV_W * 0.5 * (sx * sy * sl) ** 0.5 for sx, sy, sl in sizes])
+        # TV over all image slots (all levels in one launch).  It does not depend on the band: with the compact
+        # exchange (grid gradients reduced inside the render backward) every rank adds it itself, otherwise rank 0
+        # alone does and the all-reduce below spreads it
+        tv_everywhere = world > 1 and args.grad_exchange == "compact"
+        if rank == 0 or tv_everywhere:
+            tv = total_variation_loss_levels(grids, [TV_W * 0.5 * (sx * sy * sl) ** 0.5 for sx, sy, sl in sizes])
+            loss = loss + tv
         loss.backward()
         with render._timed("allreduce"):
-            if out["info"].get("grads_are_global"):   # the Gaussian gradients are already the job's: grids only
+            if out["info"].get("grids_are_global"):    # everything was reduced inside the render backward
+                pass
+            elif out["info"].get("grads_are_global"):  # the Gaussian gradients are already the job's: grids only
                 allreduce_grads([t.grad for t in grids])
             else:
                 allreduce_grads([t.grad for t in leaves], flat=out["info"].get("grad_flat"))

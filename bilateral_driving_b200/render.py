@@ -279,7 +279,16 @@ class _RenderFn(torch.autograd.Function):
         v_sky = torch.empty_like(sky) if (sky is not None and need[12]) else None
         v_bg = torch.zeros_like(backgrounds) if (backgrounds is not None and need[11]) else None
         # all grid-slot gradients are carved out of ONE zero-filled buffer (one fill instead of C x levels)
-        g_flat = torch.zeros(sum(g.numel() for g in grids if g is not None), **f32)
+        n_grid = sum(g.numel() for g in grids if g is not None)
+        compact = ctx.exchange is not None and cfg.exchange_mode == "compact"
+        if compact:
+            # ONE buffer for everything the ranks exchange: [Gaussian part (filled by _backward_compact) | grid slots]
+            n_gauss_part = N * 10 + opacities.numel() + Cn * N * 3
+            big = torch.zeros(n_gauss_part + n_grid, **f32)
+            g_flat = big[n_gauss_part:]
+        else:
+            big = None
+            g_flat = torch.zeros(n_grid, **f32)
         v_grids, g_off = [], 0
         for g in grids:
             v_grids.append(None if g is None else g_flat[g_off:g_off + g.numel()].view(g.shape))
@@ -296,7 +305,7 @@ class _RenderFn(torch.autograd.Function):
         # multi-GPU step all-reduces it in place: dist.allreduce_grads)
         if ctx.exchange is not None and cfg.exchange_mode == "compact":
             return _RenderFn._backward_compact(ctx, means, quats, scales, opacities, fdc, frest, viewmats, Ks, splats,
-                                               counters, v_splats, need, v_bg, v_sky, v_grids, st)
+                                               counters, v_splats, need, v_bg, v_sky, v_grids, st, big)
         parts = [("means", means), ("quats", quats), ("scales", scales), ("opac", opacities)]
         if colors is not None:
             parts.append(("colors", colors))
@@ -364,7 +373,7 @@ class _RenderFn(torch.autograd.Function):
 
 
 def _backward_compact(ctx, means, quats, scales, opacities, fdc, frest, viewmats, Ks, splats, counters, v_splats, need,
-                      v_bg, v_sky, v_grids, st):
+                      v_bg, v_sky, v_grids, st, flat):
     """Tail of ``_RenderFn.backward`` for ``exchange_mode="compact"``: projection backward with the SH gradient as one
     colour cotangent per (camera, Gaussian), ONE all-reduce of [means | quats | scales | opacities | that] over the
     exchange group, then the expansion to ``_features_dc`` / ``_features_rest``.  The gradients returned are the job's."""
@@ -376,8 +385,7 @@ def _backward_compact(ctx, means, quats, scales, opacities, fdc, frest, viewmats
     f32 = dict(device=dev, dtype=torch.float32)
     sizes = [("means", (N, 3)), ("quats", (N, 4)), ("scales", (N, 3)), ("opac", tuple(opacities.shape)), ("shc", (Cn, N, 3))]
     numel = [int(torch.Size(sh).numel()) for _, sh in sizes]
-    flat = torch.zeros(sum(numel), **f32)
-    views, off = {}, 0
+    views, off = {}, 0      # `flat` = [this Gaussian part | the grid-slot gradients composite_bwd has already written]
     for (name, sh), n_el in zip(sizes, numel):
         views[name] = flat[off:off + n_el].view(sh)
         off += n_el
@@ -389,7 +397,11 @@ def _backward_compact(ctx, means, quats, scales, opacities, fdc, frest, viewmats
                                              ptr(views["shc"]), ptr(v_view), st), "bds_project_bwd_compact_sh")
     grp = ctx.exchange[0]
     with _timed("exchange"):
-        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=grp)
+        # pieces of at most 256 MB: NCCL's in-switch reduction (NVLS) was measured slower per byte on a single 928 MB
+        # message (8 M Gaussians) than on 232 MB ones
+        piece = 64 * 1024 * 1024
+        for o in range(0, flat.numel(), piece):
+            dist.all_reduce(flat[o:o + piece], op=dist.ReduceOp.SUM, group=grp)
         if v_view is not None:
             dist.all_reduce(v_view, op=dist.ReduceOp.SUM, group=grp)
     v_fdc, v_frest = torch.empty_like(fdc), torch.empty_like(frest)
@@ -397,6 +409,7 @@ def _backward_compact(ctx, means, quats, scales, opacities, fdc, frest, viewmats
         check(lib.bds_sh_expand_bwd(C.byref(d), ptr(means), ptr(viewmats), ptr(views["shc"]), ptr(v_fdc), ptr(v_frest), st),
               "bds_sh_expand_bwd")
     ctx.holder["grads_are_global"] = True
+    ctx.holder["grids_are_global"] = True     # the grid-slot gradients rode in the same all-reduce
     ctx.holder["v_splats"] = v_splats
     return (None, None, views["means"], views["quats"], views["scales"], views["opac"], None, v_fdc, v_frest, v_view, None,
             v_bg, v_sky, *v_grids)

@@ -42,7 +42,8 @@ def _run(rank, world, group, mode="splats"):
     ((out["rgb"] * G[r0:r1]).sum() + 0.1 * out["depth"].sum()).backward()
     if world > 1:
         assert out["info"].get("grads_are_global")
-        allreduce_grads([g.grad for g in c_g], group=None)
+        if not out["info"].get("grids_are_global"):   # "compact" reduces the grid-slot gradients in the same all-reduce
+            allreduce_grads([g.grad for g in c_g], group=None)
     return {k: v.grad.cpu() for k, v in c_p.items()}, [g.grad.cpu() for g in c_g]
 
 
