@@ -69,6 +69,9 @@ def parse():
                          "NVLS in-switch reduction, 1.2 ms at 8 GPUs); splats = all-gather the per-splat gradient records "
                          "and run the projection backward over all of them on every rank (less data, but the uneven "
                          "all-gather measured slower: 3.89 vs 3.04 ms/step at 8 GPUs, profiles/r02_bench_n8_*.json)")
+    ap.add_argument("--bands", default="balanced", choices=["balanced", "equal"],
+                    help="N > 1: balanced = band boundaries chosen so that every rank gets about the same work (records of "
+                         "an untimed probe render + a per-tile constant); equal = the same number of tile rows per rank")
     ap.add_argument("--guidance", default="full", choices=["full", "lowres"],
                     help="full: guidance_factor=None fused in the composite kernel (headline); lowres: the reference's "
                          "default [4,4,2] = composite mode 1 + stand-alone low-res bilateral kernels")
@@ -317,7 +320,8 @@ def main():
 
     from bilateral_driving_b200 import _lib, render, synthetic as S
     from bilateral_driving_b200.bilateral import total_variation_loss_levels
-    from bilateral_driving_b200.dist import allreduce_grads, band_for_rank, band_pixel_rows, cameras_in_band
+    from bilateral_driving_b200.dist import (allreduce_grads, balanced_bands, band_for_rank, band_pixel_rows,
+                                             cameras_in_band)
 
     N, Cn, W, H = args.n_gauss, args.cams, args.width, args.height
     sizes = S.GRID_SIZES_BASELINE
@@ -325,6 +329,26 @@ def main():
     vm, Ks = S.make_rig(Cn, W, H)
     grids_cpu = S.make_grids(Cn, sizes)
     rb, re = band_for_rank(rank, world, Cn, H)
+    band_note = "equal tile-row counts"
+    if world > 1 and args.bands == "balanced" and args.guidance == "full":
+        # untimed probe: records per tile row of an equal split -> band boundaries of about equal work.  (A trainer
+        # gets these counts for free from the previous step.)  Cost model from the N=1 breakdown: a tile costs about
+        # as much as 146 records (per-pixel epilogues and the bilateral chain against the per-record walk).
+        tw_, th_ = (W + 15) // 16, (H + 15) // 16
+        with torch.no_grad():
+            probe = render.render_fused({k: v.to(dev) for k, v in p_cpu.items()}, vm.to(dev), Ks.to(dev), W, H, sky=None,
+                                        grid_slots=None, sh_degree=3, near_plane=0.1, row_begin=rb, row_end=re,
+                                        dense_info=False)
+        offs = probe["info"]["tile_offsets"].long()
+        per_row = (offs[1:] - offs[:-1]).view(re - rb, tw_).sum(1).float() + 146.0 * tw_
+        weights = torch.zeros(Cn * th_, device=dev)
+        weights[rb:re] = per_row
+        dist.all_reduce(weights)
+        # + about 1 M records' worth per camera a band touches: projection and emission run once per camera of the band
+        rb, re = balanced_bands(weights.tolist(), world, rows_per_camera=th_, camera_cost=1.0e6)[rank]
+        band_note = "tile-row bands of equal estimated work (records + 146 per tile + 1e6 per camera touched)"
+        del probe
+        torch.cuda.empty_cache()
     r0, r1 = band_pixel_rows(rb, re, Cn, H)
     cams = cameras_in_band(rb, re, H)
     rows = r1 - r0
@@ -474,7 +498,7 @@ def main():
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": _workload_name(N, Cn, W, H, args.guidance, world),
                    "gsplat": "not installed on the B200 box (profiles/r02_gsplat_probe.txt): no GPU reference comparator",
-                   "parallelism": f"tile-row bands x{world}" + ("" if world == 1 else f", gradient exchange: {args.grad_exchange}"),
+                   "parallelism": f"tile-row bands x{world}" + ("" if world == 1 else f" ({band_note}), gradient exchange: {args.grad_exchange}"),
                    "n_isect_rank0": I, "n_visible_rank0": Nv,
                    "l2": "inputs larger than L2 (472 MB of parameters + images per step)",
                    "composite_fwd_ms": t_fwd, "composite_bwd_ms": t_bwd},

@@ -19,6 +19,55 @@ def band_for_rank(rank: int, world: int, n_cams: int, height: int) -> Tuple[int,
     return (total * rank) // world, (total * (rank + 1)) // world
 
 
+def balanced_bands(row_weights: Sequence[float], world: int, rows_per_camera: Optional[int] = None,
+                   camera_cost: float = 0.0) -> List[Tuple[int, int]]:
+    """Contiguous bands of the global tile rows with about equal COST instead of equal row counts.  The work of a
+    tile row is far from uniform (rows at the horizon of a driving scene hold most of the records), and with equal row
+    counts every step waits for the heaviest band at the gradient exchange.  ``row_weights[i]`` = cost estimate of
+    global tile row i (e.g. records of the previous step + a per-tile constant); a band additionally pays
+    ``camera_cost`` for every camera it touches (projection and emission run once per camera of the band), cameras
+    being runs of ``rows_per_camera`` rows.  Min-max partition (binary search on the largest band cost, greedy
+    fill); returns ``world`` bands ``[begin, end)`` that partition the rows, every band non-empty when there are at
+    least ``world`` rows."""
+    n = len(row_weights)
+    w = [max(float(x), 0.0) for x in row_weights]
+    world = max(1, min(world, n)) if n else world
+
+    def cams(b, e):
+        if not rows_per_camera or e <= b:
+            return 0
+        return (e - 1) // rows_per_camera - b // rows_per_camera + 1
+
+    def fill(limit):
+        """Greedy: longest bands whose cost stays <= limit, keeping one row for every band still to come."""
+        cuts, b = [0], 0
+        for r in range(world):
+            e, acc = b, 0.0
+            last = n - (world - 1 - r)               # rows this band may take at most
+            while e < last:
+                nxt = acc + w[e] + camera_cost * (cams(b, e + 1) - cams(b, e))
+                if e > b and nxt > limit:
+                    break
+                acc, e = nxt, e + 1
+            cuts.append(e)
+            b = e
+        return cuts
+
+    lo = max(w) if w else 0.0
+    hi = sum(w) + camera_cost * (cams(0, n) + world) + 1.0
+    for _ in range(60):
+        mid = 0.5 * (lo + hi)
+        if fill(mid)[-1] >= n:
+            hi = mid
+        else:
+            lo = mid
+    cuts = fill(hi)
+    cuts[-1] = n
+    for r in range(world - 1, 0, -1):                # degenerate weights: keep every band non-empty
+        cuts[r] = min(cuts[r], cuts[r + 1] - 1)
+    return [(cuts[r], cuts[r + 1]) for r in range(world)]
+
+
 def band_pixel_rows(rb: int, re: int, n_cams: int, height: int) -> Tuple[int, int]:
     tile_h = (height + TILE - 1) // TILE
 

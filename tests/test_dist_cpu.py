@@ -8,7 +8,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from bilateral_driving_b200.dist import allreduce_grads, band_for_rank, band_pixel_rows, cameras_in_band
+from bilateral_driving_b200.dist import allreduce_grads, balanced_bands, band_for_rank, band_pixel_rows, cameras_in_band
 
 
 def test_bands_partition_the_rig():
@@ -106,3 +106,33 @@ def test_splat_record_exchange_gathers_uneven_pieces():
         counts, total, out = ret[r]
         assert counts == [5, 0, 3] and total == 8 and out.shape == (8, 12)
         assert torch.allclose(out[:5, 0], 0.0 + torch.arange(5) * 0.01) and torch.allclose(out[5:, 0], 2.0 + torch.arange(3) * 0.01)
+
+
+def test_balanced_bands_partition_rows_by_weight():
+    """dist.balanced_bands: contiguous, exhaustive, non-empty bands whose weights are far closer to each other than an
+    equal row split when the rows are not uniform (horizon-heavy driving scenes)."""
+    import math
+
+    rows = 6 * 68
+    w = [100.0 + 5000.0 * math.exp(-(((i % 68) - 34) / 6.0) ** 2) for i in range(rows)]   # heavy rows at the horizon
+    for world in (2, 3, 4, 8):
+        bands = balanced_bands(w, world)
+        assert bands[0][0] == 0 and bands[-1][1] == rows
+        assert all(b[0] < b[1] for b in bands) and all(a[1] == b[0] for a, b in zip(bands[:-1], bands[1:]))
+        sums = [sum(w[b[0]:b[1]]) for b in bands]
+        equal = [sum(w[rows * r // world:rows * (r + 1) // world]) for r in range(world)]
+        assert max(sums) <= max(equal) + 1e-6
+        assert max(sums) / (sum(w) / world) < 1.15
+    assert balanced_bands([1.0] * 3, 3) == [(0, 1), (1, 2), (2, 3)]
+    z = balanced_bands([0.0] * 8, 4)
+    assert z[0][0] == 0 and z[-1][1] == 8 and all(b[0] < b[1] for b in z)
+    # a per-camera cost: 8 bands over 6 cameras of 68 rows - bands that straddle a camera boundary get fewer rows
+    flat = [1000.0] * rows
+    plain = balanced_bands(flat, 8)
+    costly = balanced_bands(flat, 8, rows_per_camera=68, camera_cost=30000.0)
+    assert costly[0][0] == 0 and costly[-1][1] == rows and all(a[1] == b[0] for a, b in zip(costly[:-1], costly[1:]))
+
+    def cost(b):
+        return sum(flat[b[0]:b[1]]) + 30000.0 * ((b[1] - 1) // 68 - b[0] // 68 + 1)
+
+    assert max(cost(b) for b in costly) < max(cost(b) for b in plain)
