@@ -112,6 +112,24 @@ BDS_D f32x2 sub2(f32x2 a, f32x2 b) {
   return d;
 }
 
+// index of the highest set bit (FLO.U32); x != 0
+BDS_D int bfind_u32(unsigned x) {
+  int r;
+  asm("bfind.u32 %0, %1;" : "=r"(r) : "r"(x));
+  return r;
+}
+
+// 1u << pos (BMSK: no constant register needed); pos in [0, 31]
+BDS_D unsigned bit_mask(int pos) {
+  unsigned r;
+  asm("bmsk.clamp.b32 %0, %1, 1;" : "=r"(r) : "r"(pos));
+  return r;
+}
+// 32-bit shared-window address of a shared-memory pointer, and back
+BDS_D uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+template <typename T>
+BDS_D const T* smem_ptr(uint32_t a) { return reinterpret_cast<const T*>(__cvta_shared_to_generic((size_t)a)); }
+
 // fire-and-forget fp32 reduction into global memory (RED.ADD.F32)
 BDS_D void red_add(float* p, float v) { atomicAdd(p, v); }
 // four consecutive floats, 16-byte aligned, in one reduction (RED.E.ADD.F32x4)

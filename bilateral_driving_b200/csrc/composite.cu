@@ -260,18 +260,24 @@ __global__ void __launch_bounds__(kFwdThreads, BDS_FWD_MINB) composite_fwd_kerne
           // a masked-out splat is a splat of opacity 0: it fails the alpha >= 1/255 test on every pixel
           if (p.slot_keep && hit) hit = p.slot_keep[__float_as_int(r2.z)] != 0;
         }
-        unsigned m = __ballot_sync(kFull, hit);
+        // walked front to back: the mask is bit-reversed so that "highest set bit" (one FLO) is the first record;
+        // bit fb <-> record base + 31 - fb
+        unsigned m = __brev(__ballot_sync(kFull, hit));
+        const uint32_t top_addr = smem_addr(sr + (base + 31) * 3);
+        const int top_idx = idx0 + base + 31;
         while (m) {
-          const int jj = base + __ffs(m) - 1;
-          m &= m - 1;
-          const float4 r0 = sr[jj * 3], r1 = sr[jj * 3 + 1], r2 = sr[jj * 3 + 2];
+          const int fb = bfind_u32(m);
+          m ^= bit_mask(fb);
+          const float4* rp = smem_ptr<float4>(top_addr - (uint32_t)fb * kRecBytes);
+          const float4 r0 = rp[0], r1 = rp[1], r2 = rp[2];
           // e = log2(opacity) - sigma', sigma' = a' dx^2 + b' dx dy + c' dy^2  (alpha = 2^e); dx is shared by the
-          // lane's two pixels, everything in dy runs packed
-          const float dx = r0.x - pxf;
-          const float adx = r0.z * dx;
+          // lane's two pixels, everything in dy runs packed.  ndx = -dx exactly, so the bits are those of the
+          // backward's scalar form
+          const float ndx = pxf - r0.x;
+          const float adx = r0.z * -ndx;
           const f32x2 dy2 = sub2(pk2(r0.y, r0.y), pyf2);
           const f32x2 t2 = fma2(pk2(r0.w, r0.w), dy2, pk2(adx, adx));
-          f32x2 e2 = fma2(pk2(-dx, -dx), t2, pk2(r2.w, r2.w));
+          f32x2 e2 = fma2(pk2(ndx, ndx), t2, pk2(r2.w, r2.w));
           e2 = fma2(mul2(pk2(-r1.x, -r1.x), dy2), dy2, e2);
           float e0, e1;
           upk2(e2, e0, e1);
@@ -292,8 +298,8 @@ __global__ void __launch_bounds__(kFwdThreads, BDS_FWD_MINB) composite_fwd_kerne
           fma2_acc(cb2, vis2, pk2(r2.x, r2.x));
           fma2_acc(cd2, vis2, pk2(r2.y, r2.y));
           T2 = pk2(go0 ? nT0 : T0, go1 ? nT1 : T1);
-          last0 = go0 ? idx0 + jj : last0;
-          last1 = go1 ? idx0 + jj : last1;
+          last0 = go0 ? top_idx - fb : last0;
+          last1 = go1 ? top_idx - fb : last1;
           emin0 = (ok0 && !go0) ? INFINITY : emin0;
           emin1 = (ok1 && !go1) ? INFINITY : emin1;
         }
@@ -364,8 +370,7 @@ constexpr int kPanelStride = 33;       // float2 per record row: 32 pixels + 1 p
 
 struct BatchSmem {                     // per warp
   float2 panel[kBatch * kPanelStride]; // {w, fac}
-  float4 meta0[kBatch];                // record {x, y, a', b'}
-  float2 meta1[kBatch];                // record {c', bits(slot)}
+  float4 carry[kBatch * 3];            // records still pending when their TMA stage was released (whole 48-byte records)
   float4 vc[32];                       // per-pixel cotangent of the raw accumulators (C_r, C_g, C_b, D)
 };
 
@@ -375,25 +380,31 @@ BDS_D float rcp_approx(float x) {
   return r;
 }
 
-// rx0, ry0: centre of the warp rectangle's first pixel; nb: pending records (warp-uniform)
-BDS_D void flush_batch(const BatchSmem* bs, int nb, float rx0, float ry0, float* __restrict__ v_splats) {
+// rx0, ry0: centre of the warp rectangle's first pixel; nb: pending records (warp-uniform); rec_addr: lane i < nb
+// holds the shared-window address of the record pending in panel row i - inside a TMA stage that is still held,
+// or inside the warp's carry area
+BDS_D void flush_batch(const BatchSmem* bs, int nb, float rx0, float ry0, float* __restrict__ v_splats,
+                       uint32_t rec_addr) {
   __syncwarp();
   const int lane = threadIdx.x & 31;
   const int rec = lane & (kBatch - 1), part = lane / kBatch;
   const float2* row = bs->panel + rec * kPanelStride + part * kPartPix;
   const float4* vcp = bs->vc + part * kPartPix;
-  const float4 q0 = bs->meta0[rec];
-  const float2 q1 = bs->meta1[rec];
+  const float4* rp = smem_ptr<float4>(__shfl_sync(kFull, rec_addr, rec));
+  const float4 q0 = rp[0];                                         // record {x, y, a', b'}
+  const float q1x = reinterpret_cast<const float*>(rp)[4];         // c'
+  const int q1slot = reinterpret_cast<const int*>(rp)[10];         // bits(slot)
   const float X = q0.x - rx0, Y = q0.y - ry0;          // mean relative to pixel (u, v) = (0, 0)
-  const float A2 = 2.f * q0.z, B = q0.w, C2 = 2.f * q1.x;
+  const float A2 = 2.f * q0.z, B = q0.w, C2 = 2.f * q1x;
   float m0 = 0.f, mu = 0.f, mv = 0.f, muu = 0.f, muv = 0.f, mvv = 0.f;
   float ax = 0.f, ay = 0.f;
   f32x2 c01 = pk2(0.f, 0.f), c23 = c01;   // colour sums as packed fp32x2 (FFMA2)
+  const f32x2 gstep = pk2(-A2, -B);       // d(g_x, g_y) / du
 #pragma unroll
   for (int r = 0; r < kPartPix / 8; ++r) {
     const float v = (float)(part * (kPartPix / 8) + r);
     const float dy = Y - v;
-    const float gxr = fmaf(A2, X, B * dy), gyr = fmaf(B, X, C2 * dy);   // g at u = 0
+    f32x2 g2 = pk2(fmaf(A2, X, B * dy), fmaf(B, X, C2 * dy));   // (g_x, g_y) at u = 0, stepped along the row
     float s0 = 0.f, s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
@@ -405,9 +416,11 @@ BDS_D void flush_batch(const BatchSmem* bs, int nb, float rx0, float ry0, float*
       const f32x2 fac2 = pk2(d.y, d.y);
       fma2_acc(c01, fac2, pk2(c.x, c.y));
       fma2_acc(c23, fac2, pk2(c.z, c.w));
-      const float gx = fmaf(-A2, (float)u, gxr), gy = fmaf(-B, (float)u, gyr);
-      ax += fabsf(d.x * gx);
-      ay += fabsf(d.x * gy);
+      float wgx, wgy;
+      upk2(mul2(pk2(d.x, d.x), g2), wgx, wgy);
+      ax += fabsf(wgx);
+      ay += fabsf(wgy);
+      if (u < 7) g2 = add2(g2, gstep);
     }
     m0 += s0; mu += s1; muu += s2;
     mv = fmaf(v, s0, mv); muv = fmaf(v, s1, muv); mvv = fmaf(v * v, s0, mvv);
@@ -428,7 +441,7 @@ BDS_D void flush_batch(const BatchSmem* bs, int nb, float rx0, float ry0, float*
     const float mxx = fmaf(X, mx - mu, muu);
     const float mxy = fmaf(X, my, fmaf(-Y, mu, muv));
     const float myy = fmaf(Y, my - mv, mvv);
-    float* dst = v_splats + (size_t)__float_as_int(q1.y) * 12;
+    float* dst = v_splats + (size_t)q1slot * 12;
     if (kParts >= 3) {          // one 128-bit reduction per lane
       if (part == 0) red_add_v4(dst, mx, my, mxx, mxy);
       else if (part == 1) red_add_v4(dst + 4, myy, m0, c0, c1);
@@ -637,8 +650,15 @@ __global__ void __launch_bounds__(256, BDS_BWD_MINB) composite_bwd_kernel(CompPa
   float T = Tfin;
   float bufdot = -Tfin * (vA - bg_dot);
   if (!g.inside) last = -1;   // pixels outside the image never match a record
+  // deferred-reduction bookkeeping, all in registers: lane i holds in rec_addr the shared-window address of the
+  // record pending in panel row i (no per-record metadata stores)
+  float2* const pw0 = bs->panel + lane;
+  float2* pw = pw0;           // this lane's cell of the next free panel row
   int nb = 0;                 // records pending in this warp's panel (warp-uniform)
-  float2* pw = bs->panel + lane;   // this lane's cell of the next panel row
+  uint32_t rec_addr = smem_addr(dyn_smem);   // always a readable address, also in lanes >= nb
+  const uint32_t stages_end = smem_addr(dyn_smem) + (uint32_t)kBwdSmemRec;
+  const f32x2 pxy2 = pk2(pxf, pyf);
+  const f32x2 vC01 = pk2(vC[0], vC[1]), vC23 = pk2(vC[2], vC[3]);
 
   for (int q = 0; q < nchunks; ++q) {
     const int st = q % kBStages;
@@ -658,41 +678,51 @@ __global__ void __launch_bounds__(256, BDS_BWD_MINB) composite_bwd_kernel(CompPa
           hit = !(s > r2.w + (kLog2_255 + kCullMargin));
         }
         unsigned m = __ballot_sync(kFull, hit);
+        const uint32_t group_addr = smem_addr(sr + base * 3);
+        const int last_rel = last - chunk0 - base;   // this pixel takes bit <= last_rel of the group
         while (m) {
-          const int bit = 31 - __clz(m);
-          m &= ~(1u << bit);
-          const int jj = base + bit;
-          const float4 r0 = sr[jj * 3], r1 = sr[jj * 3 + 1], r2 = sr[jj * 3 + 2];
-          const float dx = r0.x - pxf, dy = r0.y - pyf;
+          const int bit = bfind_u32(m);              // from the back: highest record first
+          m ^= bit_mask(bit);
+          const uint32_t raddr = group_addr + (uint32_t)bit * kRecBytes;
+          const float4* rp = smem_ptr<float4>(raddr);
+          const float4 r0 = rp[0], r1 = rp[1], r2 = rp[2];
+          float dx, dy;
+          upk2(sub2(pk2(r0.x, r0.y), pxy2), dx, dy);
           // e = log2(opacity) - sigma', sigma' = a' dx^2 + b' dx dy + c' dy^2  (alpha = 2^e)
           float e = fmaf(-dx, fmaf(r0.w, dy, r0.z * dx), r2.w);
           e = fmaf(-(r1.x * dy), dy, e);
-          const bool valid = chunk0 + jj <= last && e <= r2.w && e >= -kLog2_255;
+          const bool valid = (bit <= last_rel) & (e >= -kLog2_255) & (r2.w >= e);
           if (!__any_sync(kFull, valid)) continue;
-          float w = 0.f, fac = 0.f;
-          if (valid) {
-            const float araw = exp2f(e);                 // opacity * exp(-sigma)
-            const float alpha = fminf(kAlphaMax, araw);
-            const float ra = rcp_approx(1.f - alpha);
-            T *= ra;                                     // transmittance in front of this record
-            fac = alpha * T;
-            const float cdot = fmaf(r1.z, vC[0], fmaf(r1.w, vC[1], fmaf(r2.x, vC[2], r2.y * vC[3])));
-            const float v_alpha = fmaf(T, cdot, -ra * bufdot);
-            bufdot = fmaf(fac, cdot, bufdot);
-            w = araw <= kAlphaMax ? araw * v_alpha : 0.f;  // the clamp at 0.999 blocks the gradient
-          }
+          // branch-free: a lane that does not take the record runs the same arithmetic with alpha = 0, which
+          // leaves T and bufdot unchanged (rcp(1) = 1, 0 * finite = 0) and stores w = fac = 0
+          const float araw = valid ? exp2f(e) : 0.f;   // opacity * exp(-sigma)
+          const float alpha = fminf(kAlphaMax, araw);
+          const float ra = rcp_approx(1.f - alpha);
+          T *= ra;                                     // transmittance in front of this record
+          const float fac = alpha * T;
+          float cd0, cd1;                              // <colour, v_C>, two channels per lane of the packed ops
+          upk2(fma2(pk2(r2.x, r2.y), vC23, mul2(pk2(r1.z, r1.w), vC01)), cd0, cd1);
+          const float cdot = cd0 + cd1;
+          const float v_alpha = fmaf(T, cdot, -ra * bufdot);
+          bufdot = fmaf(fac, cdot, bufdot);
+          const float w = araw <= kAlphaMax ? araw * v_alpha : 0.f;  // the clamp at 0.999 blocks the gradient
           *pw = make_float2(w, fac);
+          rec_addr = nb == (int)lane_id() ? raddr : rec_addr;
           pw += kPanelStride;
-          if (lane == 0) {
-            bs->meta0[nb] = r0;
-            bs->meta1[nb] = make_float2(r1.x, r2.z);
-          }
           if (++nb == kBatch) {
-            flush_batch(bs, kBatch, rxmin, rymin, p.v_splats);
+            flush_batch(bs, kBatch, rxmin, rymin, p.v_splats, rec_addr);
             nb = 0;
-            pw = bs->panel + lane;
+            pw = pw0;
           }
         }
+      }
+      // the stage is about to be released: records of it that are still pending move to the warp's carry area
+      if (lane < nb && rec_addr < stages_end) {
+        const float4* src = smem_ptr<float4>(rec_addr);
+        float4* dst = bs->carry + lane * 3;
+        const float4 c0 = src[0], c1 = src[1], c2 = src[2];
+        dst[0] = c0; dst[1] = c1; dst[2] = c2;
+        rec_addr = smem_addr(dst);
       }
     }
     // consumer release: the warp is done with stage st.  No block barrier - the other warps run ahead by up to
@@ -708,7 +738,7 @@ __global__ void __launch_bounds__(256, BDS_BWD_MINB) composite_bwd_kernel(CompPa
       bulk_g2s(&srec[st][0], p.recs + (size_t)(g.start + kk * kChunk) * 3, c2 * kRecBytes, &bars[st]);
     }
   }
-  if (nb > 0) flush_batch(bs, nb, rxmin, rymin, p.v_splats);
+  if (nb > 0) flush_batch(bs, nb, rxmin, rymin, p.v_splats, rec_addr);
   // v_backgrounds: sum over pixels of T_final * v (MODE 0)
   if (MODE == 0 && p.v_backgrounds) {
     for (int c = 0; c < p.channels; ++c) {
