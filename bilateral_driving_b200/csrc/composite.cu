@@ -810,6 +810,11 @@ static CompWorkspace carve_comp(const bds_render_desc* d, const bds_epilogue_des
 
 int check_render_desc(const bds_render_desc* d);
 
+// does camera c own a tile row of the band [row_begin, row_end) (global tile rows, tile_h per camera)?
+static bool cam_in_band(const bds_render_desc* d, int tile_h, int c) {
+  return d->row_begin < (c + 1) * tile_h && d->row_end > c * tile_h;
+}
+
 static int fill_common(CompParams& p, const bds_render_desc* d, const bds_epilogue_desc* e) {
   BDS_REQUIRE(e && e->mode >= 0 && e->mode <= 2, "composite: epilogue mode must be 0, 1 or 2");
   if (e->mode == 0) BDS_REQUIRE(e->channels == 3 || e->channels == 4, "composite: channels must be 3 or 4");
@@ -917,6 +922,8 @@ static int composite_fwd_impl(const bds_render_desc* d, const bds_epilogue_desc*
       p.bil.L[l] = e->bil.L[l]; p.bil.GY[l] = e->bil.GY[l]; p.bil.GX[l] = e->bil.GX[l];
       for (int c = 0; c < d->n_cams; ++c) {
         const float* src = host_grids[c * e->bil.n_levels + l];
+        // a camera whose tile rows meet the band runs the chain on every pixel: its repack must not be skipped
+        BDS_REQUIRE(src || !cam_in_band(d, p.tile_h, c), "composite_fwd: null grid slot for a camera inside the band");
         if (!src) continue;  // camera outside the band
         jobs.src[jobs.n] = src; jobs.dst[jobs.n] = base + (size_t)c * nodes * 12;
         jobs.L[jobs.n] = e->bil.L[l]; jobs.GY[jobs.n] = e->bil.GY[l]; jobs.GX[jobs.n] = e->bil.GX[l];
@@ -975,6 +982,7 @@ extern "C" int bds_composite_bwd(const bds_render_desc* d, const bds_epilogue_de
       p.bil.L[l] = e->bil.L[l]; p.bil.GY[l] = e->bil.GY[l]; p.bil.GX[l] = e->bil.GX[l];
       for (int c = 0; c < d->n_cams; ++c) {
         const float* src = host_grids[c * e->bil.n_levels + l];
+        BDS_REQUIRE(src || !cam_in_band(d, p.tile_h, c), "composite_bwd: null grid slot for a camera inside the band");
         if (!src) continue;
         jobs.src[jobs.n] = src; jobs.dst[jobs.n] = base + (size_t)c * nodes * 12;
         jobs.L[jobs.n] = e->bil.L[l]; jobs.GY[jobs.n] = e->bil.GY[l]; jobs.GX[jobs.n] = e->bil.GX[l];

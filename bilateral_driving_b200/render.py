@@ -122,6 +122,26 @@ def band_pixel_rows(cfg: RenderCfg, Cn: int) -> Tuple[int, int]:
     return row_of(rb), (row_of(re) if re < Cn * th else Cn * cfg.height)
 
 
+def check_grid_slots(cfg: RenderCfg, Cn: int, grids: Sequence[Optional[torch.Tensor]]) -> None:
+    """Mode 2 runs the bilateral chain on every pixel of every camera that owns a tile row of the band, so such a
+    camera needs all its grid slots; ``None`` is only meaningful for cameras outside the band (multi-GPU bands).
+    ``grids`` = camera-major flat list ``[c * n_levels + l]``."""
+    if cfg.mode != 2:
+        return
+    n_levels = len(cfg.bil_sizes)
+    if len(grids) != Cn * n_levels:
+        raise ValueError(f"expected {Cn} x {n_levels} grid slots, got {len(grids)}")
+    _, th = cfg.tiles()
+    rb = cfg.row_begin
+    re = Cn * th if cfg.row_end < 0 else cfg.row_end
+    for c in range(Cn):
+        if rb < (c + 1) * th and re > c * th:
+            missing = [l for l in range(n_levels) if grids[c * n_levels + l] is None]
+            if missing:
+                raise ValueError(f"camera {c} lies inside the band [{rb}, {re}) of tile rows but has no grid slot for "
+                                 f"level(s) {missing}; use mode 1 (grid_slots=None) for a glue-only render")
+
+
 _PINNED = {}
 
 
@@ -154,6 +174,7 @@ class _RenderFn(torch.autograd.Function):
             cont, (means, quats, scales, opacities, colors, fdc, frest, viewmats, Ks, backgrounds, sky))
         grids = [None if g is None else g.contiguous().float() for g in grids]
         N, Cn = means.shape[0], viewmats.shape[0]
+        check_grid_slots(cfg, Cn, grids)
         sh_K = 0
         if cfg.sh_degree >= 0:
             sh_K = 1 + (0 if frest is None else frest.shape[1])
@@ -610,7 +631,8 @@ def render_fused(params: Dict[str, torch.Tensor], viewmats, Ks, width: int, heig
     ``params``: ``_means [N,3], _scales (log) [N,3], _quats [N,4], _opacities (logit) [N] or [N,1],
     _features_dc [N,3], _features_rest [N,K-1,3]`` (``activated=True``: scales/opacities already
     activated and ``_rgbs [N,3]`` given instead of SH features).
-    ``grid_slots[c][l]`` = camera c's grid slot ``[12,L,GY,GX]`` of level l, or None (reference glue only).
+    ``grid_slots[c][l]`` = camera c's grid slot ``[12,L,GY,GX]`` of level l; ``grid_slots[c]`` may be None only for a
+    camera outside the band (``grid_slots=None`` altogether = reference glue only, mode 1).
     ``guidance_factor=None``: full-resolution guidance, the bilateral chain runs INSIDE the composite kernel
     (epilogue mode 2).  ``guidance_factor=[4,4,2]`` (the reference's default, modules.py:505): the composite
     kernel stops after the glue (mode 1) and the low-resolution-guidance kernels of ``bilateral.py`` finish the

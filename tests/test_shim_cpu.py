@@ -28,3 +28,29 @@ def test_gsplat_shim_exposes_the_reference_import_paths():
     code = PROBE.format(shim=os.path.join(ROOT, "shim"), root=ROOT)
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and out.stdout.strip().endswith("ok"), out.stderr[-2000:]
+
+
+def test_grid_slots_of_cameras_inside_the_band_are_required():
+    """Mode 2 runs the bilateral chain for every camera that owns a tile row of the band: a None slot there would read
+    an uninitialised workspace (round-1 advisor finding) and is refused; None stays legal outside the band."""
+    import pytest
+    import torch
+
+    sys.path.insert(0, ROOT)
+    from bilateral_driving_b200.render import RenderCfg, check_grid_slots
+
+    sizes = ((2, 2, 1), (4, 4, 2), (8, 8, 4))
+    slot = [torch.zeros(12, 1, 2, 2), torch.zeros(12, 2, 4, 4), torch.zeros(12, 4, 8, 8)]
+    full = RenderCfg(width=64, height=48, mode=2, bil_sizes=sizes)                    # 3 tile rows per camera
+    check_grid_slots(full, 2, slot + slot)
+    with pytest.raises(ValueError, match="camera 1"):
+        check_grid_slots(full, 2, slot + [None] * 3)
+    with pytest.raises(ValueError, match="level"):
+        check_grid_slots(full, 2, slot + [slot[0], None, slot[2]])
+    band = RenderCfg(width=64, height=48, mode=2, bil_sizes=sizes, row_begin=0, row_end=3)   # camera 0 only
+    check_grid_slots(band, 2, slot + [None] * 3)
+    with pytest.raises(ValueError, match="camera 0"):
+        check_grid_slots(band, 2, [None] * 3 + slot)
+    check_grid_slots(RenderCfg(width=64, height=48, mode=1), 2, [])                   # glue only: nothing to check
+    with pytest.raises(ValueError, match="expected"):
+        check_grid_slots(full, 2, slot)
