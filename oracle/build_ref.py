@@ -46,6 +46,8 @@ FILES = [
     "utils/__init__.py",
     "utils/misc.py",
     "utils/geometry.py",
+    "models/video_utils.py",      # the eval harness (render_images / render), tests/test_trainer_reference.py
+    "utils/visualization.py",
 ]
 
 

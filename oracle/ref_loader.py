@@ -69,6 +69,13 @@ def load_reference_trainers(gsplat_pkg_dir=None):
     return importlib.import_module("models.trainers.scene_graph")
 
 
+def load_reference_eval(gsplat_pkg_dir=None):
+    """Returns the reference's ``models.video_utils`` module (``render_images`` / ``render``, the eval harness of
+    ``tools/eval.py`` and ``tools/train.py``)."""
+    load_reference_trainers(gsplat_pkg_dir)
+    return importlib.import_module("models.video_utils")
+
+
 def reference_apply_chain(rgb, affine_list):
     """Restates scene_graph.py:112-117 verbatim in meaning: sequential 3x4 apply."""
     x = rgb

@@ -118,11 +118,45 @@ class _PSNR(nn.Module):
 
 
 class _LPIPS(nn.Module):
+    """NOT LPIPS (the network weights are not available offline): a deterministic stand-in (mean absolute difference)
+    so that the reference's eval harness (models/video_utils.py:271-275) can be driven end to end."""
+
     def __init__(self, **_k):
         super().__init__()
 
-    def forward(self, *_a):  # pragma: no cover
-        _not_available()
+    def forward(self, a, b):
+        return (a - b).abs().mean()
+
+
+# ---- skimage.metrics.structural_similarity (models/video_utils.py:11, 264-345) -----------------------------------------
+def structural_similarity(im1, im2, *, data_range=None, channel_axis=None, full=False, win_size=7, **_k):
+    """scikit-image's default SSIM restated (Wang et al. 2004 as implemented by skimage 0.2x): 7x7 uniform window,
+    K1 = 0.01, K2 = 0.03, sample covariance (N / (N - 1)), mean over the map cropped by (win_size - 1) // 2 on each
+    side, channels averaged.  ``full=True`` also returns the per-pixel map ([H, W, C] for multichannel input)."""
+    import numpy as np
+    from scipy.ndimage import uniform_filter
+
+    if channel_axis is not None:
+        im1, im2 = np.moveaxis(im1, channel_axis, -1), np.moveaxis(im2, channel_axis, -1)
+        res = [structural_similarity(im1[..., c], im2[..., c], data_range=data_range, full=True, win_size=win_size)
+               for c in range(im1.shape[-1])]
+        mssim = float(np.mean([r[0] for r in res]))
+        return (mssim, np.stack([r[1] for r in res], -1)) if full else mssim
+    x, y = im1.astype(np.float64), im2.astype(np.float64)
+    NP = win_size ** x.ndim
+    cov_norm = NP / (NP - 1)
+    f = lambda a: uniform_filter(a, size=win_size)  # noqa: E731
+    ux, uy = f(x), f(y)
+    vx, vy, vxy = cov_norm * (f(x * x) - ux * ux), cov_norm * (f(y * y) - uy * uy), cov_norm * (f(x * y) - ux * uy)
+    C1, C2 = (0.01 * data_range) ** 2, (0.03 * data_range) ** 2
+    S = ((2 * ux * uy + C1) * (2 * vxy + C2)) / ((ux ** 2 + uy ** 2 + C1) * (vx + vy + C2))
+    pad = (win_size - 1) // 2
+    mssim = float(S[tuple(slice(pad, -pad) for _ in range(x.ndim))].mean())
+    return (mssim, S) if full else mssim
+
+
+class _SplitWrapper:  # type annotation only in models/video_utils.py
+    pass
 
 
 class _DrivingDataset:  # type annotation only in models/trainers/scene_graph.py
@@ -150,3 +184,11 @@ def install():
     ds = _stub("datasets")
     ds.__path__ = []   # a package, so that "datasets.driving_dataset" resolves to the stub below
     ds.driving_dataset = _stub("datasets.driving_dataset", DrivingDataset=_DrivingDataset)
+    ds.base = _stub("datasets.base", SplitWrapper=_SplitWrapper)
+    # the eval harness (models/video_utils.py) and utils/visualization.py: video writing / colour maps are not exercised
+    _stub("imageio", mimwrite=_not_available, get_writer=_not_available)
+    _stub("cv2")
+    mpl = _stub("matplotlib")
+    mpl.cm = _stub("matplotlib.cm", get_cmap=_not_available)
+    sk = _stub("skimage")
+    sk.metrics = _stub("skimage.metrics", structural_similarity=structural_similarity)

@@ -209,3 +209,61 @@ def test_fused_trainer_on_gpu_against_reference_trainer(guidance):
     for key in ("rgb", "Background_rgb", "Background_opacity", "Dynamic_rgb", "Dynamic_opacity"):
         assert float(((e_fu[key] - e_ref[key].cuda()).abs() * keep_g).max()) < 2e-5, key
     assert launches < 40   # one pipeline + two masked composites, not three rasterizations
+
+
+class _EvalSplit:
+    """Stands in for datasets.base.SplitWrapper (split_wrapper.py:22-27): hands out (image_infos, cam_infos) per index."""
+    split = "test"
+
+    def __init__(self, n=2):
+        self.items = []
+        for i in range(n):
+            image_infos, cam_infos = TH.make_batch("cpu", img_idx=i, seed=20 + i)
+            image_infos.pop("lidar_depth_map")          # the lidar overlay needs cv2 / matplotlib colour maps
+            g = torch.Generator().manual_seed(40 + i)
+            H, W = image_infos["pixels"].shape[:2]
+            for k, frac in (("dynamic_masks", 0.2), ("human_masks", 0.05), ("vehicle_masks", 0.1)):
+                image_infos[k] = (torch.rand(H, W, generator=g) < frac).float()
+            cam_infos["cam_name"] = f"CAM_{i}"
+            cam_infos["cam_id"] = torch.full((H, W), i, dtype=torch.long)
+            self.items.append((image_infos, cam_infos))
+
+    def __len__(self):
+        return len(self.items)
+
+    def get_image(self, idx, camera_downscale):
+        assert camera_downscale == 1          # eval renders at full resolution (base.py:142-146)
+        image_infos, cam_infos = self.items[idx]
+        return dict(image_infos), dict(cam_infos)
+
+
+def test_eval_harness_runs_the_drop_in_trainer(monkeypatch):
+    """the reference's own eval harness (models/video_utils.py:47-620, render_images -> render, what
+    tools/eval.py and the end of tools/train.py call), unmodified, over the reference trainer and over the drop-in
+    trainer with the same parameters: same metrics, same per-frame arrays, same per-class renders.  skimage / lpips /
+    imageio are stand-ins (oracle/ref_stubs.py) applied to both arms; `.cuda()` is the identity on this CPU run."""
+    import numpy as np
+
+    from oracle.ref_loader import load_reference_eval
+    import os
+
+    _patch_cpu(monkeypatch)
+    ref = _reference_arm(0.5)
+    fused = _fused_arm(ref, "cpu", 0.5)
+    VU = load_reference_eval(os.path.join(TH.ROOT, "oracle", "gsplat_seam"))
+    monkeypatch.setattr(torch.Tensor, "cuda", lambda self, *a, **k: self)
+    data = _EvalSplit(2)
+    r_ref = VU.render_images(ref, data, compute_metrics=True, compute_error_map=True)
+    r_fu = VU.render_images(fused, data, compute_metrics=True, compute_error_map=True)
+    assert not ref.training and not fused.training
+    assert set(r_ref) == set(r_fu)
+    for k in ("psnr", "ssim", "lpips", "occupied_psnr", "occupied_ssim", "masked_psnr", "masked_ssim", "human_psnr",
+              "human_ssim", "vehicle_psnr", "vehicle_ssim"):
+        assert r_ref[k] != -1 and np.isfinite(r_ref[k]), k
+        assert abs(r_fu[k] - r_ref[k]) <= 1e-5 * max(1.0, abs(r_ref[k])), (k, r_fu[k], r_ref[k])
+    for k in ("rgbs", "depths", "opacities", "gt_rgbs", "rgb_error_maps", "rgb_sky_blend", "rgb_sky", "Background_rgbs",
+              "Background_depths", "Background_opacities"):
+        assert k in r_fu and len(r_fu[k]) == len(r_ref[k]) == 2, k
+        for a, b in zip(r_fu[k], r_ref[k]):
+            assert a.shape == b.shape and float(np.abs(a - b).max()) <= 1e-5 * max(1.0, float(np.abs(b).max())), k
+    assert r_fu["cam_names"] == r_ref["cam_names"] == ["CAM_0", "CAM_1"]
