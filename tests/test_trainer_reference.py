@@ -267,3 +267,57 @@ def test_eval_harness_runs_the_drop_in_trainer(monkeypatch):
         for a, b in zip(r_fu[k], r_ref[k]):
             assert a.shape == b.shape and float(np.abs(a - b).max()) <= 1e-5 * max(1.0, float(np.abs(b).max())), k
     assert r_fu["cam_names"] == r_ref["cam_names"] == ["CAM_0", "CAM_1"]
+
+
+def _train_iteration(tr, step, image_infos, cam_infos, fix_reference_bug=False):
+    """tools/train.py:252-284, one iteration of the reference's training loop."""
+    tr.set_train()
+    tr.preprocess_per_train_step(step=step)
+    tr.optimizer_zero_grad()
+    outputs = tr(image_infos, cam_infos)
+    tr.update_visibility_filter()
+    if fix_reference_bug:   # see _step
+        outputs["original_rgb"] = outputs["rgb_gaussians"] + outputs["rgb_sky"] * (1.0 - outputs["opacity"])
+    loss_dict = tr.compute_losses(outputs=outputs, image_infos=image_infos, cam_infos=cam_infos)
+    for k, v in loss_dict.items():
+        assert torch.isfinite(v).all(), (k, step)
+    tr.backward(loss_dict)                      # backward + optimizer step + lr schedule (base.py:502-516)
+    tr.postprocess_per_train_step(step=step)    # densification statistics; split / duplicate / cull every 100 steps
+    return {k: float(v.detach()) for k, v in loss_dict.items()}
+
+
+def test_training_loop_with_densification_matches_reference(monkeypatch):
+    """CPU: four iterations of the reference's loop (tools/train.py:252-284) over both trainers - optimizer built by
+    the reference's initialize_optimizer from each arm's param groups (Affine#grid{i} learning rates, base.py:182-208),
+    steps 3198..3201 so that step 3200 runs the reference's split / duplicate / cull surgery on the statistics the
+    taps of the drop-in fed it.  Same losses every step, same Gaussian count after the surgery, same parameters."""
+    _patch_cpu(monkeypatch)
+    ref = _reference_arm(0.5)
+    fused = _fused_arm(ref, "cpu", 0.5)
+    for tr in (ref, fused):
+        tr.initialize_optimizer()
+    names = lambda tr: sorted(g["name"] for g in tr.optimizer.param_groups)  # noqa: E731
+    assert names(ref) == names(fused) and any(n.startswith("Affine#grid") for n in names(fused))
+    lrs = lambda tr: {g["name"]: g["lr"] for g in tr.optimizer.param_groups}  # noqa: E731
+    n0 = ref.models["Background"].num_points
+    counts = []
+    for i, step in enumerate(range(3198, 3202)):
+        image_infos, cam_infos = TH.make_batch("cpu", img_idx=i % TH.N_IMAGES, seed=60 + i)
+        torch.manual_seed(1000 + step)
+        l_ref = _train_iteration(ref, step, image_infos, cam_infos, fix_reference_bug=True)
+        torch.manual_seed(1000 + step)
+        l_fu = _train_iteration(fused, step, image_infos, cam_infos)
+        assert set(l_ref) == set(l_fu) and "affine_loss" in l_fu
+        for k in l_ref:
+            assert abs(l_fu[k] - l_ref[k]) <= 1e-5 * max(1.0, abs(l_ref[k])), (step, k, l_fu[k], l_ref[k])
+        assert lrs(ref) == lrs(fused)
+        a, b = ref.models["Background"], fused.models["Background"]
+        assert a.num_points == b.num_points, step
+        counts.append(a.num_points)
+    assert counts[1] == n0 and counts[2] != n0, counts      # the surgery ran at step 3200 and changed the scene
+    pr, pf = TH.all_params(ref), TH.all_params(fused)
+    assert set(pr) == set(pf)
+    for name in pr:
+        assert pr[name].shape == pf[name].shape, name
+        scale = float(pr[name].abs().max().clamp(min=1e-12))
+        assert float((pf[name] - pr[name]).abs().max()) / scale < 1e-4, name
