@@ -321,3 +321,45 @@ def test_training_loop_with_densification_matches_reference(monkeypatch):
         assert pr[name].shape == pf[name].shape, name
         scale = float(pr[name].abs().max().clamp(min=1e-12))
         assert float((pf[name] - pr[name]).abs().max()) / scale < 1e-4, name
+
+
+def test_checkpoints_cross_load_between_reference_and_drop_in_trainer(monkeypatch, tmp_path):
+    """a checkpoint written by the reference trainer (base.py:739-752) resumes in the drop-in trainer
+    (base.py:727-737, strict) and the other way round, and the resumed trainer renders what the writer renders."""
+    import os
+
+    _patch_cpu(monkeypatch)
+    ref = _reference_arm(0.5)
+    fused = _fused_arm(ref, "cpu", 0.5)
+    image_infos, cam_infos = TH.make_batch("cpu")
+    # move both arms off their common initialisation, differently
+    g = torch.Generator().manual_seed(8)
+    for tr, amp in ((ref, 0.01), (fused, 0.02)):
+        for p in TH.all_params(tr).values():
+            p.data += amp * torch.randn(p.shape, generator=g)
+    (tmp_path / "ref").mkdir(); (tmp_path / "fused").mkdir()
+    ref.save_checkpoint(str(tmp_path / "ref"), is_final=True)
+    fused.save_checkpoint(str(tmp_path / "fused"), is_final=True)
+    ck_ref = torch.load(os.path.join(tmp_path, "ref", "checkpoint_final.pth"))
+    ck_fu = torch.load(os.path.join(tmp_path, "fused", "checkpoint_final.pth"))
+    assert set(ck_ref) == set(ck_fu)
+    for name in ck_ref["models"]:                    # same keys, same shapes: the checkpoint FORMAT is the reference's
+        a, b = ck_ref["models"][name], ck_fu["models"][name]
+        assert sorted(a) == sorted(b), name
+        assert all(a[k].shape == b[k].shape for k in a if torch.is_tensor(a[k])), name
+
+    def eval_render(tr):
+        tr.set_eval()
+        with torch.no_grad():
+            return tr(image_infos, cam_infos)
+
+    want_ref, want_fu = eval_render(ref), eval_render(fused)
+    ref2 = _reference_arm(0.5)
+    fused2 = _fused_arm(ref2, "cpu", 0.5)
+    ref2.resume_from_checkpoint(os.path.join(tmp_path, "fused", "checkpoint_final.pth"))   # drop-in -> reference
+    fused2.resume_from_checkpoint(os.path.join(tmp_path, "ref", "checkpoint_final.pth"))   # reference -> drop-in
+    assert ref2.step == fused.step and fused2.step == ref.step
+    got_ref2, got_fu2 = eval_render(ref2), eval_render(fused2)
+    for key in ("rgb", "depth", "opacity", "Background_rgb"):
+        assert float((got_ref2[key] - want_fu[key]).abs().max()) < 1e-6, key
+        assert float((got_fu2[key] - want_ref[key]).abs().max()) < 1e-6, key
