@@ -1,5 +1,6 @@
 // Fused front-to-back alpha compositing + reference glue + multi-scale bilateral chain, forward and
-// backward.  One CTA (256 threads = 8 warps x 8x4 pixels) per 16x16 tile of the band.
+// backward.  One CTA per 16x16 tile of the band: 128 threads = 4 warps x 8x8 pixels (two pixels per lane) in the
+// forward, 256 threads = 8 warps x 8x4 pixels in the backward.
 //
 // Replaces, in one launch each way (paths relative to /root/reference/project):
 //   gsplat rasterize_to_pixels_fwd/bwd          called via models/trainers/base.py:393-408
@@ -12,15 +13,17 @@
 //   * the tile's depth-sorted 48-byte splat records are contiguous in HBM (binning.cu) and are staged
 //     into shared memory with 1-D TMA bulk copies (cp.async.bulk ... mbarrier::complete_tx), 3 stages
 //     of 128 records, issued by one elected thread;
-//   * each warp tests 32 records at a time (one per lane) against its own 8x4 pixel rectangle with an
+//   * each warp tests 32 records at a time (one per lane) against its own pixel rectangle with an
 //     exact ellipse-vs-rectangle bound, ballots, and only walks the survivors - the blend itself reads
 //     records from shared memory as 128-bit broadcasts; transmittance lives in a register per pixel and
-//     a warp vote retires the warp when all its pixels are saturated;
+//     a warp vote retires the warp when all its pixels are saturated; stages are handed back with
+//     consumer-release mbarriers (no block barrier in either walk);
 //   * the backward re-walks the same records back to front (2 stages of 128 records) with one running scalar
 //     per pixel; the per-record reduction across the warp is DEFERRED: the walk stores two scalars per (pixel,
 //     record) into a per-warp shared panel and every 16 records the warp transposes the work (lane = record)
 //     and sums the panel into pixel moments in registers - no shuffle tree - that leave as three 128-bit vector
-//     reductions into a 48-byte-per-splat gradient record (see flush_batch);
+//     reductions into a 48-byte-per-splat gradient record (see flush_batch); the walk's bookkeeping is in
+//     registers (lane i remembers where the record of panel row i lies in shared memory);
 //   * FMA-dense parts (trilinear slice, colour sums) use packed fp32x2 FMAs (FFMA2);
 //   * no tensor cores: the work is gather / pointwise / scatter.
 #include <stdlib.h>
