@@ -85,6 +85,32 @@ def test_projection_forward_and_vjp(hc):
         assert np.abs(vview - ref_view).max() < 2e-3 * np.abs(ref_view).max()
 
 
+def test_projection_culls_radius_clip_and_far_plane(hc):
+    """The viewer path renders with radius_clip=4.0 (base.py:811-826) and the trainers pass a far plane: the device
+    projection math (compiled for the host) must cull exactly the Gaussians the oracle culls (radius <= radius_clip,
+    depth outside [near, far])."""
+    a, vm, Ks, W, H = _scene(n=600)
+    n = a["means"].shape[0]
+    a["scales"] = a["scales"].clone()
+    a["scales"][::3] *= 0.03                                          # every third Gaussian projects to 2-4 pixels
+    args = [np.ascontiguousarray(t.float().numpy()) for t in (a["means"], a["quats"], a["scales"], vm[0], Ks[0])]
+    base = R.project(a["means"].double(), a["quats"].double(), a["scales"].double(), vm[0].double(), Ks[0].double(), W, H,
+                     near_plane=0.1)
+    far = float(base["depths"][base["radii"] > 0].median())          # a far plane that cuts the scene in two
+    for clip, far_plane in ((4.0, 1e10), (0.0, far), (4.0, far)):
+        pr = R.project(a["means"].double(), a["quats"].double(), a["scales"].double(), vm[0].double(), Ks[0].double(),
+                       W, H, near_plane=0.1, far_plane=far_plane, radius_clip=clip)
+        out = np.zeros((n, 8), np.float32)
+        hc.hc_project(n, *map(fp, args), W, H, C.c_float(0.3), C.c_float(0.1), C.c_float(far_plane), C.c_float(clip),
+                      fp(out))
+        ours = torch.from_numpy(out[:, 6]).long()
+        near_far = (base["depths"] - far_plane).abs() < 1e-4 * far_plane          # depth within rounding of the plane
+        ok = (ours == pr["radii"]) | pr["ambiguous"] | base["ambiguous"] | near_far
+        assert bool(ok.all()), (clip, far_plane, int((~ok).sum()))
+        culled = int(((base["radii"] > 0) & (pr["radii"] == 0)).sum())
+        assert culled > 10, (clip, far_plane, culled)                             # the option does cull something here
+
+
 def test_projection_clamped_fov_branch(hc):
     # Gaussians far off-axis exercise the 1.3*tan(fov) clamp in J (appendix A.4)
     W, H = 64, 48
